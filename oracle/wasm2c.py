@@ -673,6 +673,9 @@ class FuncGen:
         assert not ctrl, "unbalanced control in f%d" % self.fidx
         # assemble
         hdr = [self.signature() + "{"]
+        if self.fidx in HOOKS:
+            hdr.append("if(w2c_hook_fn)w2c_hook_fn(%d,%s);" % (
+                self.fidx, ",".join(["(u64)l%d" % i for i in range(min(len(params), 4))] + ["0"] * (4 - min(len(params), 4)))))
         for i in range(len(params), len(ltypes)):
             hdr.append("%s l%d=0;" % (CT[ltypes[i]], i))
         for (d, t) in sorted(self.maxdepth):
@@ -730,6 +733,8 @@ def rettype(q):
     return "ret_" + "".join(SUF[t] for t in q)
 
 
+HOOKS = set(int(x) for x in os.environ.get("W2C_HOOKS", "").split(",") if x)
+
 RUNTIME_H = r'''
 #include <stdint.h>
 #include <string.h>
@@ -738,6 +743,7 @@ typedef uint32_t u32; typedef uint64_t u64; typedef float f32; typedef double f6
 extern uint8_t* mem; extern u32 mem_pages;
 u32 mem_grow(u32 delta);
 void* tbl_get(u32 idx);
+extern void (*w2c_hook_fn)(int fn, u64 a0, u64 a1, u64 a2, u64 a3);
 void wasm_trap(int fn) __attribute__((noreturn));
 #define TRAP(f) wasm_trap(f)
 static inline u32 clz32(u32 x){return x?__builtin_clz(x):32;}
@@ -769,6 +775,8 @@ RUNTIME_C = r'''
 #include <stdlib.h>
 #include <setjmp.h>
 #include <sys/mman.h>
+void (*w2c_hook_fn)(int,u64,u64,u64,u64);
+void w2c_set_hook(void (*f)(int,u64,u64,u64,u64)){w2c_hook_fn=f;}
 uint8_t* mem; u32 mem_pages; static u32 mem_max_pages = 65536;
 static jmp_buf trap_jmp; static int trap_armed; static char trap_msg[512];
 void wasm_trap(int fn){
