@@ -34,7 +34,7 @@ def _mix_chacha_statement(channel, log_size, pub):
         channel.mix_u64(struct.unpack_from("<I", pub, 16 + 4 * i)[0])
 
 
-def prove_stream_internal(log_size, key, nonce, counters, pt, ct, pub, config=None, debug=None):
+def prove_stream_internal(log_size, key, nonce, counters, pt, ct, pub, config=None, debug=None, n_input_rows=None):
     """air_stream.rs:160-234.  Inputs are per-row arrays (see chacha_air.generate_stream_trace)."""
     config = config or PcsConfig()
     if log_size < 4:
@@ -44,7 +44,7 @@ def prove_stream_internal(log_size, key, nonce, counters, pt, ct, pub, config=No
     channel = Blake2sChannel()
     scheme = CommitmentSchemeProver(config)
     scheme.commit_polys([], channel)                                   # empty preprocessed tree
-    trace, valid = ca.generate_stream_trace(log_size, key, nonce, counters, pt, ct)
+    trace, valid = ca.generate_stream_trace(log_size, key, nonce, counters, pt, ct, n_input_rows)
     if not valid:
         raise ProofError("Ciphertext does not match encryption - invalid witness")
     _mix_chacha_statement(channel, log_size, pub)
@@ -65,10 +65,42 @@ def prove_stream_internal(log_size, key, nonce, counters, pt, ct, pub, config=No
     proof, info = prove_values(scheme, sample_points, channel, eval_log)
     if debug is not None:
         debug.update(info, random_coeff_composition=random_coeff, oods=oods, acc=acc, scheme=scheme)
-    # sanity check of prove(): composition OODS value vs constraints at the OODS point is exercised by the
-    # verifier test; an unsatisfied AIR shows up as ProofError there.
+    # prove()'s closing sanity check (prover/mod.rs): composition value recombined from the sampled halves must
+    # equal the constraints evaluated on the sampled mask values, else ProvingError::ConstraintsNotSatisfied.
+    if not composition_oods_check(log_size, oods, info["sampled"], random_coeff):
+        raise ProofError("Proof generation failed: ConstraintsNotSatisfied")
     stmt = struct.pack("<I", log_size) + pub
     return stmt + proof
+
+
+def composition_oods_check(log_size, oods, sampled, random_coeff):
+    """Verifier-side identity (core/air/components.rs eval_composition_polynomial_at_point +
+    core/verifier.rs): left(z) + pi^{n-1}(z.x) * right(z) == sum_k alpha^(K-1-k) C_k(mask(z)) / Z_H(z)."""
+    from stwo_core import Coset, index_to_point
+    from prover import secure_powers
+    px, py = oods
+    mask = np.array([[cv[0].v] for cv in sampled[1]], dtype=U64)          # [C,1,4]
+    apr = secure_powers(random_coeff, ca.N_CONSTRAINTS)[::-1].copy()
+    num = ca.evaluate_constraints(mask, apr)[0]
+    num = QM31(*[int(v) for v in num])
+    # coset_vanishing(CanonicCoset(n).coset, z)
+    coset = Coset.odds(log_size)
+    t = index_to_point((-coset.initial_index + (coset.step_size >> 1)) & ((1 << 31) - 1))
+    x = px * t[0] - py * t[1]
+    for _ in range(1, log_size):
+        x = x * x * 2 - 1
+    lhs_expected = num * x.inv()
+    comp = sampled[2]
+    left = QM31(0); right = QM31(0)
+    units = [QM31(1), QM31(0, 1), QM31(0, 0, 1), QM31(0, 0, 0, 1)]
+    for c in range(4):
+        left = left + comp[c][0] * units[c]
+        right = right + comp[4 + c][0] * units[c]
+    # pi^{n-1}(z.x): x doubled (log_size - 1) times
+    pix = px
+    for _ in range(log_size - 1):
+        pix = pix * pix * 2 - 1
+    return left + pix * right == lhs_expected
 
 
 def build_chacha_inputs(key, nonce, counter, plaintext, ciphertext):
@@ -88,7 +120,7 @@ def build_chacha_inputs(key, nonce, counter, plaintext, ciphertext):
     CT[:num_blocks] = np.frombuffer(bytes(ciphertext), dtype="<u4").reshape(num_blocks, 16)
     for row in range(num_blocks, m):
         CT[row] = ca.chacha20_block_words(kw, (counter + row) & 0xFFFFFFFF, nw)
-    return log_size, K, NO, C, PT, CT
+    return log_size, K, NO, C, PT, CT, m
 
 
 def generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext, debug=None):
@@ -104,10 +136,10 @@ def generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext, debug=No
     num_blocks = len(plaintext) // 64
     if num_blocks > 1 and counter + num_blocks - 1 > 0xFFFFFFFF:
         return {"error": "Counter overflow: counter %d + %d blocks would exceed u32::MAX" % (counter, num_blocks)}
-    log_size, K, NO, C, PT, CT = build_chacha_inputs(key, nonce, counter, plaintext, ciphertext)
+    log_size, K, NO, C, PT, CT, m = build_chacha_inputs(key, nonce, counter, plaintext, ciphertext)
     pub = chacha_public_inputs(nonce, counter, plaintext, ciphertext)
     try:
-        proof = prove_stream_internal(log_size, K, NO, C, PT, CT, pub, debug=debug)
+        proof = prove_stream_internal(log_size, K, NO, C, PT, CT, pub, debug=debug, n_input_rows=m)
     except ProofError as e:
         return {"error": str(e)}
     return {"success": True, "blocks": num_blocks, "algorithm": "chacha20",

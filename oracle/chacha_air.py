@@ -58,8 +58,9 @@ def chacha20_keystream_bytes(key, nonce, counter, n_blocks):
 
 
 # ---------------------------------------------------------------- witness (gen_stream.rs)
-def generate_stream_trace(log_size, key, nonce, counters, plaintext, ciphertext):
-    """All arguments are per-row uint arrays: key[N,8], nonce[N,3], counters[N], plaintext[N,16], ciphertext[N,16]
+def generate_stream_trace(log_size, key, nonce, counters, plaintext, ciphertext, n_input_rows=None):
+    """n_input_rows: rows covered by caller-provided inputs; only those enter the validity flag
+    (gen_stream.rs:240-250 ignores the result for default rows).  All arguments are per-row uint arrays: key[N,8], nonce[N,3], counters[N], plaintext[N,16], ciphertext[N,16]
     (the reference splats key/nonce over the 16 lanes of a vec-row and zero-fills rows beyond the inputs,
     gen_stream.rs:237-250 -- callers build those arrays).  Returns (trace[N_COLS, N] uint64 bits, valid)."""
     n = 1 << log_size
@@ -109,7 +110,8 @@ def generate_stream_trace(log_size, key, nonce, counters, plaintext, ciphertext)
     valid = True
     for i in range(16):
         append_u32_bits(ct[:, i])
-        if np.any((ks[i] ^ pt[:, i]) != ct[:, i]):
+        m = n if n_input_rows is None else n_input_rows
+        if np.any((ks[i][:m] ^ pt[:m, i]) != ct[:m, i]):
             valid = False
     assert col[0] == N_COLS
     return trace, valid
@@ -119,29 +121,47 @@ def generate_stream_trace(log_size, key, nonce, counters, plaintext, ciphertext)
 class _Acc:
     """sum_k alpha^(K-1-k) * C_k(row): add_constraint semantics of the framework's domain evaluator."""
 
-    def __init__(self, n_rows, alpha_pows_rev):
+    def __init__(self, n_rows, alpha_pows_rev, ext):
         self.acc = np.zeros((n_rows, 4), dtype=U64)
         self.k = 0
         self.apr = alpha_pows_rev           # [K,4]: entry k = alpha^(K-1-k)
+        self.ext = ext
 
     def emit(self, cmat):
         m = cmat.shape[0]
         co = self.apr[self.k:self.k + m]                       # [m,4]
-        prod = (cmat[:, :, None] * co[:, None, :]) % U64(P)    # [m,R,4]
+        if self.ext:                                           # cmat [m,R,4] QM31 values
+            from stwo_core import q_mul
+            prod = q_mul(cmat, co[:, None, :])
+        else:                                                  # cmat [m,R] M31 values
+            prod = (cmat[:, :, None] * co[:, None, :]) % U64(P)
         self.acc = (self.acc + prod.sum(axis=0)) % U64(P)
         self.k += m
 
 
 def evaluate_constraints(lde, alpha_pows_rev):
-    """lde: [N_COLS, R] uint64 column values on the evaluation domain (any row order).
+    """lde: [N_COLS, R] uint64 M31 column values on the evaluation domain (any row order), or [N_COLS, R, 4]
+    QM31 values (the verifier / prove()'s sanity check evaluate the same constraints on the OODS mask values).
     Returns acc[R,4] = sum_k alpha_pows_rev[k] * C_k(row), before multiplication by the vanishing inverse."""
+    ext = lde.ndim == 3
     R = lde.shape[1]
-    A = _Acc(R, alpha_pows_rev)
+    A = _Acc(R, alpha_pows_rev, ext)
     col = [0]
-    one, two = U64(1), U64(2)
+    if ext:
+        from stwo_core import q_mul, q_add, q_sub
+        mul, add, sub = q_mul, q_add, q_sub
+        one = np.array([1, 0, 0, 0], dtype=U64)
+        two = np.array([2, 0, 0, 0], dtype=U64)
+        zrow = np.zeros((1, R, 4), dtype=U64)
+        cshape = (64, R, 4)
+    else:
+        mul, add, sub = m_mul, m_add, m_sub
+        one, two = U64(1), U64(2)
+        zrow = np.zeros((1, R), dtype=U64)
+        cshape = (64, R)
 
     def boolean(b):
-        return m_mul(b, m_sub(one, b))
+        return mul(b, sub(one, b))
 
     def next_u32():
         b = lde[col[0]:col[0] + 32]
@@ -153,11 +173,11 @@ def evaluate_constraints(lde, alpha_pows_rev):
         res = next_u32()
         car = lde[col[0]:col[0] + 32]
         col[0] += 32
-        cin = np.concatenate([np.zeros((1, R), dtype=U64), car[:-1]], axis=0)
-        cm = np.empty((64, R), dtype=U64)
+        cin = np.concatenate([zrow, car[:-1]], axis=0)
+        cm = np.empty(cshape, dtype=U64)
         cm[0::2] = boolean(car)
         # result + 2*carry - a - b - carry_in
-        cm[1::2] = m_sub(m_sub(m_sub(m_add(res, m_mul(two, car)), a), b), cin)
+        cm[1::2] = sub(sub(sub(add(res, mul(two, car)), a), b), cin)
         A.emit(cm)
         return res
 
@@ -165,7 +185,7 @@ def evaluate_constraints(lde, alpha_pows_rev):
         res = next_u32()
         src = (np.arange(32) + 32 - r) % 32
         sa, sb = a[src], b[src]
-        A.emit(m_add(m_sub(m_sub(res, sa), sb), m_mul(two, m_mul(sa, sb))))
+        A.emit(add(sub(sub(res, sa), sb), mul(two, mul(sa, sb))))
         return res
 
     init = [next_u32() for _ in range(16)]
@@ -180,7 +200,7 @@ def evaluate_constraints(lde, alpha_pows_rev):
     pt = [next_u32() for _ in range(16)]
     ct = [next_u32() for _ in range(16)]
     for i in range(16):
-        comp = m_sub(m_add(ks[i], pt[i]), m_mul(two, m_mul(ks[i], pt[i])))
-        A.emit(m_sub(comp, ct[i]))
+        comp = sub(add(ks[i], pt[i]), mul(two, mul(ks[i], pt[i])))
+        A.emit(sub(comp, ct[i]))
     assert col[0] == N_COLS and A.k == N_CONSTRAINTS
     return A.acc

@@ -292,9 +292,18 @@ def prove_values(scheme, sample_points_per_tree, channel, lifting_log):
     # sampled values
     sampled = []
     for tree, pts in zip(scheme.trees, sample_points_per_tree):
-        tv = []
-        for coeffs, plist in zip(tree.coeffs, pts):
-            tv.append([QM31(*[int(v) for v in eval_at_point(coeffs, px, py)]) for (px, py) in plist])
+        tv = [[None] * len(plist) for plist in pts]
+        # batch columns that share (size, point): one vectorised eval_at_point per group
+        groups = {}
+        for j, (coeffs, plist) in enumerate(zip(tree.coeffs, pts)):
+            for k, (px, py) in enumerate(plist):
+                groups.setdefault((len(coeffs), px.v, py.v), []).append((j, k, px, py))
+        for (_, _, _), members in groups.items():
+            px, py = members[0][2], members[0][3]
+            mat = np.stack([tree.coeffs[j] for (j, _, _, _) in members], axis=0)
+            res = eval_at_point(mat, px, py)
+            for (j, k, _, _), v in zip(members, res):
+                tv[j][k] = QM31(int(v[0]), int(v[1]), int(v[2]), int(v[3]))
         sampled.append(tv)
     flat = [v for tv in sampled for cv in tv for v in cv]
     channel.mix_felts(flat)
