@@ -1,0 +1,133 @@
+/* s2c_b200.h -- C ABI of the B200 (sm_100a) stwo prover backend for reclaimprotocol/zk-symmetric-crypto.
+ *
+ * Two layers, both plain C (pointers + sizes, int status, no C++/torch types):
+ *
+ *  (1) cb_*  : one entry point per backend-trait method the reference's prover reaches through upstream stwo's
+ *              `SimdBackend` (the generic parameter `B: BackendForChannel<MC>` of `CommitmentSchemeProver<B,MC>` and
+ *              `prove<B,MC>`, /root/reference/stwo/src/chacha/bitwise/air_stream.rs:143-153,185-231;
+ *              /root/reference/stwo/src/aes/lookup/air_ctr.rs:297-414).  A Rust `CudaBackend` implements
+ *              `PolyOps`, `MerkleOps`/`MerkleOpsLifted`, `QuotientOps`, `FriOps`, `GrindOps`, `ColumnOps` and
+ *              `ComponentProver` as one-line FFI calls onto these (INTEGRATION.md shows the `extern "C"` block).
+ *              All `uint32_t*` column arguments are DEVICE pointers (column-major, one column = 2^log_size words in
+ *              stwo's bit-reversed circle-domain order, M31 values in [0,p)); `*_host` arguments are host pointers.
+ *
+ *  (2) s2c_* : the product-level functions the reference exports from its WASM build
+ *              (/root/reference/stwo/src/wasm_api.rs:467-648,953-1008; JS binding
+ *              /root/reference/js/src/stwo/s2circuits.cjs): bytes in, malloc'd JSON string out, `s2c_free` to release --
+ *              the same convention as `__wbindgen_malloc/__wbindgen_free` and as the gnark library
+ *              (/root/reference/gnark/libraries/prover/libprove.go:26-48).
+ *
+ * Status codes: 0 = ok, non-zero = error; `cb_last_error(ctx)` returns the message (valid until the next call on ctx).
+ * Threading: one cb_ctx per (GPU, stream); a ctx must not be used from two threads at once; many contexts may coexist.
+ * There is no CPU fallback: every entry point fails with an error if no CUDA device is usable.
+ */
+#ifndef S2C_B200_H
+#define S2C_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb_ctx cb_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+int cb_init(int device, cb_ctx** out);
+void cb_destroy(cb_ctx* ctx);
+const char* cb_last_error(cb_ctx* ctx);
+/* Run all subsequent work of this context on an existing CUDA stream (cudaStream_t as void*); NULL = own stream. */
+int cb_set_stream(cb_ctx* ctx, void* cuda_stream);
+int cb_sync(cb_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t cb_launch_count(cb_ctx* ctx);
+
+/* ---- ColumnOps: device buffers (Col<B,T>::{zeros,uninitialized,to_cpu}, bit_reverse_column) ------------------------ */
+int cb_malloc(cb_ctx* ctx, size_t bytes, void** dptr);
+int cb_free(cb_ctx* ctx, void* dptr);
+int cb_h2d(cb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int cb_d2h(cb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int cb_memset_zero(cb_ctx* ctx, void* dptr, size_t bytes);
+
+/* ---- PolyOps ------------------------------------------------------------------------------------------------------ */
+/* PolyOps::precompute_twiddles for CanonicCoset(max_log).circle_domain().half_coset (and every smaller canonic domain);
+ * cached in the context (air_stream.rs:185-189). */
+int cb_precompute_twiddles(cb_ctx* ctx, int max_log);
+/* PolyOps::interpolate_columns: n_cols columns of 2^log_size evaluations (stride words apart) -> coefficients, in place. */
+int cb_interpolate_columns(cb_ctx* ctx, uint32_t* cols, size_t stride, int n_cols, int log_size);
+/* PolyOps::evaluate_polynomials / extend: coefficients (2^log_size) -> evaluations on CanonicCoset(log_size+log_ext). */
+int cb_evaluate_polynomials(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, int log_ext,
+                            uint32_t* evals, size_t eval_stride);
+/* Fused TreeBuilder::extend_evals + evaluate for a commitment: evaluations -> coefficients (coeffs_out, may be NULL) and
+ * LDE on CanonicCoset(log_size+log_ext).  src_kind: 0 = M31 words, 1 = packed bits (column j = bit j&31 of word j>>5),
+ * 2 = packed bytes (column j = byte j&3 of word j>>2); for packed kinds `src_stride` is the word-row stride. */
+int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* src, size_t src_stride, uint32_t first_col, int n_cols, int log_size,
+                  int log_ext, uint32_t* coeffs_out, size_t coeff_stride, uint32_t* lde_out, size_t lde_stride);
+/* PolyOps::eval_at_point for n_cols polynomials at one point of the QM31 circle; point_host = {x[4], y[4]},
+ * out_host = n_cols x 4 words. */
+int cb_eval_at_point(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, const uint32_t point_host[8],
+                     uint32_t* out_host);
+
+/* ---- MerkleOps<Blake2sMerkleHasher> (lifted VCS) --------------------------------------------------------------------- */
+/* build_leaves: Blake2s over the (lifted) values of all columns of a row.  Columns come as `n_groups` groups of equally
+ * sized, equally strided columns.  hashes_out: 2^lifting_log x 8 words. */
+int cb_merkle_build_leaves(cb_ctx* ctx, const uint32_t* const* group_base, const size_t* group_stride, const int* group_ncols,
+                           const int* group_log_size, int n_groups, int lifting_log, uint32_t* hashes_out);
+/* Streaming form for column tiles: state = 8 x 2^lifting_log words, `bytes_before` = bytes hashed by earlier calls;
+ * every non-final call must carry a multiple of 16 columns. */
+int cb_merkle_leaves_absorb(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, int log_size, int lifting_log,
+                            uint32_t* state, uint64_t bytes_before, int is_first, int is_final, uint32_t* hashes_out);
+/* build_next_layer / legacy commit_on_layer(prev, no columns): n_parents node hashes from 2*n_parents children. */
+int cb_merkle_next_layer(cb_ctx* ctx, const uint32_t* prev_hashes, uint32_t n_parents, uint32_t* out_hashes);
+
+/* ---- ComponentProver::evaluate_constraint_quotients_on_domain + AccumulationOps ------------------------------------- */
+/* generate_secure_powers, reversed: out[k] = alpha^(n-1-k) (4 words each). */
+int cb_generate_secure_powers_rev(cb_ctx* ctx, const uint32_t alpha_host[4], int n, uint32_t* out_dev);
+/* ChaCha20 stream AIR (constraints_stream.rs:20-70) on the 2^eval_log evaluation domain; lde = 33,280 columns;
+ * alpha_pows_rev from cb_generate_secure_powers_rev(n = 54,784); accum = 4 coordinate columns (accum_stride apart). */
+int cb_eval_constraints_chacha_stream(cb_ctx* ctx, const uint32_t* lde, size_t stride, int eval_log, int trace_log,
+                                      const uint32_t* alpha_pows_rev, uint32_t* accum, size_t accum_stride, int accumulate);
+
+/* ---- QuotientOps / FriOps / GrindOps -------------------------------------------------------------------------------- */
+/* accumulate_quotients for one sample point shared by all columns (the ChaCha case): sampled_host = n_cols x 4 words,
+ * point_host = {x[4], y[4]}, random_coeff_host[4]; out = 4 coordinate columns on the 2^domain_log domain. */
+int cb_accumulate_quotients(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, int domain_log,
+                            const uint32_t* sampled_host, const uint32_t point_host[8], const uint32_t random_coeff_host[4],
+                            uint32_t* out, size_t out_stride);
+int cb_fold_circle_into_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t alpha_host[4],
+                             uint32_t* dst, size_t dst_stride, int dst_is_zero);
+int cb_fold_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t alpha_host[4], uint32_t* dst,
+                 size_t dst_stride);
+/* Lowest nonce whose Blake2s(prefixed_digest || nonce) has >= pow_bits trailing zero bits. */
+int cb_grind_blake2s(cb_ctx* ctx, const uint8_t prefixed_digest_host[32], uint32_t pow_bits, uint64_t* nonce_out);
+int cb_gather_rows(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, const uint32_t* rows_host, int n_rows,
+                   uint32_t* out_host);
+
+/* ---- trace generation ----------------------------------------------------------------------------------------------- */
+/* generate_stream_trace (gen_stream.rs:226-261) in packed form: 1,040 words per row (words_out[w*stride + row]).
+ * pt/ct: host byte buffers of n_blocks*64 bytes.  *valid_out = 1 iff keystream^pt == ct on every provided row. */
+int cb_gen_trace_chacha_stream(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter,
+                               const uint8_t* plaintext_host, const uint8_t* ciphertext_host, uint32_t n_blocks, int log_size,
+                               uint32_t* words_out, size_t stride, int* valid_out);
+
+/* ---- product level (wasm_api.rs exports) -------------------------------------------------------------------------- */
+/* Each returns a malloc'd NUL-terminated JSON string in *json_out (release with s2c_free), identical in content to the
+ * reference's return string: {"success":true,"blocks":N,"algorithm":"chacha20","proof":"<base64>","proof_size_bytes":S}
+ * or {"error":"..."}.  ctx may be NULL (a process-wide context on device 0 is used). */
+int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                                size_t ciphertext_len, char** json_out, size_t* json_len);
+/* Raw form used by the benchmark and tests: proof bytes (bincode StreamProof) instead of base64-in-JSON. */
+int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           const uint8_t* ciphertext, size_t len, uint8_t** proof_out, size_t* proof_len);
+/* Per-stage device times (ms) of the last proof on ctx when profiling is enabled: "name=ms;name=ms;..." */
+int cb_set_profile(cb_ctx* ctx, int enable);
+const char* cb_stage_times(cb_ctx* ctx);
+int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                                 char** json_out, size_t* json_len);
+int s2c_get_circuits_info(char** json_out, size_t* json_len);
+void s2c_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,234 @@
+"""GPU parity tests (-m gpu): every CUDA stage through the C ABI against the CPU oracle on the same inputs (bit-exact:
+all arithmetic is M31/QM31 integer), then whole proofs against the oracle, the golden fixtures and (when oracle/_ref
+travelled to the box) the reference's own verifier."""
+import ctypes
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import api as oracle_api
+import chacha_air as ca
+import prover as op
+import stwo_core as sc
+import ref_wasm
+from make_golden import case_inputs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chacha20_golden.json")))["cases"]
+U32P = ctypes.POINTER(ctypes.c_uint32)
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def hp(a):
+    return a.ctypes.data_as(U32P)
+
+
+def q4(q):
+    return (ctypes.c_uint32 * 4)(*q.v)
+
+
+@pytest.mark.parametrize("log_n", [4, 6, 10, 12, 13, 14, 16])
+def test_interpolate_evaluate(backend, log_n):
+    be = backend
+    rng = np.random.default_rng(log_n)
+    ncols = 5 if log_n >= 14 else 37
+    v = rng.integers(0, sc.P, size=(ncols, 1 << log_n), dtype=np.uint64)
+    coef = sc.circle_ifft(v)
+    lde = sc.circle_fft(coef, log_n + 1)
+    n, m = 1 << log_n, 2 << log_n
+    d_v = be.upload(v)
+    be._ck(be.L.cb_interpolate_columns(be.ctx, d_v, ctypes.c_size_t(n), ncols, log_n))
+    assert np.array_equal(be.download(d_v, (ncols, n)), coef)
+    d_e = be.malloc(ncols * m * 4)
+    be._ck(be.L.cb_evaluate_polynomials(be.ctx, d_v, ctypes.c_size_t(n), ncols, log_n, 1, d_e, ctypes.c_size_t(m)))
+    assert np.array_equal(be.download(d_e, (ncols, m)), lde)
+    # evaluate with no extension returns the original values
+    d_b = be.malloc(ncols * n * 4)
+    be._ck(be.L.cb_evaluate_polynomials(be.ctx, d_v, ctypes.c_size_t(n), ncols, log_n, 0, d_b, ctypes.c_size_t(n)))
+    assert np.array_equal(be.download(d_b, (ncols, n)), v)
+    # fused commit path from M31 values
+    d_v2 = be.upload(v)
+    d_c2 = be.malloc(ncols * n * 4)
+    d_e2 = be.malloc(ncols * m * 4)
+    be._ck(be.L.cb_commit_lde(be.ctx, 0, d_v2, ctypes.c_size_t(n), 0, ncols, log_n, 1, d_c2, ctypes.c_size_t(n), d_e2, ctypes.c_size_t(m)))
+    assert np.array_equal(be.download(d_c2, (ncols, n)), coef)
+    assert np.array_equal(be.download(d_e2, (ncols, m)), lde)
+    for p in (d_v, d_e, d_b, d_v2, d_c2, d_e2):
+        be.free(p)
+
+
+def _witness(be, nb, seed):
+    key, nonce, counter, pt, ct = case_inputs(nb, seed)
+    log, K, NO, C, PT, CT, mrows = oracle_api.build_chacha_inputs(key, nonce, counter, pt, ct)
+    trace, valid = ca.generate_stream_trace(log, K, NO, C, PT, CT, mrows)
+    n = 1 << log
+    d_w = be.malloc(1040 * n * 4)
+    ok = ctypes.c_int()
+    be._ck(be.L.cb_gen_trace_chacha_stream(be.ctx, key, nonce, ctypes.c_uint32(counter), pt, ct, ctypes.c_uint32(nb), log, d_w,
+                                           ctypes.c_size_t(n), ctypes.byref(ok)))
+    return (key, nonce, counter, pt, ct), log, trace, valid, d_w, ok.value
+
+
+@pytest.mark.parametrize("nb,seed", [(1, None), (16, 1), (40, 3), (100, 9)])
+def test_chacha_witness(backend, nb, seed):
+    be = backend
+    _, log, trace, valid, d_w, ok = _witness(be, nb, seed)
+    n = 1 << log
+    words = be.download(d_w, (1040, n)).astype(np.uint64)
+    bits = ((words[:, None, :] >> np.arange(32, dtype=np.uint64)[None, :, None]) & 1).reshape(1040 * 32, n)
+    assert np.array_equal(bits, trace)
+    assert bool(ok) == valid
+    be.free(d_w)
+
+
+def test_chacha_witness_flags_bad_ciphertext(backend):
+    be = backend
+    key, nonce, counter, pt, ct = case_inputs(3, 5)
+    bad = bytearray(ct); bad[70] ^= 0x10
+    ok = ctypes.c_int()
+    d_w = be.malloc(1040 * 16 * 4)
+    be._ck(be.L.cb_gen_trace_chacha_stream(be.ctx, key, nonce, ctypes.c_uint32(counter), pt, bytes(bad), ctypes.c_uint32(3), 4, d_w,
+                                           ctypes.c_size_t(16), ctypes.byref(ok)))
+    assert ok.value == 0
+    be.free(d_w)
+
+
+@pytest.mark.parametrize("nb,seed", [(16, 1), (64, 4)])
+def test_chacha_commit_constraints_pipeline(backend, nb, seed):
+    """packed witness -> LDE (bit expansion fused in the FFT load) -> Merkle root -> constraint quotients."""
+    be = backend
+    _, log, trace, valid, d_w, ok = _witness(be, nb, seed)
+    n, m = 1 << log, 2 << log
+    C = ca.N_COLS
+    coef = sc.circle_ifft(trace)
+    lde = sc.circle_fft(coef, log + 1)
+    d_c = be.malloc(C * n * 4)
+    d_l = be.malloc(C * m * 4)
+    be._ck(be.L.cb_commit_lde(be.ctx, 1, d_w, ctypes.c_size_t(n), 0, C, log, 1, d_c, ctypes.c_size_t(n), d_l, ctypes.c_size_t(m)))
+    assert np.array_equal(be.download(d_c, (C, n)), coef)
+    assert np.array_equal(be.download(d_l, (C, m)), lde)
+    # Merkle: leaves + all layers
+    tree = sc.MerkleTree([lde[j] for j in range(C)])
+    d_h = be.malloc(m * 32)
+    bases = (ctypes.c_void_p * 1)(d_l.value)
+    strides = (ctypes.c_size_t * 1)(m)
+    ncols = (ctypes.c_int * 1)(C)
+    logs = (ctypes.c_int * 1)(log + 1)
+    be._ck(be.L.cb_merkle_build_leaves(be.ctx, bases, strides, ncols, logs, 1, log + 1, d_h))
+    leaves = be.download(d_h, (m, 8))
+    assert leaves.tobytes() == b"".join(tree.layers[0])
+    # streaming absorb in 3 tiles gives the same leaves
+    d_state = be.malloc(m * 32)
+    d_h2 = be.malloc(m * 32)
+    tiles = [(0, 1024), (1024, 16384), (16384, C)]
+    for i, (c0, c1) in enumerate(tiles):
+        ptr = ctypes.c_void_p(d_l.value + c0 * m * 4)
+        be._ck(be.L.cb_merkle_leaves_absorb(be.ctx, ptr, ctypes.c_size_t(m), c1 - c0, log + 1, log + 1, d_state,
+                                            ctypes.c_uint64(c0 * 4), int(i == 0), int(i == len(tiles) - 1), d_h2))
+    assert np.array_equal(be.download(d_h2, (m, 8)), leaves)
+    cur, n_cur = d_h, m
+    for layer in tree.layers[1:]:
+        d_n = be.malloc((n_cur // 2) * 32)
+        be._ck(be.L.cb_merkle_next_layer(be.ctx, cur, ctypes.c_uint32(n_cur // 2), d_n))
+        assert be.download(d_n, (n_cur // 2, 8)).tobytes() == b"".join(layer)
+        cur, n_cur = d_n, n_cur // 2
+    # constraints
+    alpha = sc.QM31(123456789, 987654321, 55555, 2147483000)
+    apr = op.secure_powers(alpha, ca.N_CONSTRAINTS)[::-1].copy()
+    d_apr = be.malloc(ca.N_CONSTRAINTS * 16)
+    be._ck(be.L.cb_generate_secure_powers_rev(be.ctx, q4(alpha), ca.N_CONSTRAINTS, d_apr))
+    assert np.array_equal(be.download(d_apr, (ca.N_CONSTRAINTS, 4)), apr)
+    acc = ca.evaluate_constraints(lde, apr)
+    acc = sc.q_mul_m31(acc, sc.m_inv(op.coset_vanishing_on_domain(log, log + 1)))
+    d_acc = be.malloc(4 * m * 4)
+    be._ck(be.L.cb_eval_constraints_chacha_stream(be.ctx, d_l, ctypes.c_size_t(m), log + 1, log, d_apr, d_acc, ctypes.c_size_t(m), 0))
+    assert np.array_equal(be.download(d_acc, (4, m)), acc.T)
+    # eval_at_point + quotients + folds
+    z = sc.get_random_point(sc.Blake2sChannel())
+    pt8 = (ctypes.c_uint32 * 8)(*(z[0].v + z[1].v))
+    ncheck = 640
+    got = np.empty((ncheck, 4), dtype=np.uint32)
+    be._ck(be.L.cb_eval_at_point(be.ctx, d_c, ctypes.c_size_t(n), ncheck, log, pt8, hp(got)))
+    want = sc.eval_at_point(coef[:ncheck], z[0], z[1])
+    assert np.array_equal(got, want)
+    rc = sc.QM31(5, 6, 7, 8)
+    batches = [((z[0], z[1]), [(j, sc.QM31(*[int(x) for x in want[j]])) for j in range(ncheck)])]
+    quot = op.fri_quotients([lde[j] for j in range(ncheck)], batches, rc, log + 1)
+    d_q = be.malloc(4 * m * 4)
+    be._ck(be.L.cb_accumulate_quotients(be.ctx, d_l, ctypes.c_size_t(m), ncheck, log + 1, hp(u32(want)), pt8, q4(rc), d_q, ctypes.c_size_t(m)))
+    assert np.array_equal(be.download(d_q, (4, m)), quot.T)
+    a1 = sc.QM31(11, 22, 33, 44)
+    line = op.fold_circle_into_line(np.zeros((m // 2, 4), dtype=np.uint64), quot, a1, log + 1)
+    d_line = be.malloc(4 * (m // 2) * 4)
+    be._ck(be.L.cb_fold_circle_into_line(be.ctx, d_q, ctypes.c_size_t(m), log + 1, q4(a1), d_line, ctypes.c_size_t(m // 2), 1))
+    assert np.array_equal(be.download(d_line, (4, m // 2)), line.T)
+    line2 = op.fold_line(line, a1, sc.Coset.half_odds(log))
+    d_line2 = be.malloc(4 * (m // 4) * 4)
+    be._ck(be.L.cb_fold_line(be.ctx, d_line, ctypes.c_size_t(m // 2), log, q4(a1), d_line2, ctypes.c_size_t(m // 4)))
+    assert np.array_equal(be.download(d_line2, (4, m // 4)), line2.T)
+    rows = u32([3, 7, m - 1])
+    outv = np.empty((ncheck, 3), dtype=np.uint32)
+    be._ck(be.L.cb_gather_rows(be.ctx, d_l, ctypes.c_size_t(m), ncheck, hp(rows), 3, hp(outv)))
+    assert np.array_equal(outv, lde[:ncheck][:, rows])
+
+
+def test_grind_returns_lowest_nonce(backend):
+    be = backend
+    ch = sc.Blake2sChannel()
+    ch.mix_u64(42)
+    want = ch.grind(10)
+    pd = ch.pow_prefixed_digest(10)
+    nonce = ctypes.c_uint64()
+    be._ck(be.L.cb_grind_blake2s(be.ctx, pd, 10, ctypes.byref(nonce)))
+    assert nonce.value == want
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN], ids=lambda c: c["name"])
+def test_proof_bytes_match_golden(backend, case):
+    key, nonce, counter, pt, ct = case_inputs(case["n_blocks"], case["seed"])
+    res = backend.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    if "error" in case:
+        assert res == {"error": case["error"]}
+        return
+    assert res["success"] is True and res["blocks"] == case["blocks"] and res["algorithm"] == "chacha20"
+    assert res["proof_size_bytes"] == case["proof_size_bytes"]
+    assert hashlib.sha256(res["proof"].encode()).hexdigest() == case["b64_sha256"]
+
+
+def test_proof_matches_oracle_bytes(backend):
+    key, nonce, counter, pt, ct = case_inputs(5, 21)
+    want = oracle_api.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof_bytes"]
+    got = backend.prove_chacha20_raw(key, nonce, counter, pt, ct)
+    assert got == want
+
+
+def test_error_behaviour(backend):
+    import zk_symmetric_crypto_b200 as z
+    zero = bytes(64)
+    assert backend.generate_chacha20_proof(bytes(31), bytes(12), 0, zero, zero) == {"error": "Key must be 32 bytes, got 31"}
+    assert backend.generate_chacha20_proof(bytes(32), bytes(12), 0, zero, zero) == \
+        {"error": "Ciphertext does not match encryption - invalid witness"}
+    with pytest.raises(z.BackendError):
+        backend.prove_chacha20_raw(bytes(32), bytes(12), 0, zero, zero)
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not on this box")
+@pytest.mark.parametrize("nb", [300, 1024])
+def test_reference_verifier_accepts_gpu_proofs(backend, nb):
+    """Sizes beyond the golden set: the reference's own verifier (wasm_api.rs:609) is the acceptance test, and the
+    reference prover must produce the same bytes."""
+    key, nonce, counter, pt, ct = case_inputs(nb, 100 + nb)
+    res = backend.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    assert res.get("success") is True, res
+    assert ref_wasm.verify_chacha20_proof(res["proof"], nonce, counter, pt, ct) == {"algorithm": "chacha20", "valid": True}
+    bad = bytearray(pt); bad[0] ^= 1
+    assert ref_wasm.verify_chacha20_proof(res["proof"], nonce, counter, bytes(bad), ct)["valid"] is False
+    if nb <= 512:
+        assert ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof"] == res["proof"]

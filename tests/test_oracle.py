@@ -1,0 +1,131 @@
+"""CPU tests (no GPU): the oracle against the reference's own KATs, the golden fixtures generated from the reference,
+and (when oracle/_ref is built) the reference itself, byte for byte."""
+import base64
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import api as oracle_api
+import chacha_air as ca
+import stwo_core as sc
+import ref_wasm
+from make_golden import case_inputs
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chacha20_golden.json")))["cases"]
+
+
+def test_rfc7539_block_kat():
+    # /root/reference/stwo/src/chacha/block.rs:116-139
+    key = struct.unpack("<8I", bytes(range(32)))
+    nonce = struct.unpack("<3I", bytes([0, 0, 0, 9, 0, 0, 0, 0x4A, 0, 0, 0, 0]))
+    out = ca.chacha20_block_words(key, 1, nonce)
+    assert out[:4] == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3]
+    assert out[-1] == 0x4E3C50A2
+
+
+def test_quarter_round_kat():
+    # /root/reference/stwo/src/chacha/quarter_round.rs:135-140 (RFC 7539 2.1.1)
+    a, b, c, d = 0x11111111, 0x01020304, 0x9B8D6F43, 0x01234567
+    M = 0xFFFFFFFF
+    rotl = lambda x, r: ((x << r) | (x >> (32 - r))) & M
+    a = (a + b) & M; d = rotl(d ^ a, 16); c = (c + d) & M; b = rotl(b ^ c, 12)
+    a = (a + b) & M; d = rotl(d ^ a, 8); c = (c + d) & M; b = rotl(b ^ c, 7)
+    assert (a, b, c, d) == (0xEA2A92F4, 0xCB1CF8CE, 0x4581472E, 0x5881C4BB)
+
+
+def test_field_identities():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, sc.P, size=(64, 4), dtype=np.uint64)
+    b = rng.integers(1, sc.P, size=(64, 4), dtype=np.uint64)
+    one = np.zeros((64, 4), dtype=np.uint64); one[:, 0] = 1
+    assert np.array_equal(sc.q_mul(b, sc.q_inv(b)), one)
+    assert np.array_equal(sc.q_mul(a, b), sc.q_mul(b, a))
+    x = sc.QM31(*[int(v) for v in a[0]]); y = sc.QM31(*[int(v) for v in b[0]])
+    assert tuple(int(v) for v in sc.q_mul(a[:1], b[:1])[0]) == (x * y).v
+    assert (y * y.inv()).v == (1, 0, 0, 0)
+
+
+def test_circle_generator_and_domain():
+    g = sc.GEN
+    assert (g[0] * g[0] + g[1] * g[1]) % sc.P == 1
+    p = g
+    for _ in range(30):
+        p = sc.pt_double(p)
+    assert p == (sc.P - 1, 0) or p == ((-1) % sc.P, 0)       # order 2^31
+    d = sc.canonic_domain(5)
+    xs, ys = d.points()
+    assert np.array_equal(xs[16:], xs[:16]) and np.array_equal(ys[16:], sc.m_neg(ys[:16]))
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 4, 7, 10])
+def test_fft_roundtrip_and_eval(log_n):
+    rng = np.random.default_rng(log_n)
+    v = rng.integers(0, sc.P, size=(3, 1 << log_n), dtype=np.uint64)
+    c = sc.circle_ifft(v)
+    assert np.array_equal(sc.circle_fft(c), v)
+    # the LDE restricted through eval_at_point: value at a domain point equals the polynomial evaluated there
+    lde = sc.circle_fft(c, log_n + 1)
+    xs, ys = sc.canonic_domain(log_n + 1).points_bitrev()
+    for row in (0, 1, (1 << log_n) + 3 if log_n > 1 else 1):
+        got = sc.eval_at_point(c, sc.QM31(int(xs[row])), sc.QM31(int(ys[row])))
+        assert np.array_equal(got[:, 0], lde[:, row]) and not got[:, 1:].any()
+
+
+def test_merkle_empty_and_lifting():
+    assert sc.MerkleTree([]).root().hex() == "69217a3079908094e11121d042354a7c1f55b6482ca1a51e1b250dfd1ed0eef9"
+    assert [sc.lifted_index(i, 4, 2) for i in range(16)] == [0, 1, 0, 1, 0, 1, 0, 1, 2, 3, 2, 3, 2, 3, 2, 3]
+
+
+def test_trace_satisfies_constraints_on_trace_domain():
+    # semantics of assert_constraints_on_polys (/root/reference/stwo/src/chacha/bitwise/mod.rs:116-216)
+    key, nonce, counter, pt, ct = case_inputs(16, 7)
+    log, K, NO, C, PT, CT, m = oracle_api.build_chacha_inputs(key, nonce, counter, pt, ct)
+    trace, valid = ca.generate_stream_trace(log, K, NO, C, PT, CT, m)
+    assert valid and trace.shape == (ca.N_COLS, 16)
+    apr = np.ones((ca.N_CONSTRAINTS, 4), dtype=np.uint64)
+    assert not ca.evaluate_constraints(trace, apr).any()
+    bad = bytearray(ct); bad[5] ^= 1
+    log, K, NO, C, PT, CT, m = oracle_api.build_chacha_inputs(key, nonce, counter, pt, bytes(bad))
+    trace, valid = ca.generate_stream_trace(log, K, NO, C, PT, CT, m)
+    assert not valid and ca.evaluate_constraints(trace, apr).any()
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN if c["n_blocks"] <= 17], ids=lambda c: c["name"])
+def test_oracle_matches_golden(case):
+    key, nonce, counter, pt, ct = case_inputs(case["n_blocks"], case["seed"])
+    res = oracle_api.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    assert len(res["proof_bytes"]) == case["proof_len"]
+    assert hashlib.sha256(res["proof_bytes"]).hexdigest() == case["proof_sha256"]
+    assert hashlib.sha256(res["proof"].encode()).hexdigest() == case["b64_sha256"]
+
+
+def test_oracle_constraints_not_satisfied_quirk():
+    case = [c for c in GOLDEN if "error" in c][0]
+    key, nonce, counter, pt, ct = case_inputs(case["n_blocks"], case["seed"])
+    assert oracle_api.generate_chacha20_proof(key, nonce, counter, pt, ct) == {"error": case["error"]}
+
+
+def test_oracle_input_validation_messages():
+    z = bytes(64)
+    assert oracle_api.generate_chacha20_proof(bytes(31), bytes(12), 0, z, z)["error"] == "Key must be 32 bytes, got 31"
+    assert oracle_api.generate_chacha20_proof(bytes(32), bytes(11), 0, z, z)["error"] == "Nonce must be 12 bytes, got 11"
+    assert "non-empty multiple of 64" in oracle_api.generate_chacha20_proof(bytes(32), bytes(12), 0, b"", b"")["error"]
+    assert "same length" in oracle_api.generate_chacha20_proof(bytes(32), bytes(12), 0, z, z + z)["error"]
+    assert "Counter overflow" in oracle_api.generate_chacha20_proof(bytes(32), bytes(12), 0xFFFFFFFF, z + z, z + z)["error"]
+    assert oracle_api.generate_chacha20_proof(bytes(32), bytes(12), 0, z, z)["error"].startswith("Ciphertext does not match")
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_reference_live():
+    key, nonce, counter, pt, ct = case_inputs(3, 11)
+    ref = ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    mine = oracle_api.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    assert mine["proof"] == ref["proof"]
+    assert ref_wasm.verify_chacha20_proof(mine["proof"], nonce, counter, pt, ct) == {"algorithm": "chacha20", "valid": True}
+    assert ref_wasm.verify_chacha20_proof(mine["proof"], nonce, counter + 1, pt, ct)["valid"] is False
+    assert ref_wasm.get_circuits_info()["chacha20"] == {"cols": ca.N_COLS, "constraints": ca.N_CONSTRAINTS,
+                                                        "block_bytes": 64, "key_bytes": 32}

@@ -1,0 +1,189 @@
+"""ctypes binding of libs2c_b200.so (C ABI: include/s2c_b200.h)."""
+import ctypes
+import json
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+
+# every symbol include/s2c_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "cb_init", "cb_destroy", "cb_last_error", "cb_set_stream", "cb_sync", "cb_launch_count",
+    "cb_malloc", "cb_free", "cb_h2d", "cb_d2h", "cb_memset_zero",
+    "cb_precompute_twiddles", "cb_interpolate_columns", "cb_evaluate_polynomials", "cb_commit_lde", "cb_eval_at_point",
+    "cb_merkle_build_leaves", "cb_merkle_leaves_absorb", "cb_merkle_next_layer",
+    "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
+    "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
+    "cb_gen_trace_chacha_stream",
+    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "cb_set_profile", "cb_stage_times",
+    "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
+]
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libs2c_b200.so")
+
+
+def lib():
+    """Load the CUDA backend; fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise BackendError("%s missing: run `make` (or __graft_entry__.build()) -- there is no CPU fallback" % p)
+        L = ctypes.CDLL(p)
+        L.cb_last_error.restype = ctypes.c_char_p
+        L.cb_stage_times.restype = ctypes.c_char_p
+        L.cb_launch_count.restype = ctypes.c_uint64
+        L.s2c_free.argtypes = [ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _bytes(b):
+    b = bytes(b)
+    return (ctypes.c_uint8 * max(len(b), 1)).from_buffer_copy(b if b else b"\0"), len(b)
+
+
+def _take_json(L, out, n):
+    s = ctypes.string_at(out.value, n.value).decode()
+    L.s2c_free(out)
+    return json.loads(s)
+
+
+class Backend:
+    """One backend context = one (GPU, stream).  Thin object wrapper over the cb_* entry points."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.ctx = ctypes.c_void_p()
+        rc = self.L.cb_init(int(device), ctypes.byref(self.ctx))
+        if rc != 0:
+            raise BackendError("cb_init(device=%d) failed with status %d: no usable CUDA device; no CPU fallback" % (device, rc))
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            self.L.cb_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BackendError(self.L.cb_last_error(self.ctx).decode(errors="replace"))
+
+    # ---- memory
+    def malloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._ck(self.L.cb_malloc(self.ctx, ctypes.c_size_t(nbytes), ctypes.byref(p)))
+        return p
+
+    def free(self, p):
+        self._ck(self.L.cb_free(self.ctx, p))
+
+    def upload(self, arr):
+        """numpy uint32 array -> device pointer."""
+        import numpy as np
+        a = np.ascontiguousarray(arr, dtype=np.uint32)
+        p = self.malloc(a.nbytes)
+        self._ck(self.L.cb_h2d(self.ctx, p, a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(a.nbytes)))
+        return p
+
+    def download(self, p, shape):
+        import numpy as np
+        a = np.empty(shape, dtype=np.uint32)
+        self._ck(self.L.cb_d2h(self.ctx, a.ctypes.data_as(ctypes.c_void_p), p, ctypes.c_size_t(a.nbytes)))
+        return a
+
+    def sync(self):
+        self._ck(self.L.cb_sync(self.ctx))
+
+    def launch_count(self):
+        return int(self.L.cb_launch_count(self.ctx))
+
+    def set_profile(self, on=True):
+        self.L.cb_set_profile(self.ctx, int(on))
+
+    def stage_times(self):
+        s = self.L.cb_stage_times(self.ctx).decode()
+        out = {}
+        for item in s.split(";"):
+            if "=" in item:
+                k, v = item.split("=")
+                out[k] = out.get(k, 0.0) + float(v)
+        return out
+
+    # ---- product level
+    def prove_chacha20_raw(self, key, nonce, counter, plaintext, ciphertext):
+        kb, _ = _bytes(key)
+        nb, _ = _bytes(nonce)
+        pb = bytes(plaintext)
+        cbuf = bytes(ciphertext)
+        out = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,
+                                           ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n))
+        self._ck(rc)
+        proof = ctypes.string_at(out, n.value)
+        self.L.s2c_free(out)
+        return proof
+
+    def generate_chacha20_proof(self, key, nonce, counter, plaintext, ciphertext):
+        key, nonce, pb, cbuf = bytes(key), bytes(nonce), bytes(plaintext), bytes(ciphertext)
+        out = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        rc = self.L.s2c_generate_chacha20_proof(self.ctx, key, ctypes.c_size_t(len(key)), nonce, ctypes.c_size_t(len(nonce)),
+                                                ctypes.c_uint32(counter & 0xFFFFFFFF), pb, ctypes.c_size_t(len(pb)), cbuf,
+                                                ctypes.c_size_t(len(cbuf)), ctypes.byref(out), ctypes.byref(n))
+        if not out:
+            raise BackendError("s2c_generate_chacha20_proof failed with status %d" % rc)
+        return _take_json(self.L, out, n)
+
+
+_DEFAULT = None
+
+
+def _default():
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Backend(int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("S2C_USE_LOCAL_RANK") else 0)
+    return _DEFAULT
+
+
+def generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext):
+    """wasm_api.rs:467 generate_chacha20_proof -> dict (same keys as the reference's JSON)."""
+    return _default().generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext)
+
+
+def prove_chacha20_raw(key, nonce, counter, plaintext, ciphertext):
+    return _default().prove_chacha20_raw(key, nonce, counter, plaintext, ciphertext)
+
+
+def debug_chacha20_keystream(key, nonce, counter):
+    L = lib()
+    key, nonce = bytes(key), bytes(nonce)
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    L.s2c_debug_chacha20_keystream(key, ctypes.c_size_t(len(key)), nonce, ctypes.c_size_t(len(nonce)),
+                                   ctypes.c_uint32(counter), ctypes.byref(out), ctypes.byref(n))
+    return _take_json(L, out, n)
+
+
+def get_circuits_info():
+    L = lib()
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    L.s2c_get_circuits_info(ctypes.byref(out), ctypes.byref(n))
+    return _take_json(L, out, n)

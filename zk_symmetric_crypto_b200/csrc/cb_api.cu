@@ -1,0 +1,473 @@
+// C ABI (include/s2c_b200.h): thin, exception-free wrappers over the kernels and the proof drivers.
+#include <mutex>
+#include <stdlib.h>
+#include "../../include/s2c_b200.h"
+#include "prover.hpp"
+
+using namespace m31;
+
+#define CB_TRY(ctx) try {
+#define CB_CATCH(ctx)                                  \
+    }                                                  \
+    catch (const std::exception& e) {                  \
+        if (ctx) (ctx)->err = e.what();                \
+        return 1;                                      \
+    }                                                  \
+    return 0;
+
+static std::string g_stage_str;
+
+extern "C" {
+
+int cb_init(int device, cb_ctx** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= device) return 2;  // no usable CUDA device: there is no CPU fallback
+    cb_ctx* ctx = new cb_ctx();
+    try {
+        ctx->device = device;
+        CB_CUDA(cudaSetDevice(device));
+        CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        CB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        fft_init_attrs();
+        chacha_init_attrs();
+    } catch (const std::exception& ex) {
+        delete ctx;
+        return 3;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void cb_destroy(cb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->tw_dev) cudaFree(ctx->tw_dev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cb_last_error(cb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cb_set_stream(cb_ctx* ctx, void* s) {
+    CB_TRY(ctx)
+    ctx->sync();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    } else {
+        CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    CB_CATCH(ctx)
+}
+
+int cb_sync(cb_ctx* ctx) {
+    CB_TRY(ctx)
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+uint64_t cb_launch_count(cb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cb_malloc(cb_ctx* ctx, size_t bytes, void** dptr) {
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    *dptr = ctx->dmalloc(bytes);
+    CB_CATCH(ctx)
+}
+int cb_free(cb_ctx* ctx, void* dptr) {
+    CB_TRY(ctx)
+    ctx->dfree(dptr);
+    CB_CATCH(ctx)
+}
+int cb_h2d(cb_ctx* ctx, void* d, const void* h, size_t bytes) {
+    CB_TRY(ctx)
+    CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+int cb_d2h(cb_ctx* ctx, void* h, const void* d, size_t bytes) {
+    CB_TRY(ctx)
+    CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+int cb_memset_zero(cb_ctx* ctx, void* d, size_t bytes) {
+    CB_TRY(ctx)
+    CB_CUDA(cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    CB_CATCH(ctx)
+}
+
+int cb_precompute_twiddles(cb_ctx* ctx, int max_log) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(max_log);
+    CB_CATCH(ctx)
+}
+
+int cb_interpolate_columns(cb_ctx* ctx, uint32_t* cols, size_t stride, int n_cols, int log_size) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(log_size);
+    ColSrc src{SRC_M31, cols, stride, 0};
+    CB_CUDA(launch_fft(ctx->stream, src, n_cols, log_size, 0, 1 | 2, cols, stride, nullptr, 0, ctx->tw, cols, stride));
+    ctx->launches += log_size <= 13 ? 1 : 2;
+    CB_CATCH(ctx)
+}
+
+int cb_evaluate_polynomials(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, int log_ext,
+                            uint32_t* evals, size_t eval_stride) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(log_size + log_ext);
+    ColSrc src{SRC_M31, coeffs, stride, 0};
+    CB_CUDA(launch_fft(ctx->stream, src, n_cols, log_size, log_ext, 4, nullptr, 0, evals, eval_stride, ctx->tw, nullptr, 0));
+    ctx->launches += log_size + log_ext <= 13 ? 1 : 2;
+    CB_CATCH(ctx)
+}
+
+int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* srcp, size_t src_stride, uint32_t first_col, int n_cols, int log_size,
+                  int log_ext, uint32_t* coeffs_out, size_t coeff_stride, uint32_t* lde_out, size_t lde_stride) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(log_size + log_ext);
+    ColSrc src{src_kind, srcp, src_stride, first_col};
+    int mode = 1 | 4 | (coeffs_out ? 2 : 0);
+    DBuf<uint32_t> scratch;
+    uint32_t* sc = coeffs_out;
+    size_t sc_stride = coeff_stride;
+    if (!coeffs_out && log_size + log_ext > 13) {
+        scratch = DBuf<uint32_t>(ctx, (size_t)n_cols << log_size);
+        sc = scratch.p;
+        sc_stride = (size_t)1 << log_size;
+    }
+    CB_CUDA(launch_fft(ctx->stream, src, n_cols, log_size, log_ext, mode, coeffs_out, coeff_stride, lde_out, lde_stride, ctx->tw, sc,
+                       sc_stride));
+    ctx->launches += log_size + log_ext <= 13 ? 1 : 3;
+    CB_CATCH(ctx)
+}
+
+int cb_eval_at_point(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, const uint32_t pt[8],
+                     uint32_t* out_host) {
+    CB_TRY(ctx)
+    const size_t N = (size_t)1 << log_size;
+    QM31 x{{pt[0], pt[1], pt[2], pt[3]}}, y{{pt[4], pt[5], pt[6], pt[7]}};
+    std::vector<QM31> maps(log_size > 0 ? log_size : 1);
+    maps[0] = y;
+    for (int j = 1; j < log_size; j++) { maps[j] = x; x = qsub(qmul_m(qmul(x, x), 2), qone()); }
+    DBuf<uint32_t> basis(ctx, 4 * N), d_out(ctx, (size_t)n_cols * 4);
+    CB_CUDA(launch_basis(ctx->stream, basis.p, N, log_size, maps.data()));
+    CB_CUDA(launch_oods_dot(ctx->stream, coeffs, stride, n_cols, log_size, basis.p, N, d_out.p));
+    ctx->launches += log_size + 1;
+    CB_CUDA(cudaMemcpyAsync(out_host, d_out.p, (size_t)n_cols * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+
+int cb_merkle_build_leaves(cb_ctx* ctx, const uint32_t* const* base, const size_t* stride, const int* ncols, const int* logs,
+                           int n_groups, int lifting_log, uint32_t* hashes_out) {
+    CB_TRY(ctx)
+    if (n_groups > MAX_LEAF_GROUPS) throw CbError("too many column groups");
+    LeafGroups g{};
+    g.n = n_groups;
+    for (int i = 0; i < n_groups; i++) g.g[i] = {base[i], stride[i], ncols[i], logs[i]};
+    CB_CUDA(launch_merkle_leaves(ctx->stream, g, lifting_log, nullptr, 0, 1, 1, hashes_out));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_merkle_leaves_absorb(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, int log_size, int lifting_log,
+                            uint32_t* state, uint64_t bytes_before, int is_first, int is_final, uint32_t* hashes_out) {
+    CB_TRY(ctx)
+    if (!is_final && (n_cols % 16)) throw CbError("non-final absorb needs a multiple of 16 columns");
+    LeafGroups g{};
+    g.n = 1;
+    g.g[0] = {cols, stride, n_cols, log_size};
+    CB_CUDA(launch_merkle_leaves(ctx->stream, g, lifting_log, state, bytes_before, is_first, is_final, hashes_out));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_merkle_next_layer(cb_ctx* ctx, const uint32_t* prev, uint32_t n_parents, uint32_t* out) {
+    CB_TRY(ctx)
+    CB_CUDA(launch_merkle_nodes(ctx->stream, prev, n_parents, out));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_generate_secure_powers_rev(cb_ctx* ctx, const uint32_t a[4], int n, uint32_t* out_dev) {
+    CB_TRY(ctx)
+    CB_CUDA(launch_secure_powers_rev(ctx->stream, QM31{{a[0], a[1], a[2], a[3]}}, n, out_dev));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_eval_constraints_chacha_stream(cb_ctx* ctx, const uint32_t* lde, size_t stride, int eval_log, int trace_log,
+                                      const uint32_t* apr, uint32_t* accum, size_t accum_stride, int accumulate) {
+    CB_TRY(ctx)
+    const int ext = eval_log - trace_log;
+    std::vector<uint32_t> den((size_t)1 << ext);
+    for (uint32_t i = 0; i < den.size(); i++) {
+        uint32_t row = i << trace_log;
+        host::Pt p = host::index_to_point(host::canonic_index_at(eval_log, host::bit_reverse(row, eval_log)));
+        den[i] = inv(host::coset_vanishing_m31(trace_log, p));
+    }
+    DBuf<uint32_t> d_den(ctx, den.size());
+    CB_CUDA(cudaMemcpyAsync(d_den.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sync();
+    CB_CUDA(launch_chacha_constraints(ctx->stream, lde, stride, eval_log, trace_log, apr, d_den.p, accum, accum_stride, accumulate));
+    ctx->launches++;
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+
+int cb_accumulate_quotients(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, int domain_log, const uint32_t* sampled,
+                            const uint32_t pt[8], const uint32_t rcw[4], uint32_t* out, size_t out_stride) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(domain_log);
+    QM31 zx{{pt[0], pt[1], pt[2], pt[3]}}, zy{{pt[4], pt[5], pt[6], pt[7]}}, rc{{rcw[0], rcw[1], rcw[2], rcw[3]}};
+    std::vector<uint32_t> coefs((size_t)n_cols * 4);
+    QM31 alpha = qone(), lin_a = qzero(), lin_b = qzero();
+    const QM31 c = qsub(qconj(zy), zy);
+    for (int j = 0; j < n_cols; j++) {
+        QM31 v{{sampled[4 * j], sampled[4 * j + 1], sampled[4 * j + 2], sampled[4 * j + 3]}};
+        QM31 a = qsub(qconj(v), v);
+        QM31 b = qsub(qmul(v, c), qmul(a, zy));
+        lin_a = qadd(lin_a, qmul(alpha, a));
+        lin_b = qadd(lin_b, qmul(alpha, b));
+        QM31 ac = qmul(alpha, c);
+        for (int k = 0; k < 4; k++) coefs[(size_t)j * 4 + k] = ac.v[k];
+        alpha = qmul(alpha, rc);
+    }
+    DBuf<uint32_t> d_coefs(ctx, coefs.size());
+    CB_CUDA(cudaMemcpyAsync(d_coefs.p, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    QuotBatch qb{};
+    qb.prx = {zx.v[0], zx.v[1]}; qb.pix = {zx.v[2], zx.v[3]};
+    qb.pry = {zy.v[0], zy.v[1]}; qb.piy = {zy.v[2], zy.v[3]};
+    qb.lin_a = lin_a; qb.lin_b = lin_b; qb.batch_coeff = qzero();
+    qb.coefs = d_coefs.p; qb.col_idx = nullptr; qb.n_cols = n_cols;
+    DBuf<QuotBatch> d_qb(ctx, 1);
+    CB_CUDA(cudaMemcpyAsync(d_qb.p, &qb, sizeof(qb), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(launch_quotients(ctx->stream, cols, stride, n_cols, nullptr, 0, d_qb.p, 1, domain_log, ctx->tw, out, out_stride));
+    ctx->launches++;
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+
+int cb_fold_circle_into_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t a[4], uint32_t* dst,
+                             size_t dst_stride, int dst_is_zero) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(src_log);
+    CB_CUDA(launch_fold_circle(ctx->stream, src, src_stride, src_log, QM31{{a[0], a[1], a[2], a[3]}}, ctx->tw, dst, dst_stride,
+                               dst_is_zero));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_fold_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t a[4], uint32_t* dst,
+                 size_t dst_stride) {
+    CB_TRY(ctx)
+    ctx->ensure_twiddles(src_log + 1);
+    CB_CUDA(launch_fold_line(ctx->stream, src, src_stride, src_log, QM31{{a[0], a[1], a[2], a[3]}}, ctx->tw, dst, dst_stride));
+    ctx->launches++;
+    CB_CATCH(ctx)
+}
+
+int cb_grind_blake2s(cb_ctx* ctx, const uint8_t pd[32], uint32_t pow_bits, uint64_t* nonce_out) {
+    CB_TRY(ctx)
+    DBuf<uint32_t> d_pd(ctx, 8);
+    DBuf<unsigned long long> d_best(ctx, 1);
+    unsigned long long best = ~0ull;
+    CB_CUDA(cudaMemcpyAsync(d_pd.p, pd, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(d_best.p, &best, 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t base = 0;; base += (1ull << 20)) {
+        CB_CUDA(launch_grind(ctx->stream, d_pd.p, pow_bits, base, 1ull << 20, d_best.p));
+        ctx->launches++;
+        CB_CUDA(cudaMemcpyAsync(&best, d_best.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();
+        if (best != ~0ull) break;
+    }
+    *nonce_out = best;
+    CB_CATCH(ctx)
+}
+
+int cb_gather_rows(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, const uint32_t* rows, int n_rows, uint32_t* out) {
+    CB_TRY(ctx)
+    DBuf<uint32_t> d_rows(ctx, n_rows), d_out(ctx, (size_t)n_cols * n_rows);
+    CB_CUDA(cudaMemcpyAsync(d_rows.p, rows, (size_t)n_rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(launch_gather_rows(ctx->stream, cols, stride, n_cols, d_rows.p, n_rows, d_out.p));
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n_cols * n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+
+int cb_gen_trace_chacha_stream(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                               const uint8_t* ct, uint32_t n_blocks, int log_size, uint32_t* words_out, size_t stride, int* valid) {
+    CB_TRY(ctx)
+    uint32_t kw[8], nw[3];
+    for (int i = 0; i < 8; i++) kw[i] = host::load_le32(key + 4 * i);
+    for (int i = 0; i < 3; i++) nw[i] = host::load_le32(nonce + 4 * i);
+    size_t len = (size_t)n_blocks * 64;
+    DBuf<uint32_t> d_pt(ctx, len / 4), d_ct(ctx, len / 4);
+    DBuf<int> d_inv(ctx, 1);
+    CB_CUDA(cudaMemcpyAsync(d_pt.p, pt, len, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(d_ct.p, ct, len, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaMemsetAsync(d_inv.p, 0, 4, ctx->stream));
+    uint32_t rows_needed = (n_blocks + 15) / 16;
+    CB_CUDA(launch_chacha_witness(ctx->stream, kw, nw, counter, n_blocks, rows_needed * 16, d_pt.p, d_ct.p, log_size, words_out, stride,
+                                  d_inv.p));
+    ctx->launches++;
+    int invalid = 0;
+    CB_CUDA(cudaMemcpyAsync(&invalid, d_inv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->sync();
+    *valid = !invalid;
+    CB_CATCH(ctx)
+}
+
+int cb_set_profile(cb_ctx* ctx, int enable) {
+    if (!ctx) return 1;
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+const char* cb_stage_times(cb_ctx* ctx) {
+    static thread_local std::string s;
+    s.clear();
+    if (!ctx) return "";
+    for (auto& st : ctx->stages) s += st.name + "=" + std::to_string(st.ms) + ";";
+    return s.c_str();
+}
+
+// ---------------------------------------------------------------------------------------------- product level
+static cb_ctx* default_ctx(std::string& err) {
+    static std::mutex mu;
+    static cb_ctx* g = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!g) {
+        int rc = cb_init(0, &g);
+        if (rc) {
+            err = "no usable CUDA device (cb_init=" + std::to_string(rc) + "); this backend has no CPU fallback";
+            g = nullptr;
+        }
+    }
+    return g;
+}
+
+static int ret_json(const std::string& s, char** out, size_t* len) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) return 1;
+    memcpy(p, s.c_str(), s.size() + 1);
+    *out = p;
+    if (len) *len = s.size();
+    return 0;
+}
+
+static std::string json_escape(const std::string& s) {
+    std::string o;
+    for (char c : s) {
+        if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back(c); }
+        else if (c == '\n') o += "\\n";
+        else o.push_back(c);
+    }
+    return o;
+}
+static std::string json_error(const std::string& m) { return "{\"error\":\"" + json_escape(m) + "\"}"; }
+
+int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                           const uint8_t* ct, size_t len, uint8_t** proof_out, size_t* proof_len) {
+    std::string derr;
+    if (!ctx) ctx = default_ctx(derr);
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (len == 0 || len % 64) throw CbError("Plaintext must be non-empty multiple of 64 bytes, got " + std::to_string(len));
+    std::vector<uint8_t> proof;
+    std::string e = prove_chacha20(ctx, key, nonce, counter, pt, ct, len, proof);
+    if (!e.empty()) throw CbError(e);
+    uint8_t* p = (uint8_t*)malloc(proof.size());
+    memcpy(p, proof.data(), proof.size());
+    *proof_out = p;
+    *proof_len = proof.size();
+    CB_CATCH(ctx)
+}
+
+// StarkProof::size_estimate() of the reference is reported as proof_size_bytes; see estimate in prove driver notes.
+int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
+                                size_t* json_len) {
+    // validation order and messages: wasm_api.rs:475-493
+    if (key_len != 32) return ret_json(json_error("Key must be 32 bytes, got " + std::to_string(key_len)), json_out, json_len);
+    if (nonce_len != 12) return ret_json(json_error("Nonce must be 12 bytes, got " + std::to_string(nonce_len)), json_out, json_len);
+    if (pt_len == 0 || pt_len % 64 != 0)
+        return ret_json(json_error("Plaintext must be non-empty multiple of 64 bytes, got " + std::to_string(pt_len)), json_out, json_len);
+    if (ct_len != pt_len)
+        return ret_json(json_error("Ciphertext must be same length as plaintext, got " + std::to_string(ct_len) + " vs " +
+                                   std::to_string(pt_len)), json_out, json_len);
+    size_t num_blocks = pt_len / 64;
+    if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
+        return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
+                                   " blocks would exceed u32::MAX"), json_out, json_len);
+    std::string derr;
+    if (!ctx) ctx = default_ctx(derr);
+    if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
+    std::vector<uint8_t> proof;
+    std::string e;
+    try {
+        CB_CUDA(cudaSetDevice(ctx->device));
+        e = prove_chacha20(ctx, key, nonce, counter, pt, ct, pt_len, proof);
+    } catch (const std::exception& ex) {
+        ctx->err = ex.what();
+        ret_json(json_error(std::string("backend failure: ") + ex.what()), json_out, json_len);
+        return 1;
+    }
+    if (!e.empty()) return ret_json(json_error(e), json_out, json_len);
+    std::string b64 = host::base64_encode(proof.data(), proof.size());
+    std::string js = "{\"algorithm\":\"chacha20\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
+                     "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 84)) +
+                     ",\"success\":true}";
+    return ret_json(js, json_out, json_len);
+}
+
+int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                                 char** json_out, size_t* json_len) {
+    // wasm_api.rs:953-990: native block function (chacha/block.rs:95), hex of the 64 keystream bytes
+    if (key_len != 32 || nonce_len != 12) return ret_json(json_error("Invalid key or nonce length"), json_out, json_len);
+    uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u}, v[16];
+    for (int i = 0; i < 8; i++) s[4 + i] = host::load_le32(key + 4 * i);
+    s[12] = counter;
+    for (int i = 0; i < 3; i++) s[13 + i] = host::load_le32(nonce + 4 * i);
+    memcpy(v, s, sizeof v);
+    auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+    auto qr = [&](int a, int b, int c, int d) {
+        v[a] += v[b]; v[d] = rotl(v[d] ^ v[a], 16); v[c] += v[d]; v[b] = rotl(v[b] ^ v[c], 12);
+        v[a] += v[b]; v[d] = rotl(v[d] ^ v[a], 8);  v[c] += v[d]; v[b] = rotl(v[b] ^ v[c], 7);
+    };
+    for (int r = 0; r < 10; r++) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    static const char* H = "0123456789abcdef";
+    std::string hex;
+    for (int i = 0; i < 16; i++) {
+        uint32_t w = v[i] + s[i];
+        for (int b = 0; b < 4; b++) { uint8_t x = (uint8_t)(w >> (8 * b)); hex.push_back(H[x >> 4]); hex.push_back(H[x & 15]); }
+    }
+    std::string js = "{\"counter\":" + std::to_string(counter) + ",\"key_len\":32,\"keystream_hex\":\"" + hex + "\",\"nonce_len\":12}";
+    return ret_json(js, json_out, json_len);
+}
+
+int s2c_get_circuits_info(char** json_out, size_t* json_len) {
+    // wasm_api.rs:993-1008 (values confirmed against the reference binary's own get_circuits_info())
+    return ret_json("{\"aes128_ctr\":{\"block_bytes\":16,\"cols\":24480,\"constraints\":34464,\"key_bytes\":16},"
+                    "\"aes256_ctr\":{\"block_bytes\":16,\"cols\":34784,\"constraints\":49024,\"key_bytes\":32},"
+                    "\"chacha20\":{\"block_bytes\":64,\"cols\":33280,\"constraints\":54784,\"key_bytes\":32}}",
+                    json_out, json_len);
+}
+
+void s2c_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Backend context shared by the C ABI (cb_*) and the proof drivers (s2c_*).
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "common.cuh"
+#include "host_util.hpp"
+
+struct CbError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CB_CUDA(x)                                                                                          \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess)                                                                              \
+            throw CbError(std::string(#x) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct StageTime {
+    std::string name;
+    float ms;
+};
+
+struct cb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    // twiddles (device) for canonic domains up to tw.max_log
+    FftTables tw{nullptr, nullptr, nullptr, nullptr, 0};
+    uint32_t* tw_dev = nullptr;
+    // per-stage device timing of the last proof (CUDA events on `stream`)
+    bool profile = false;
+    std::vector<StageTime> stages;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    uint64_t launches = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
+
+    void ensure_twiddles(int max_log);
+    void* dmalloc(size_t bytes);
+    void dfree(void* p);
+    void sync() { CB_CUDA(cudaStreamSynchronize(stream)); }
+    void stage_begin(const char* name);
+    void stage_end();
+    void collect_stages();
+};
+
+// RAII device buffer on the context's stream-ordered pool
+template <typename T>
+struct DBuf {
+    cb_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(cb_ctx* c, size_t count) : ctx(c), n(count) { p = count ? (T*)c->dmalloc(count * sizeof(T)) : nullptr; }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            ctx = o.ctx; p = o.p; n = o.n; o.p = nullptr;
+        }
+        return *this;
+    }
+    void release() {
+        if (p) ctx->dfree(p);
+        p = nullptr;
+    }
+    ~DBuf() { release(); }
+};
+
+// Device Merkle tree: all layers concatenated, layer 0 = leaves (2^log_leaves hashes of 8 words)
+struct DevMerkle {
+    DBuf<uint32_t> nodes;
+    int log_leaves = 0;
+    host::Hash32 root;
+    size_t layer_offset(int layer) const {  // in hashes
+        size_t off = 0;
+        for (int l = 0; l < layer; l++) off += (size_t)1 << (log_leaves - l);
+        return off;
+    }
+};
+
+// kernel launchers (kernels_*.cu)
+cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int lifting_log, uint32_t* h_state, uint64_t bytes_before,
+                                 int is_first, int is_final, uint32_t* out);
+cudaError_t launch_merkle_nodes(cudaStream_t st, const uint32_t* prev, uint32_t n_parents, uint32_t* out);
+cudaError_t launch_chacha_witness(cudaStream_t st, const uint32_t key[8], const uint32_t nonce[3], uint32_t counter,
+                                  uint32_t num_blocks, uint32_t n_active_rows, const uint32_t* pt, const uint32_t* ct, int log_size,
+                                  uint32_t* W, size_t stride, int* invalid);
+cudaError_t launch_chacha_constraints(cudaStream_t st, const uint32_t* lde, size_t stride, int eval_log, int trace_log,
+                                      const uint32_t* apr, const uint32_t* den_inv, uint32_t* out, size_t out_stride, int accumulate);
+void chacha_init_attrs();
+cudaError_t launch_basis(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const m31::QM31* maps);
+cudaError_t launch_oods_dot(cudaStream_t st, const uint32_t* coeffs, size_t stride, int n_cols, int log_n, const uint32_t* basis,
+                            size_t b_stride, uint32_t* out);
+cudaError_t launch_quotients(cudaStream_t st, const uint32_t* cols, size_t stride, int n_main, const uint32_t* extra,
+                             size_t extra_stride, const void* batches_dev, int n_batches, int m, const FftTables& tw, uint32_t* out,
+                             size_t out_stride);
+cudaError_t launch_fold_circle(cudaStream_t st, const uint32_t* src, size_t s_stride, int m, m31::QM31 alpha, const FftTables& tw,
+                               uint32_t* dst, size_t d_stride, int dst_is_zero);
+cudaError_t launch_fold_line(cudaStream_t st, const uint32_t* src, size_t s_stride, int L, m31::QM31 alpha, const FftTables& tw,
+                             uint32_t* dst, size_t d_stride);
+cudaError_t launch_grind(cudaStream_t st, const uint32_t* prefixed_digest_dev, uint32_t pow_bits, uint64_t base, uint64_t count,
+                         unsigned long long* best_dev);
+cudaError_t launch_gather_rows(cudaStream_t st, const uint32_t* cols, size_t stride, int n_cols, const uint32_t* rows_dev, int n_rows,
+                               uint32_t* out);
+cudaError_t launch_gather_hashes(cudaStream_t st, const uint32_t* hashes, const uint32_t* idx_dev, int n, uint32_t* out);
+cudaError_t launch_secure_powers_rev(cudaStream_t st, m31::QM31 alpha, int K, uint32_t* apr);
+
+
+// shared prover building blocks (prover_common.cu)
+DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log);
+std::vector<host::Hash32> merkle_decommit(cb_ctx* ctx, const DevMerkle& t, const std::vector<uint32_t>& positions);

@@ -1,0 +1,117 @@
+// Blake2s lifted-Merkle kernels for sm_100a: one thread per leaf, integer pipe only.
+//
+// Replaces upstream stwo `MerkleProverLifted::commit` / `MerkleOpsLifted::{build_leaves, build_next_layer}` for
+// SimdBackend (prover/vcs_lifted/prover.rs, backend/simd/blake2s_lifted.rs), reached from the reference through
+// `TreeBuilder::commit` (/root/reference/stwo/src/chacha/bitwise/air_stream.rs:197,212).
+//   leaf i  = Blake2s( LE u32 of col_0[lift_0(i)] || col_1[lift_1(i)] || ... )      (all columns of the tree, in order)
+//   lift(i) for a column of log size k < L:  ((i >> (L-k+1)) << 1) | (i & 1)
+//   node    = Blake2s( left || right )
+// Columns arrive as groups of equally sized, equally strided columns; leaf state (h[8]) can be carried across calls
+// so that a tree can be absorbed tile by tile while the LDE is streamed (column count per non-final call must be a
+// multiple of 16 = one 64-byte Blake2s block).
+#include "common.cuh"
+#include "blake2s.cuh"
+
+
+namespace merk {
+
+// state: h_state[w * n_leaves + leaf] (SoA) when carrying; bytes_before = bytes absorbed by earlier calls.
+__global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lifting_log, uint32_t* __restrict__ h_state,
+                                                     uint64_t bytes_before, int is_first, int is_final,
+                                                     uint32_t* __restrict__ out) {
+    const uint32_t n_leaves = 1u << lifting_log;
+    const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    uint32_t h[8];
+    if (is_first) {
+        blake2s::init(h);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) h[w] = h_state[(size_t)w * n_leaves + leaf];
+    }
+    uint64_t t = bytes_before;
+    uint32_t m[16];
+    int k = 0;  // words buffered in m (only non-zero on the slow path / at the very end)
+    int total_cols = 0;
+    for (int gi = 0; gi < groups.n; gi++) total_cols += groups.g[gi].ncols;
+    int done_cols = 0;
+    for (int gi = 0; gi < groups.n; gi++) {
+        const LeafGroup g = groups.g[gi];
+        uint32_t row = leaf;
+        if (g.log_size < lifting_log) {
+            int sh = lifting_log - g.log_size;
+            row = ((leaf >> (sh + 1)) << 1) | (leaf & 1);
+        }
+        const uint32_t* p = g.base + row;
+        int c = 0;
+        if (k == 0) {
+            // fast path: whole 64-byte blocks straight from 16 coalesced column loads
+            for (; c + 16 <= g.ncols; c += 16) {
+#pragma unroll
+                for (int w = 0; w < 16; w++) m[w] = __ldg(p + (size_t)(c + w) * g.stride);
+                t += 64;
+                bool last = is_final && (done_cols + c + 16 == total_cols);
+                blake2s::compress(h, m, t, last);
+            }
+        }
+        for (; c < g.ncols; c++) {
+            uint32_t v = __ldg(p + (size_t)c * g.stride);
+#pragma unroll
+            for (int w = 0; w < 16; w++)
+                if (w == k) m[w] = v;
+            k++;
+            if (k == 16) {
+                t += 64;
+                bool last = is_final && (done_cols + c + 1 == total_cols);
+                blake2s::compress(h, m, t, last);
+                k = 0;
+            }
+        }
+        done_cols += g.ncols;
+    }
+    if (is_final && (k > 0 || total_cols == 0 && is_first)) {
+#pragma unroll
+        for (int w = 0; w < 16; w++)
+            if (w >= k) m[w] = 0;
+        t += 4 * k;
+        blake2s::compress(h, m, t, true);
+    }
+    if (is_final) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) out[(size_t)leaf * 8 + w] = h[w];
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) h_state[(size_t)w * n_leaves + leaf] = h[w];
+    }
+}
+
+// parent[i] = Blake2s(child[2i] || child[2i+1]); hashes are 8 consecutive u32
+__global__ void __launch_bounds__(256) nodes_kernel(const uint4* __restrict__ prev, uint32_t n_parents, uint4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parents) return;
+    uint4 a = prev[4 * (size_t)i], b = prev[4 * (size_t)i + 1], c = prev[4 * (size_t)i + 2], d = prev[4 * (size_t)i + 3];
+    uint32_t m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    uint32_t h[8];
+    blake2s::init(h);
+    blake2s::compress(h, m, 64, true);
+    out[2 * (size_t)i] = make_uint4(h[0], h[1], h[2], h[3]);
+    out[2 * (size_t)i + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+}  // namespace merk
+
+cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int lifting_log, uint32_t* h_state,
+                                 uint64_t bytes_before, int is_first, int is_final, uint32_t* out) {
+    uint32_t n = 1u << lifting_log;
+    int threads = n >= 128 * 148 * 2 ? 128 : 64;
+    if (n < 64) threads = 32;
+    merk::leaves_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before, is_first,
+                                                                         is_final, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merkle_nodes(cudaStream_t st, const uint32_t* prev, uint32_t n_parents, uint32_t* out) {
+    int threads = 128;
+    merk::nodes_kernel<<<(n_parents + threads - 1) / threads, threads, 0, st>>>((const uint4*)prev, n_parents, (uint4*)out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,44 @@
+// Prover-level declarations shared by the AIR drivers.
+#pragma once
+#include <array>
+#include "ctx.hpp"
+
+// PcsConfig::default() of the pinned stwo rev, as serialised inside every reference proof (oracle/prover.py PcsConfig):
+// pow_bits 10, FriConfig{log_blowup_factor 1, log_last_layer_degree_bound 0, n_queries 3, fold_step 1}, Option::None.
+struct PcsConfig {
+    uint32_t pow_bits = 10;
+    uint32_t log_blowup = 1;
+    uint32_t log_last_layer_degree_bound = 0;
+    uint64_t n_queries = 3;
+    uint32_t fold_step = 1;
+    void serialize(std::vector<uint8_t>& out) const {
+        host::put_u32(out, pow_bits);
+        host::put_u32(out, log_blowup);
+        host::put_u32(out, log_last_layer_degree_bound);
+        host::put_u64(out, n_queries);
+        host::put_u32(out, fold_step);
+        out.push_back(0);
+    }
+};
+
+struct ProveOptions {
+    int force_log_size = 0;            // prove on a larger trace than the block count needs (rows beyond are default rows)
+    bool empty_public_hashes = false;  // hash empty byte strings into the statement (reference test-data generator)
+};
+
+struct FriProverState {
+    std::vector<DBuf<uint32_t>> evals;  // evals[0] = circle layer [4][2^m]; evals[i>=1] = line layers [4][2^(m-i)]
+    std::vector<DevMerkle> trees;       // one per committed layer
+    std::vector<int> logs;              // log size of each committed layer
+    std::vector<m31::QM31> last_poly;   // last-layer coefficients
+};
+
+FriProverState fri_commit(cb_ctx* ctx, host::Channel& ch, const PcsConfig& cfg, DBuf<uint32_t>&& quot, int m);
+std::vector<uint8_t> fri_decommit(cb_ctx* ctx, FriProverState& fri, const PcsConfig& cfg, const std::vector<uint32_t>& queries);
+uint64_t grind(cb_ctx* ctx, const host::Channel& ch, uint32_t pow_bits);
+m31::QM31 coset_vanishing_q(int trace_log, const host::CirclePointQ& z);
+
+size_t stark_proof_size_estimate(const uint8_t* p, size_t len, size_t stark_off);
+
+std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof, ProveOptions opt = ProveOptions());
