@@ -1,0 +1,290 @@
+#!/usr/bin/env python3
+"""bench.py -- ChaCha20 stwo proofs/sec on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA backend (through the C ABI)
+  python bench.py --impl reference --gpus N ...            the reference's own CPU prover (oracle/_ref = its shipped WASM
+                                                           build compiled natively; single-threaded like the reference)
+
+A step = one ChaCha20 stream proof (prove only) of 2^log_n_rows 64-byte blocks of synthetic data, PcsConfig::default().
+`value`  : whole-job proofs/s with plaintext/ciphertext already resident in HBM (device-input entry point).
+`e2e`    : same through the host-buffer C-ABI call (pinned host inputs -> H2D inside, proof bytes D2H inside).
+Independent proofs shard across ranks with no data-path collective ("weak" scaling: one proof per GPU per step).
+"""
+import argparse
+import ctypes
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_COLS = 33280
+N_CONSTRAINTS = 54784
+
+
+def synth_inputs(log_n, rank):
+    """Deterministic synthetic workload: key 00..1f, nonce per rank, counter 1, plaintext = seeded random bytes,
+    ciphertext = ChaCha20 keystream xor plaintext (computed with numpy; test data only)."""
+    import numpy as np
+    n = 1 << log_n
+    key = bytes(range(32))
+    nonce = bytes([0, 0, 0, rank, 0, 0, 0, 0x4A, 0, 0, 0, 0])
+    counter = 1
+    rng = np.random.default_rng(1000 + rank)
+    pt = rng.integers(0, 2 ** 32, size=(n, 16), dtype=np.uint64).astype(np.uint32)
+    kw = np.frombuffer(key, dtype="<u4").astype(np.uint32)
+    nw = np.frombuffer(nonce, dtype="<u4").astype(np.uint32)
+    init = np.empty((16, n), dtype=np.uint32)
+    init[0], init[1], init[2], init[3] = 0x61707865, 0x3320646E, 0x79622D32, 0x6B206574
+    for i in range(8):
+        init[4 + i] = kw[i]
+    init[12] = (counter + np.arange(n, dtype=np.uint64)).astype(np.uint32)
+    for i in range(3):
+        init[13 + i] = nw[i]
+    v = init.copy()
+
+    def rotl(x, r):
+        return (x << np.uint32(r)) | (x >> np.uint32(32 - r))
+
+    def qr(a, b, c, d):
+        v[a] += v[b]; v[d] = rotl(v[d] ^ v[a], 16); v[c] += v[d]; v[b] = rotl(v[b] ^ v[c], 12)
+        v[a] += v[b]; v[d] = rotl(v[d] ^ v[a], 8); v[c] += v[d]; v[b] = rotl(v[b] ^ v[c], 7)
+
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        ks = (v + init).T
+    ct = pt ^ ks
+    return key, nonce, counter, np.ascontiguousarray(pt), np.ascontiguousarray(ct)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.lines = []
+        self.proc = None
+        self.gpu = gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1].split()[0])); mx = max(mx, float(f[2].split()[0]))
+            except Exception:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(log_sample, steps, warmup):
+    """Times the reference's own prover (oracle/_ref) on this box's host cores: 2^log_sample blocks per proof."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_wasm
+    import numpy as np
+    key, nonce, counter, pt, ct = synth_inputs(log_sample, 0)
+    ptb, ctb = pt.tobytes(), ct.tobytes()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = ref_wasm.generate_chacha20_proof(key, nonce, counter, ptb, ctb)
+        dt = time.perf_counter() - t0
+        assert res.get("success") is True, res
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--log-size", type=int, default=int(os.environ.get("S2C_BENCH_LOG", "16")))
+    ap.add_argument("--cpu-log-size", type=int, default=9, help="size of the bounded CPU-reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    L = args.log_size
+    workload = "chacha20_stream log_n_rows=%d blowup=2 (one proof of %d blocks per GPU per step)" % (L, 1 << L)
+    config = {"workload": workload, "log_n_rows": L, "columns": N_COLS, "constraints": N_CONSTRAINTS,
+              "pcs": "pow_bits=10,n_queries=3,log_blowup=1,last_layer=0", "l2": "inputs larger than L2 (LDE %.1f GB)" %
+              (N_COLS * (2 << L) * 4 / 1e9), "sharding": "independent proofs, one per rank, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        S = args.cpu_log_size
+        sec = cpu_reference_run(S, max(1, min(args.steps, 3)), 1 if args.warmup else 0)
+        # scale to the workload's unit: prover cost is ~linear in rows at fixed column count (optimistic for the CPU)
+        scaled = 1.0 / (sec * (1 << (L - S))) if L >= S else 1.0 / sec
+        line = {"impl": "reference", "metric": "chacha20_proofs_per_sec", "value": scaled, "unit": "proofs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / scaled, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32(M31)", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": scaled, "unit": "proofs/s", "cores": 1, "kind": "reference",
+                                 "sample": "reference prover (shipped WASM build compiled natively, single-threaded as shipped) on "
+                                           "2^%d blocks: %.3f s/proof, linearly scaled to 2^%d blocks" % (S, sec, L)},
+                "e2e": {"value": scaled, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_symmetric_crypto_b200 as z
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = z.Backend(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    be.set_stream(stream.cuda_stream)
+    key, nonce, counter, pt, ct = synth_inputs(L, rank)
+    nbytes = pt.nbytes
+    # pinned host copies (e2e path) and device-resident copies (value path)
+    pt_pin = torch.from_numpy(pt.view(np.int32)).pin_memory()
+    ct_pin = torch.from_numpy(ct.view(np.int32)).pin_memory()
+    pt_dev = pt_pin.to("cuda:%d" % local_rank)
+    ct_dev = ct_pin.to("cuda:%d" % local_rank)
+    pt_hash = hashlib.blake2s(pt.tobytes()).digest()
+    ct_hash = hashlib.blake2s(ct.tobytes()).digest()
+
+    def step_dev():
+        return be.prove_chacha20_ptr(key, nonce, counter, pt_dev.data_ptr(), ct_dev.data_ptr(), nbytes, on_device=True,
+                                     pt_hash=pt_hash, ct_hash=ct_hash)
+
+    def step_e2e():
+        return be.prove_chacha20_ptr(key, nonce, counter, pt_pin.data_ptr(), ct_pin.data_ptr(), nbytes)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            proof = fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        ms = dev_ms  # device clock on the launching stream (the proof call is host-synchronous, so this is the step time)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1000.0
+        return ms, wall, proof
+
+    for _ in range(max(args.warmup, 3)):
+        proof = step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = be.launch_count()
+    ms, wall, proof = timed(step_dev, args.steps)
+    launches = be.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e, wall_e2e, proof_e2e = timed(step_e2e, args.steps)
+    assert proof_e2e == proof, "host-input and device-input paths must give the same proof"
+    # one profiled step for the per-kernel breakdown (CUDA events on the launching stream around each kernel)
+    be.set_profile(True)
+    step_dev()
+    stages = be.stage_times()
+    be.set_profile(False)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        N = 1 << L
+        # algorithmic bytes per launch: words moved x 4 B
+        alg = {
+            "ifft_low": N_COLS * N * 4 * (1 / 32 + 1),          # read packed bits (1/32 word per value), write N
+            "fft_mid": N_COLS * N * 4 * (1 + 1 + 2),            # read N, write N coefficients, write 2N
+            "fft_low": N_COLS * N * 4 * (2 + 2),                # read 2N, write 2N
+            "fft_small": N_COLS * N * 4 * (1 / 32 + 1 + 2),     # fused small-size kernel: bits in, coeffs + LDE out
+            "trace_merkle_leaves": N_COLS * N * 4 * 2 + 2 * N * 32,
+            "constraints": N_COLS * N * 4 * 2 + 4 * 2 * N * 4,
+            "quotients": (N_COLS + 8) * N * 4 * 2 + 4 * 2 * N * 4,
+        }
+        top = max((k for k in stages if k in alg), key=lambda k: stages[k], default=None)
+        roofline = None
+        if top:
+            achieved = alg[top] / (stages[top] / 1000.0) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg[top], "launch_ms": stages[top],
+                        "all_kernels_gbs": {k: alg[k] / (stages[k] / 1000.0) / 1e9 for k in stages if k in alg}}
+        value = world * args.steps / (ms / 1000.0)
+        e2e_value = world * args.steps / (ms_e2e / 1000.0)
+        line = {"metric": "chacha20_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32(M31)", "data": "synthetic", "config": config,
+                "blocks_per_sec": value * N, "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": len(proof_e2e),
+                        "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1000.0 / args.steps},
+                "wall_ms_per_step": wall * 1000.0 / args.steps, "stage_ms": stages, "roofline": roofline}
+        if not args.no_cpu_baseline:
+            S = args.cpu_log_size
+            try:
+                sec = cpu_reference_run(S, 1, 0)
+                scaled = 1.0 / (sec * (1 << (L - S))) if L >= S else 1.0 / sec
+                line["cpu_baseline"] = {"value": scaled, "unit": "proofs/s", "cores": 1, "kind": "reference",
+                                        "sample": "reference prover (oracle/_ref: shipped WASM build compiled natively, 1 thread as "
+                                                  "shipped) on 2^%d blocks: %.3f s/proof, linearly scaled to 2^%d blocks" % (S, sec, L)}
+            except Exception as ex:  # oracle/_ref absent on this box
+                line["cpu_baseline"] = {"value": None, "unit": "proofs/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % ex}
+        print(json.dumps(line))
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,11 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
 /* Raw form used by the benchmark and tests: proof bytes (bincode StreamProof) instead of base64-in-JSON. */
 int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            const uint8_t* ciphertext, size_t len, uint8_t** proof_out, size_t* proof_len);
+/* Same, with plaintext/ciphertext already resident in device memory (pt_dev/ct_dev: len bytes each) and the two Blake2s
+ * public-input hashes supplied by the caller; used to time the prover with inputs in HBM. */
+int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const void* pt_dev,
+                           const void* ct_dev, size_t len, const uint8_t pt_hash[32], const uint8_t ct_hash[32],
+                           uint8_t** proof_out, size_t* proof_len);
 /* Per-stage device times (ms) of the last proof on ctx when profiling is enabled: "name=ms;name=ms;..." */
 int cb_set_profile(cb_ctx* ctx, int enable);
 const char* cb_stage_times(cb_ctx* ctx);

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
     "cb_gen_trace_chacha_stream",
-    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "cb_set_profile", "cb_stage_times",
+    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
 ]
 
@@ -135,6 +135,29 @@ class Backend:
         n = ctypes.c_size_t()
         rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,
                                            ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n))
+        self._ck(rc)
+        proof = ctypes.string_at(out, n.value)
+        self.L.s2c_free(out)
+        return proof
+
+    def set_stream(self, cuda_stream_ptr):
+        """Run this context's work on an existing CUDA stream (e.g. torch.cuda.Stream().cuda_stream)."""
+        self._ck(self.L.cb_set_stream(self.ctx, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def prove_chacha20_ptr(self, key, nonce, counter, pt_ptr, ct_ptr, nbytes, on_device=False, pt_hash=None, ct_hash=None):
+        """Raw-pointer form: host pointers (e.g. pinned memory) or, with on_device=True, device pointers plus the two
+        public-input hashes.  Returns the proof bytes."""
+        kb, _ = _bytes(key)
+        nb, _ = _bytes(nonce)
+        out = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        if on_device:
+            rc = self.L.s2c_prove_chacha20_dev(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), ctypes.c_void_p(pt_ptr),
+                                               ctypes.c_void_p(ct_ptr), ctypes.c_size_t(nbytes), bytes(pt_hash), bytes(ct_hash),
+                                               ctypes.byref(out), ctypes.byref(n))
+        else:
+            rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), ctypes.c_void_p(pt_ptr),
+                                               ctypes.c_void_p(ct_ptr), ctypes.c_size_t(nbytes), ctypes.byref(out), ctypes.byref(n))
         self._ck(rc)
         proof = ctypes.string_at(out, n.value)
         self.L.s2c_free(out)

@@ -395,6 +395,28 @@ int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     CB_CATCH(ctx)
 }
 
+int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const void* pt_dev,
+                           const void* ct_dev, size_t len, const uint8_t pt_hash[32], const uint8_t ct_hash[32],
+                           uint8_t** proof_out, size_t* proof_len) {
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (len == 0 || len % 64) throw CbError("Plaintext must be non-empty multiple of 64 bytes, got " + std::to_string(len));
+    ProveOptions opt;
+    opt.pt_dev = (const uint32_t*)pt_dev;
+    opt.ct_dev = (const uint32_t*)ct_dev;
+    opt.pt_hash = pt_hash;
+    opt.ct_hash = ct_hash;
+    std::vector<uint8_t> proof;
+    std::string e = prove_chacha20(ctx, key, nonce, counter, nullptr, nullptr, len, proof, opt);
+    if (!e.empty()) throw CbError(e);
+    uint8_t* p = (uint8_t*)malloc(proof.size());
+    memcpy(p, proof.data(), proof.size());
+    *proof_out = p;
+    *proof_len = proof.size();
+    CB_CATCH(ctx)
+}
+
 // StarkProof::size_estimate() of the reference is reported as proof_size_bytes; see estimate in prove driver notes.
 int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
                                 uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,

@@ -43,7 +43,13 @@ struct QuotBatch {
     int n_cols;
 };
 
+// optional per-kernel profiling callback (begin=1 before a launch, begin=0 after it)
+struct StageHook {
+    void (*fn)(void* user, const char* name, int begin);
+    void* user;
+};
+
 cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n, int ext, int mode, uint32_t* coef_out,
                        size_t coef_stride, uint32_t* eval_out, size_t eval_stride, const FftTables& tw, uint32_t* scratch,
-                       size_t scratch_stride);
+                       size_t scratch_stride, const StageHook* hook = nullptr);
 void fft_init_attrs();

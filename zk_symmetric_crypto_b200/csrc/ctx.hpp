@@ -45,6 +45,11 @@ struct cb_ctx {
     void stage_begin(const char* name);
     void stage_end();
     void collect_stages();
+    static void hook_fn(void* user, const char* name, int begin) {
+        cb_ctx* c = (cb_ctx*)user;
+        if (begin) c->stage_begin(name); else c->stage_end();
+    }
+    StageHook hook() { return StageHook{&cb_ctx::hook_fn, this}; }
 };
 
 // RAII device buffer on the context's stream-ordered pool
@@ -113,5 +118,5 @@ cudaError_t launch_secure_powers_rev(cudaStream_t st, m31::QM31 alpha, int K, ui
 
 
 // shared prover building blocks (prover_common.cu)
-DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log);
+DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log, const char* leaf_stage = nullptr);
 std::vector<host::Hash32> merkle_decommit(cb_ctx* ctx, const DevMerkle& t, const std::vector<uint32_t>& positions);

@@ -201,16 +201,19 @@ void fft_init_attrs() {
 // When mode&1 is clear the source must be an M31 array of coefficients.
 cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n, int ext, int mode, uint32_t* coef_out,
                        size_t coef_stride, uint32_t* eval_out, size_t eval_stride, const FftTables& tw, uint32_t* scratch,
-                       size_t scratch_stride) {
+                       size_t scratch_stride, const StageHook* hook) {
     using namespace fftk;
+#define HOOK(name, b) do { if (hook) hook->fn(hook->user, name, b); } while (0)
     if (ncols <= 0) return cudaSuccess;
     const int m = log_n + ext;
     if (m <= 13) {
         int big = 1 << m;
         int cpb = max(1, 4096 / big);
         size_t smem = (size_t)cpb * big * 4;
+        HOOK("fft_small", 1);
         fft_small_kernel<<<(ncols + cpb - 1) / cpb, 256, smem, st>>>(src, ncols, log_n, ext, mode, cpb, coef_out, coef_stride,
                                                                        eval_out, eval_stride, tw);
+        HOOK("fft_small", 0);
         return cudaGetLastError();
     }
     // multi-pass.  k1 = contiguous tile bits; strided pass holds 2^(m-k1) x Q words.
@@ -225,7 +228,9 @@ cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n,
     if (mode & 1) {
         // pass 1 writes to scratch (may alias coef_out; every element is read and written by the same block)
         dim3 g1((1u << log_n) / T, (ncols + cpb - 1) / cpb);
+        HOOK("ifft_low", 1);
         ifft_low_kernel<<<g1, 256, (size_t)cpb * T * 4, st>>>(src, ncols, log_n, k1, cpb, scratch, scratch_stride, tw);
+        HOOK("ifft_low", 0);
         mid_in = scratch;
         mid_stride = scratch_stride;
     } else {
@@ -234,11 +239,15 @@ cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n,
     }
     dim3 g2(T >> qbits, ncols);
     size_t smem2 = ((size_t)1 << (m - k1 + qbits)) * 4;
+    HOOK("fft_mid", 1);
     fft_mid_kernel<<<g2, 512, smem2, st>>>(mid_in, mid_stride, ncols, log_n, k1, ext, qbits, mode, coef_out, coef_stride,
                                            eval_out, eval_stride, tw);
+    HOOK("fft_mid", 0);
     if (mode & 4) {
         dim3 g3((1u << m) / T, (ncols + cpb - 1) / cpb);
+        HOOK("fft_low", 1);
         fft_low_kernel<<<g3, 256, (size_t)cpb * T * 4, st>>>(eval_out, eval_stride, ncols, m, k1, cpb, tw);
+        HOOK("fft_low", 0);
     }
     return cudaGetLastError();
 }

@@ -114,12 +114,19 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- witness
     ctx->stage_begin("witness");
-    DBuf<uint32_t> d_pt(ctx, len / 4), d_ct(ctx, len / 4), W(ctx, (size_t)N_WORDS * N);
+    DBuf<uint32_t> d_pt, d_ct, W(ctx, (size_t)N_WORDS * N);
     DBuf<int> d_invalid(ctx, 1);
-    CB_CUDA(cudaMemcpyAsync(d_pt.p, plaintext, len, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(d_ct.p, ciphertext, len, cudaMemcpyHostToDevice, st));
+    const uint32_t *pt_d = opt.pt_dev, *ct_d = opt.ct_dev;
+    if (!pt_d) {
+        d_pt = DBuf<uint32_t>(ctx, len / 4);
+        d_ct = DBuf<uint32_t>(ctx, len / 4);
+        CB_CUDA(cudaMemcpyAsync(d_pt.p, plaintext, len, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(d_ct.p, ciphertext, len, cudaMemcpyHostToDevice, st));
+        pt_d = d_pt.p;
+        ct_d = d_ct.p;
+    }
     CB_CUDA(cudaMemsetAsync(d_invalid.p, 0, sizeof(int), st));
-    CB_CUDA(launch_chacha_witness(st, key_w, nonce_w, counter, num_blocks, rows_needed * 16, d_pt.p, d_ct.p, n, W.p, N, d_invalid.p));
+    CB_CUDA(launch_chacha_witness(st, key_w, nonce_w, counter, num_blocks, rows_needed * 16, pt_d, ct_d, n, W.p, N, d_invalid.p));
     ctx->launches++;
     ctx->stage_end();
     int invalid = 0;
@@ -132,8 +139,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     host::put_u32(stmt, (uint32_t)log_size);
     host::put_bytes(stmt, nonce, 12);
     host::put_u32(stmt, counter);
-    Hash32 pth = host::blake2s_bytes(plaintext, len), cth = host::blake2s_bytes(ciphertext, len);
-    if (opt.empty_public_hashes) { pth = host::blake2s_bytes(nullptr, 0); cth = pth; }
+    Hash32 pth, cth;
+    if (opt.pt_hash) {
+        memcpy(pth.b, opt.pt_hash, 32);
+        memcpy(cth.b, opt.ct_hash, 32);
+    } else if (opt.empty_public_hashes) {
+        pth = host::blake2s_bytes(nullptr, 0);
+        cth = pth;
+    } else {
+        pth = host::blake2s_bytes(plaintext, len);
+        cth = host::blake2s_bytes(ciphertext, len);
+    }
     host::put_bytes(stmt, pth.b, 32);
     host::put_bytes(stmt, cth.b, 32);
     ch.mix_u64((uint64_t)log_size);
@@ -142,20 +158,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
 
     // ---- tree 1: interpolate + LDE + Merkle
-    ctx->stage_begin("commit_trace_fft");
     DBuf<uint32_t> coeffs(ctx, (size_t)N_COLS * N), lde(ctx, (size_t)N_COLS * M);
     {
         ColSrc src{SRC_BITS, W.p, N, 0};
-        CB_CUDA(launch_fft(st, src, N_COLS, n, cfg.log_blowup, 1 | 2 | 4, coeffs.p, N, lde.p, M, ctx->tw, coeffs.p, N));
+        StageHook hk = ctx->hook();
+        CB_CUDA(launch_fft(st, src, N_COLS, n, cfg.log_blowup, 1 | 2 | 4, coeffs.p, N, lde.p, M, ctx->tw, coeffs.p, N, &hk));
         ctx->launches += (m <= 13) ? 1 : 3;
     }
-    ctx->stage_end();
-    ctx->stage_begin("commit_trace_merkle");
     LeafGroups g1{};
     g1.n = 1;
     g1.g[0] = {lde.p, M, N_COLS, m};
-    DevMerkle tree1 = build_merkle(ctx, g1, m);
-    ctx->stage_end();
+    DevMerkle tree1 = build_merkle(ctx, g1, m, "trace_merkle_leaves");
     roots.push_back(tree1.root);
     ch.mix_root(tree1.root);
 

@@ -24,6 +24,12 @@ struct PcsConfig {
 struct ProveOptions {
     int force_log_size = 0;            // prove on a larger trace than the block count needs (rows beyond are default rows)
     bool empty_public_hashes = false;  // hash empty byte strings into the statement (reference test-data generator)
+    // plaintext/ciphertext already resident on the device (skips the H2D copies); the caller then supplies the two
+    // Blake2s public-input hashes (ChaChaPublicInputs::new, air_stream.rs:44-53), which are host work in the reference too
+    const uint32_t* pt_dev = nullptr;
+    const uint32_t* ct_dev = nullptr;
+    const uint8_t* pt_hash = nullptr;
+    const uint8_t* ct_hash = nullptr;
 };
 
 struct FriProverState {

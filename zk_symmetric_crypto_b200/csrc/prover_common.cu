@@ -52,13 +52,15 @@ void cb_ctx::collect_stages() {
     pending_events.clear();
 }
 
-DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log) {
+DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log, const char* leaf_stage) {
     DevMerkle t;
     t.log_leaves = lifting_log;
     size_t n_hashes = ((size_t)2 << lifting_log) - 1;
     t.nodes = DBuf<uint32_t>(ctx, n_hashes * 8);
+    if (leaf_stage) ctx->stage_begin(leaf_stage);
     CB_CUDA(launch_merkle_leaves(ctx->stream, groups, lifting_log, nullptr, 0, 1, 1, t.nodes.p));
     ctx->launches++;
+    if (leaf_stage) ctx->stage_end();
     for (int l = 0; l < lifting_log; l++) {
         const uint32_t* prev = t.nodes.p + t.layer_offset(l) * 8;
         uint32_t* out = t.nodes.p + t.layer_offset(l + 1) * 8;
