@@ -62,6 +62,13 @@ int cb_evaluate_polynomials(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, 
  * 2 = packed bytes (column j = byte j&3 of word j>>2); for packed kinds `src_stride` is the word-row stride. */
 int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* src, size_t src_stride, uint32_t first_col, int n_cols, int log_size,
                   int log_ext, uint32_t* coeffs_out, size_t coeff_stride, uint32_t* lde_out, size_t lde_stride);
+/* Packed-witness form of the same fused interpolate+extend (blow-up 2): `src_words` = n_words rows of 2^log_size packed
+ * words (src_kind 1: 32 one-bit columns per word, 2: 4 byte columns per word); tiles_out = n_words tiles of
+ * [32 or 4][2^(log_size+1)] LDE values.  This is the transform the streaming provers use (coefficients stay on chip). */
+int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out);
+/* Streaming provers keep as many LDE tiles as device memory allows between the commitment pass and the constraint pass;
+ * this caps that number (0 = recompute every tile, -1 = default).  Results do not depend on it. */
+int cb_set_max_cached_tiles(cb_ctx* ctx, int n_tiles);
 /* PolyOps::eval_at_point for n_cols polynomials at one point of the QM31 circle; point_host = {x[4], y[4]},
  * out_host = n_cols x 4 words. */
 int cb_eval_at_point(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, const uint32_t point_host[8],

@@ -64,6 +64,35 @@ def test_interpolate_evaluate(backend, log_n):
         be.free(p)
 
 
+@pytest.mark.parametrize("log_n,kind", [(4, 1), (5, 1), (8, 1), (11, 1), (12, 1), (13, 1), (14, 1), (16, 1), (18, 1), (20, 1),
+                                        (22, 1), (6, 2), (12, 2), (15, 2)])
+def test_lde_packed(backend, log_n, kind):
+    """Packed-witness fused interpolate+extend (the transform of the streaming prover) against the oracle's circle
+    iFFT/FFT, for every kernel schedule: whole-column (<=12), three-pass (>=13), padded strided tiles (>=22)."""
+    be = backend
+    rng = np.random.default_rng(100 + log_n)
+    n, m = 1 << log_n, 2 << log_n
+    n_words = 3 if log_n <= 16 else 1
+    cpj = 32 if kind == 1 else 4
+    words = rng.integers(0, 1 << 32, size=(n_words, n), dtype=np.uint64).astype(np.uint32)
+    d_w = be.upload(words)
+    d_t = be.malloc(n_words * cpj * m * 4)
+    be._ck(be.L.cb_lde_packed(be.ctx, kind, d_w, n_words, log_n, d_t))
+    tiles = be.download(d_t, (n_words, cpj, m))
+    check_cols = range(cpj) if log_n <= 14 else ([0, 13, 31] if kind == 1 else [0, 3])
+    for w in range(n_words):
+        wv = words[w].astype(np.uint64)
+        if kind == 1:
+            cols = np.stack([(wv >> np.uint64(c)) & np.uint64(1) for c in check_cols])
+        else:
+            cols = np.stack([(wv >> np.uint64(8 * c)) & np.uint64(0xFF) for c in check_cols])
+        lde = sc.circle_fft(sc.circle_ifft(cols), log_n + 1)
+        for i, c in enumerate(check_cols):
+            assert np.array_equal(tiles[w, c], lde[i]), (w, c)
+    be.free(d_w)
+    be.free(d_t)
+
+
 def _witness(be, nb, seed):
     key, nonce, counter, pt, ct = case_inputs(nb, seed)
     log, K, NO, C, PT, CT, mrows = oracle_api.build_chacha_inputs(key, nonce, counter, pt, ct)
@@ -207,6 +236,18 @@ def test_proof_matches_oracle_bytes(backend):
     want = oracle_api.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof_bytes"]
     got = backend.prove_chacha20_raw(key, nonce, counter, pt, ct)
     assert got == want
+
+
+def test_proof_independent_of_tile_cache(backend):
+    """The streaming prover recomputes LDE tiles that do not fit the cache; the proof must not depend on the cache size."""
+    key, nonce, counter, pt, ct = case_inputs(16, 33)
+    want = backend.prove_chacha20_raw(key, nonce, counter, pt, ct)
+    for cap in (0, 100):
+        backend._ck(backend.L.cb_set_max_cached_tiles(backend.ctx, cap))
+        try:
+            assert backend.prove_chacha20_raw(key, nonce, counter, pt, ct) == want
+        finally:
+            backend._ck(backend.L.cb_set_max_cached_tiles(backend.ctx, -1))
 
 
 def test_error_behaviour(backend):

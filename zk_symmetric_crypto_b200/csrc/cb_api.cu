@@ -35,6 +35,7 @@ int cb_init(int device, cb_ctx** out) {
         uint64_t thr = UINT64_MAX;
         CB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         fft_init_attrs();
+        fft2_init_attrs();
         chacha_init_attrs();
     } catch (const std::exception& ex) {
         delete ctx;
@@ -148,6 +149,37 @@ int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* srcp, size_t src_st
                        sc_stride));
     ctx->launches += log_size + log_ext <= 13 ? 1 : 3;
     CB_CATCH(ctx)
+}
+
+int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out) {
+    CB_TRY(ctx)
+    if (src_kind != SRC_BITS && src_kind != SRC_BYTES) throw CbError("cb_lde_packed: src_kind must be 1 (bits) or 2 (bytes)");
+    if (log_size < 1 || log_size > 24) throw CbError("cb_lde_packed: log_size out of range");
+    ctx->ensure_twiddles(log_size + 1);
+    const int cpj = src_kind == SRC_BITS ? 32 : 4;
+    const int batch = n_words < MAX_FFT_JOBS ? n_words : MAX_FFT_JOBS;
+    DBuf<uint32_t> scratch(ctx, fft_packed_scratch_words(src_kind, batch, log_size));
+    std::vector<const uint32_t*> src(n_words);
+    std::vector<uint32_t*> out(n_words);
+    for (int w = 0; w < n_words; w++) {
+        src[w] = src_words + ((size_t)w << log_size);
+        out[w] = tiles_out + (((size_t)w * cpj) << (log_size + 1));
+    }
+    int nl = 0;
+    StageHook hk = ctx->hook();
+    ctx->pending_events.clear();
+    CB_CUDA(launch_fft_packed(ctx->stream, src_kind, src.data(), out.data(), n_words, log_size, ctx->tw, scratch.p,
+                              ctx->profile ? &hk : nullptr, &nl));
+    ctx->launches += nl;
+    ctx->collect_stages();
+    ctx->sync();
+    CB_CATCH(ctx)
+}
+
+int cb_set_max_cached_tiles(cb_ctx* ctx, int n_tiles) {
+    if (!ctx) return 1;
+    ctx->max_cached_tiles = n_tiles;
+    return 0;
 }
 
 int cb_eval_at_point(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, const uint32_t pt[8],

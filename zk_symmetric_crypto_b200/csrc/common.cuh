@@ -27,7 +27,7 @@ struct LeafGroup {
     int ncols;
     int log_size;
 };
-#define MAX_LEAF_GROUPS 8
+#define MAX_LEAF_GROUPS 16
 struct LeafGroups {
     LeafGroup g[MAX_LEAF_GROUPS];
     int n;
@@ -43,6 +43,30 @@ struct QuotBatch {
     int n_cols;
 };
 
+// ---- streaming prover job lists (passed to kernels by value) ----
+#define MAX_FFT_JOBS 16
+struct CombineJob {
+    const uint32_t *a, *b, *c;  // operand tiles and carry tile, [32][M] each
+    uint32_t* res;              // sum tile (may alias a)
+};
+#define MAX_COMBINE_JOBS 16
+struct CombineJobs {
+    CombineJob j[MAX_COMBINE_JOBS];
+    int n;
+};
+enum { CJ_BOOL = 0, CJ_XOR = 1, CJ_XORN = 2 };
+struct ConstraintJob {
+    const uint32_t *t0, *t1, *t2;  // tiles [32][M]
+    int k0;                        // index of the first constraint of the job in the reversed alpha-power table
+    int arg;                       // CJ_BOOL: constraint index step per bit; CJ_XOR*: left rotation
+    int type;
+};
+#define MAX_CONSTRAINT_JOBS 48
+struct ConstraintJobs {
+    ConstraintJob j[MAX_CONSTRAINT_JOBS];
+    int n;
+};
+
 // optional per-kernel profiling callback (begin=1 before a launch, begin=0 after it)
 struct StageHook {
     void (*fn)(void* user, const char* name, int begin);
@@ -53,3 +77,16 @@ cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n,
                        size_t coef_stride, uint32_t* eval_out, size_t eval_stride, const FftTables& tw, uint32_t* scratch,
                        size_t scratch_stride, const StageHook* hook = nullptr);
 void fft_init_attrs();
+void fft2_init_attrs();
+size_t fft_packed_scratch_words(int kind, int njobs, int log_n);
+cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches);
+cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t M);
+cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr, uint32_t* acc,
+                                     int first);
+cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv);
+cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
+                              uint32_t* out);
+cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g);
+cudaError_t launch_basis4(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const uint32_t init[4],
+                          const uint32_t (*maps)[4]);

@@ -36,6 +36,7 @@ struct cb_ctx {
     bool profile = false;
     std::vector<StageTime> stages;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    int max_cached_tiles = -1;  // streaming prover: cap on LDE tiles kept between passes (-1 = as many as memory allows)
     uint64_t launches = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
 
     void ensure_twiddles(int max_log);

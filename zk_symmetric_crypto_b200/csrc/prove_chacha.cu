@@ -7,6 +7,7 @@
 // The Fiat-Shamir channel (tiny Blake2s calls) stays on the host; every heavy step is a kernel from kernels_*.cu.
 // Output bytes = bincode(StreamProof{stmt, stark_proof}) exactly as the reference serialises it
 // (air_stream.rs:30-131, wasm_api.rs:588): byte-identical to the reference, checked in tests/.
+#include <array>
 #include "prover.hpp"
 
 using namespace m31;
@@ -18,6 +19,7 @@ namespace {
 constexpr int N_COLS = 33280;
 constexpr int N_WORDS = 1040;
 constexpr int N_CONSTRAINTS = 54784;
+constexpr int N_INDEP_WORDS = 704;  // words transformed from the packed witness (all but the 336 adder sum words)
 
 // ---- host evaluation of the AIR on QM31 mask values (prove()'s closing sanity check; same sequence as the kernel) ----
 struct QAcc {
@@ -85,6 +87,155 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ streaming plan
+// Packed witness word indices (kernels_chacha.cu): 0..15 initial state | 80 quarter rounds x [sum,carry,xor]x4 |
+// 16 final adds x [sum,carry] | 16 plaintext | 16 ciphertext.  Sum words are "dependent" (combined from operand tiles,
+// kernels_stream.cu fact 1); all other words are transformed from the packed witness.
+namespace {
+
+struct Comb { int res, a, b, c; };
+struct CJ { int type, w0, w1, w2, k0, arg; };
+struct Group {
+    std::vector<int> fft;         // independent words transformed in this group
+    std::vector<Comb> comb;       // adder sum words, in dependency order
+    std::vector<int> hash;        // words absorbed into the Merkle leaves, in column order (<= MAX_LEAF_GROUPS)
+    std::vector<CJ> cons;         // constraints evaluated while the group's tiles are live (<= MAX_CONSTRAINT_JOBS)
+    std::vector<int> free_after;  // tiles dead after this group
+};
+
+std::vector<Group> build_plan() {
+    std::vector<Group> plan;
+    int state[16];
+    {
+        Group g;
+        for (int w = 0; w < 16; w++) {
+            state[w] = w;
+            g.fft.push_back(w);
+            g.hash.push_back(w);
+            g.cons.push_back({CJ_BOOL, w, -1, -1, 32 * w, 1});
+        }
+        plan.push_back(g);
+    }
+    static const int ROT[4] = {16, 12, 8, 7};
+    for (int q = 0; q < 80; q++) {
+        const int qi = q & 7, a0 = qi & 3;
+        int a = a0, b, c, d;
+        if (qi < 4) { b = 4 + a0; c = 8 + a0; d = 12 + a0; }
+        else { b = 4 + ((a0 + 1) & 3); c = 8 + ((a0 + 2) & 3); d = 12 + ((a0 + 3) & 3); }
+        const int base = 16 + 12 * q, kb = 512 + 640 * q;
+        const int S1 = base, C1 = base + 1, X1 = base + 2, S2 = base + 3, C2 = base + 4, X2 = base + 5, S3 = base + 6,
+                  C3 = base + 7, X3 = base + 8, S4 = base + 9, C4 = base + 10, X4 = base + 11;
+        Group g;
+        g.fft = {C1, X1, C2, X2, C3, X3, C4, X4};
+        g.comb = {{S1, state[a], state[b], C1}, {S2, state[c], X1, C2}, {S3, S1, X2, C3}, {S4, S2, X3, C4}};
+        for (int w = base; w < base + 12; w++) g.hash.push_back(w);
+        const int S[4] = {S1, S2, S3, S4}, C[4] = {C1, C2, C3, C4}, X[4] = {X1, X2, X3, X4};
+        const int XD[4] = {state[d], state[b], X1, X2};  // second xor operand (the rotated word's previous value)
+        for (int t = 0; t < 4; t++) {
+            const int k = kb + 160 * t;
+            g.cons.push_back({CJ_BOOL, S[t], -1, -1, k, 1});
+            g.cons.push_back({CJ_BOOL, C[t], -1, -1, k + 32, 2});
+            g.cons.push_back({CJ_BOOL, X[t], -1, -1, k + 96, 1});
+            g.cons.push_back({CJ_XOR, X[t], S[t], XD[t], k + 128, ROT[t]});
+        }
+        for (int w : {state[a], state[b], state[c], state[d]})
+            if (w >= 16) g.free_after.push_back(w);
+        for (int w : {S1, C1, X1, S2, C2, X2, C3, C4}) g.free_after.push_back(w);
+        state[a] = S3; state[b] = X4; state[c] = S4; state[d] = X3;
+        plan.push_back(g);
+    }
+    const int kf = 512 + 640 * 80, k_pt = kf + 96 * 16, k_ct = k_pt + 512, k_eq = k_ct + 512;
+    for (int half = 0; half < 2; half++) {
+        Group g;
+        for (int i = 8 * half; i < 8 * half + 8; i++) {
+            const int S = 976 + 2 * i, C = 977 + 2 * i;
+            g.fft.push_back(C);
+            g.comb.push_back({S, state[i], i, C});
+            g.hash.push_back(S);
+            g.hash.push_back(C);
+            g.cons.push_back({CJ_BOOL, S, -1, -1, kf + 96 * i, 1});
+            g.cons.push_back({CJ_BOOL, C, -1, -1, kf + 96 * i + 32, 2});
+            if (state[i] >= 16) g.free_after.push_back(state[i]);
+            g.free_after.push_back(C);
+            g.free_after.push_back(i);  // initial-state tile i is no longer needed
+        }
+        plan.push_back(g);
+    }
+    {
+        Group g;
+        for (int i = 0; i < 16; i++) {
+            g.fft.push_back(1008 + i);
+            g.hash.push_back(1008 + i);
+            g.cons.push_back({CJ_BOOL, 1008 + i, -1, -1, k_pt + 32 * i, 1});
+        }
+        plan.push_back(g);
+    }
+    {
+        Group g;
+        for (int i = 0; i < 16; i++) {
+            g.fft.push_back(1024 + i);
+            g.hash.push_back(1024 + i);
+            g.cons.push_back({CJ_BOOL, 1024 + i, -1, -1, k_ct + 32 * i, 1});
+            g.cons.push_back({CJ_XORN, 1024 + i, 976 + 2 * i, 1008 + i, k_eq + 32 * i, 0});
+            g.free_after.push_back(1024 + i);
+            g.free_after.push_back(1008 + i);
+            g.free_after.push_back(976 + 2 * i);
+        }
+        plan.push_back(g);
+    }
+    return plan;
+}
+
+// LDE tile slots: a cache of independent tiles that survives from the commitment pass to the constraint pass, plus
+// transient slots recycled as words die.
+struct Tiles {
+    int n_cache = 0, n_trans = 0, cache_used = 0;
+    size_t tile_words = 0;
+    uint32_t* arena = nullptr;
+    std::vector<int> slot_of, cache_slot, free_trans;
+    int in_use = 0, peak = 0;
+    void init(int cache, int trans, size_t tw_, uint32_t* mem) {
+        n_cache = cache; n_trans = trans; tile_words = tw_; arena = mem; cache_used = 0;
+        slot_of.assign(N_WORDS, -1);
+        cache_slot.assign(N_WORDS, -1);
+        free_trans.clear();
+        for (int i = trans - 1; i >= 0; i--) free_trans.push_back(i);
+        in_use = peak = 0;
+    }
+    uint32_t* ptr(int w) const {
+        if (slot_of[w] < 0) throw CbError("internal: tile of word " + std::to_string(w) + " is not live");
+        return arena + (size_t)slot_of[w] * tile_words;
+    }
+    // returns true when the tile must be (re)computed
+    bool acquire(int w, bool indep, int pass) {
+        if (indep && pass == 2 && cache_slot[w] >= 0) { slot_of[w] = cache_slot[w]; return false; }
+        if (indep && pass == 1 && cache_used < n_cache) { cache_slot[w] = cache_used++; slot_of[w] = cache_slot[w]; return true; }
+        if (free_trans.empty()) throw CbError("internal: transient tile slots exhausted");
+        slot_of[w] = n_cache + free_trans.back();
+        free_trans.pop_back();
+        if (++in_use > peak) peak = in_use;
+        return true;
+    }
+    void release(int w) {
+        if (slot_of[w] < 0) return;
+        if (slot_of[w] >= n_cache) { free_trans.push_back(slot_of[w] - n_cache); in_use--; }
+        slot_of[w] = -1;
+    }
+};
+
+int plan_peak_transient(const std::vector<Group>& plan) {
+    Tiles t;
+    t.init(0, N_WORDS, 0, nullptr);
+    for (auto& g : plan) {
+        for (int w : g.fft) t.acquire(w, true, 1);
+        for (auto& c : g.comb) t.acquire(c.res, false, 1);
+        for (int w : g.free_after) t.release(w);
+    }
+    return t.peak;
+}
+
+}  // namespace
+
 // Proves ChaCha20 encryption of `len` bytes (multiple of 64).  On success fills proof bytes (bincode StreamProof).
 // Returns "" on success, else the reference's error string.
 std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
@@ -98,9 +249,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const int n = log_size, m = n + cfg.log_blowup;  // trace / LDE domain logs
     const size_t N = (size_t)1 << n, M = (size_t)1 << m;
     const uint32_t rows_needed = (num_blocks + 15) / 16;
+    const uint32_t inv_n = 1u << (31 - n);
     cudaStream_t st = ctx->stream;
     ctx->ensure_twiddles(m);
     ctx->pending_events.clear();
+    StageHook hk = ctx->hook();
+    const StageHook* hkp = ctx->profile ? &hk : nullptr;
 
     uint32_t key_w[8], nonce_w[3];
     for (int i = 0; i < 8; i++) key_w[i] = host::load_le32(key + 4 * i);
@@ -112,7 +266,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     roots.push_back(host::blake2s_bytes(nullptr, 0));
     ch.mix_root(roots[0]);
 
-    // ---- witness
+    // ---- witness (packed: 1,040 words per row)
     ctx->stage_begin("witness");
     DBuf<uint32_t> d_pt, d_ct, W(ctx, (size_t)N_WORDS * N);
     DBuf<int> d_invalid(ctx, 1);
@@ -133,6 +287,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     CB_CUDA(cudaMemcpyAsync(&invalid, d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ctx->sync();
     if (invalid) return "Ciphertext does not match encryption - invalid witness";
+    d_pt.release();
+    d_ct.release();
 
     // ---- statement
     std::vector<uint8_t> stmt;
@@ -157,26 +313,103 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ch.mix_u64(counter);
     for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
 
-    // ---- tree 1: interpolate + LDE + Merkle
-    DBuf<uint32_t> coeffs(ctx, (size_t)N_COLS * N), lde(ctx, (size_t)N_COLS * M);
+    // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
+    static const std::vector<Group> plan = build_plan();
+    static const int peak_trans = plan_peak_transient(plan);
+    const size_t tile_words = 32 * M;
+    const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, MAX_FFT_JOBS, n);
+    int n_cache = N_INDEP_WORDS;
     {
-        ColSrc src{SRC_BITS, W.p, N, 0};
-        StageHook hk = ctx->hook();
-        CB_CUDA(launch_fft(st, src, N_COLS, n, cfg.log_blowup, 1 | 2 | 4, coeffs.p, N, lde.p, M, ctx->tw, coeffs.p, N, &hk));
-        ctx->launches += (m <= 13) ? 1 : 3;
+        size_t free_b = 0, total_b = 0;
+        CB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPool_t pool;
+        CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        uint64_t reserved = 0, used = 0;
+        CB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+        CB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+        const size_t avail = free_b + (size_t)(reserved - used);
+        // everything else this proof allocates: scratch, leaf state + tree (24 M words), accumulators / composition /
+        // quotient / FRI columns (~48 M words), plus slack for the allocator
+        const size_t other = (scratch_words + 96 * M) * 4 + ((size_t)3 << 30);
+        const size_t tile_bytes = tile_words * 4;
+        const size_t can = avail > other ? (avail - other) / tile_bytes : 0;
+        if (can < (size_t)peak_trans) throw CbError("not enough device memory for the tile arena at log_size " + std::to_string(n));
+        const int cap = opt.max_cached_tiles >= 0 ? opt.max_cached_tiles : ctx->max_cached_tiles;
+        if (cap >= 0 && n_cache > cap) n_cache = cap;
+        if ((size_t)n_cache > can - peak_trans) n_cache = (int)(can - peak_trans);
     }
-    LeafGroups g1{};
-    g1.n = 1;
-    g1.g[0] = {lde.p, M, N_COLS, m};
-    DevMerkle tree1 = build_merkle(ctx, g1, m, "trace_merkle_leaves");
+    DBuf<uint32_t> arena(ctx, (size_t)(n_cache + peak_trans) * tile_words);
+    DBuf<uint32_t> scratch(ctx, scratch_words);
+    Tiles tiles;
+    tiles.init(n_cache, peak_trans, tile_words, arena.p);
+
+    auto run_pass = [&](int pass, auto&& consume) {
+        for (size_t gi = 0; gi < plan.size(); gi++) {
+            const Group& g = plan[gi];
+            std::vector<const uint32_t*> src;
+            std::vector<uint32_t*> out;
+            for (int w : g.fft)
+                if (tiles.acquire(w, true, pass)) {
+                    src.push_back(W.p + (size_t)w * N);
+                    out.push_back(tiles.ptr(w));
+                }
+            if (!src.empty()) {
+                int nl = 0;
+                CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch.p, hkp, &nl));
+                ctx->launches += nl;
+            }
+            if (!g.comb.empty()) {
+                CombineJobs cj{};
+                for (auto& c : g.comb) {
+                    tiles.acquire(c.res, false, pass);
+                    cj.j[cj.n++] = {tiles.ptr(c.a), tiles.ptr(c.b), tiles.ptr(c.c), tiles.ptr(c.res)};
+                }
+                ctx->stage_begin("combine");
+                CB_CUDA(launch_combine_add(st, cj, M));
+                ctx->stage_end();
+                ctx->launches++;
+            }
+            consume(gi, g);
+            for (int w : g.free_after) tiles.release(w);
+        }
+        for (int w = 0; w < N_WORDS; w++) tiles.release(w);
+    };
+
+    // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree
+    DevMerkle tree1;
+    tree1.log_leaves = m;
+    tree1.nodes = DBuf<uint32_t>(ctx, (((size_t)2 << m) - 1) * 8);
+    {
+        DBuf<uint32_t> hstate(ctx, 8 * M);
+        uint64_t bytes_before = 0;
+        run_pass(1, [&](size_t gi, const Group& g) {
+            LeafGroups lg{};
+            lg.n = (int)g.hash.size();
+            for (int i = 0; i < lg.n; i++) lg.g[i] = {tiles.ptr(g.hash[i]), M, 32, m};
+            ctx->stage_begin("trace_merkle_leaves");
+            CB_CUDA(launch_merkle_leaves(st, lg, m, hstate.p, bytes_before, gi == 0, gi + 1 == plan.size(), tree1.nodes.p));
+            ctx->stage_end();
+            ctx->launches++;
+            bytes_before += 128ull * g.hash.size();
+        });
+        ctx->stage_begin("merkle_nodes");
+        for (int l = 0; l < m; l++) {
+            CB_CUDA(launch_merkle_nodes(st, tree1.nodes.p + tree1.layer_offset(l) * 8, 1u << (m - l - 1),
+                                        tree1.nodes.p + tree1.layer_offset(l + 1) * 8));
+            ctx->launches++;
+        }
+        ctx->stage_end();
+        CB_CUDA(cudaMemcpyAsync(tree1.root.b, tree1.nodes.p + tree1.layer_offset(m) * 8, 32, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
+    }
     roots.push_back(tree1.root);
     ch.mix_root(tree1.root);
 
-    // ---- composition polynomial
+    // ---- composition polynomial (pass 2): constraint quotients accumulated tile by tile
     QM31 random_coeff = ch.draw_secure_felt();
-    ctx->stage_begin("constraints");
     DBuf<uint32_t> apr(ctx, (size_t)N_CONSTRAINTS * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, 4 * M);
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
+    ctx->launches++;
     {
         std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);
         for (uint32_t i = 0; i < den.size(); i++) {
@@ -187,15 +420,28 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         CB_CUDA(cudaMemcpyAsync(d_den.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, st));
         ctx->sync();
     }
-    CB_CUDA(launch_chacha_constraints(st, lde.p, M, m, n, apr.p, d_den.p, acc.p, M, 0));
-    ctx->launches += 2;
-    ctx->stage_end();
+    run_pass(2, [&](size_t gi, const Group& g) {
+        ConstraintJobs cj{};
+        for (auto& c : g.cons)
+            cj.j[cj.n++] = {tiles.ptr(c.w0), c.w1 >= 0 ? tiles.ptr(c.w1) : nullptr, c.w2 >= 0 ? tiles.ptr(c.w2) : nullptr, c.k0, c.arg,
+                            c.type};
+        ctx->stage_begin("constraints");
+        CB_CUDA(launch_constraints_tiles(st, cj, M, apr.p, acc.p, gi == 0));
+        ctx->stage_end();
+        ctx->launches++;
+    });
+    CB_CUDA(launch_scale_rows(st, acc.p, M, n, d_den.p));
+    ctx->launches++;
+    arena.release();
+    scratch.release();
+
     ctx->stage_begin("composition_commit");
     // interpolate the 4 coordinate columns (log m), split into halves, evaluate each half (log n) on the LDE domain
-    DBuf<uint32_t> comp_coef(ctx, 4 * M), comp_lde(ctx, 8 * M), scratch(ctx, 4 * M);
+    DBuf<uint32_t> comp_coef(ctx, 4 * M), comp_lde(ctx, 8 * M);
     {
+        DBuf<uint32_t> scratch4(ctx, 4 * M);
         ColSrc src{SRC_M31, acc.p, M, 0};
-        CB_CUDA(launch_fft(st, src, 4, m, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw, scratch.p, M));
+        CB_CUDA(launch_fft(st, src, 4, m, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw, scratch4.p, M));
         for (int half = 0; half < 2; half++) {
             ColSrc cs{SRC_M31, comp_coef.p + half * N, M, 0};
             CB_CUDA(launch_fft(st, cs, 4, n, cfg.log_blowup, 4, nullptr, 0, comp_lde.p + (size_t)half * 4 * M, M, ctx->tw, nullptr, 0));
@@ -210,28 +456,33 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     roots.push_back(tree2.root);
     ch.mix_root(tree2.root);
 
-    // ---- OODS sampling
+    // ---- OODS sampling: f_j(z) = 2^-n <bits_j, (FFT with inverse twiddles)(basis(z))>  (kernels_stream.cu fact 2)
     host::CirclePointQ z = host::get_random_point(ch);
     ctx->stage_begin("oods");
     std::vector<QM31> sampled((size_t)N_COLS + 8);
+    const FftTables tw_t{ctx->tw.IX, ctx->tw.IY, ctx->tw.X, ctx->tw.Y, ctx->tw.max_log};  // transposed inverse transform
+    DBuf<uint32_t> basis(ctx, 4 * N), wt(ctx, 4 * N);
     {
         std::vector<QM31> maps(n);
         maps[0] = z.y;
         QM31 x = z.x;
         for (int j = 1; j < n; j++) { maps[j] = x; x = qsub(qmul_m(qmul(x, x), 2), qone()); }
-        DBuf<uint32_t> basis(ctx, 4 * N), d_sampled(ctx, ((size_t)N_COLS + 8) * 4);
+        DBuf<uint32_t> d_sampled(ctx, ((size_t)N_COLS + 8) * 4);
         CB_CUDA(launch_basis(st, basis.p, N, n, maps.data()));
-        CB_CUDA(launch_oods_dot(st, coeffs.p, N, N_COLS, n, basis.p, N, d_sampled.p));
+        ColSrc bs{SRC_M31, basis.p, N, 0};
+        CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
+        CB_CUDA(launch_bitcol_dot(st, W.p, N, N_WORDS, wt.p, inv_n, d_sampled.p));
         for (int half = 0; half < 2; half++)
             CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
-        ctx->launches += n + 3;
+        ctx->launches += n + 6;
         CB_CUDA(cudaMemcpyAsync(sampled.data(), d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
     }
     ctx->stage_end();
     ch.mix_felts(sampled.data(), sampled.size());
 
-    // ---- FRI quotients
+    // ---- FRI quotients: numerator of the 33,280 trace columns = extension of one row-wise combination of the packed
+    //      witness (kernels_stream.cu fact 3); the 8 composition columns are read from their LDE
     QM31 rc = ch.draw_secure_felt();
     ctx->stage_begin("quotients");
     DBuf<uint32_t> quot(ctx, 4 * M);
@@ -250,17 +501,24 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             for (int k = 0; k < 4; k++) coefs[j * 4 + k] = ac.v[k];
             alpha = qmul(alpha, rc);
         }
-        DBuf<uint32_t> d_coefs(ctx, nc * 4);
+        DBuf<uint32_t> d_coefs(ctx, nc * 4), g(ctx, 4 * N), g_lde(ctx, 4 * M), d_bc(ctx, 12 * 4);
         CB_CUDA(cudaMemcpyAsync(d_coefs.p, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, st));
+        CB_CUDA(launch_bitrow_comb(st, W.p, N, N_WORDS, d_coefs.p, g.p));
+        ColSrc gs{SRC_M31, g.p, N, 0};
+        CB_CUDA(launch_fft(st, gs, 4, n, cfg.log_blowup, 1 | 4, nullptr, 0, g_lde.p, M, ctx->tw, g.p, N));
+        uint32_t bc[12 * 4] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        for (int j = 0; j < 8; j++)
+            for (int k = 0; k < 4; k++) bc[(4 + j) * 4 + k] = coefs[((size_t)N_COLS + j) * 4 + k];
+        CB_CUDA(cudaMemcpyAsync(d_bc.p, bc, sizeof bc, cudaMemcpyHostToDevice, st));
         QuotBatch qb{};
         qb.prx = {z.x.v[0], z.x.v[1]}; qb.pix = {z.x.v[2], z.x.v[3]};
         qb.pry = {z.y.v[0], z.y.v[1]}; qb.piy = {z.y.v[2], z.y.v[3]};
         qb.lin_a = lin_a; qb.lin_b = lin_b; qb.batch_coeff = qzero();
-        qb.coefs = d_coefs.p; qb.col_idx = nullptr; qb.n_cols = (int)nc;
+        qb.coefs = d_bc.p; qb.col_idx = nullptr; qb.n_cols = 12;
         DBuf<QuotBatch> d_qb(ctx, 1);
         CB_CUDA(cudaMemcpyAsync(d_qb.p, &qb, sizeof(qb), cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_quotients(st, lde.p, M, N_COLS, comp_lde.p, M, d_qb.p, 1, m, ctx->tw, quot.p, M));
-        ctx->launches++;
+        CB_CUDA(launch_quotients(st, g_lde.p, M, 4, comp_lde.p, M, d_qb.p, 1, m, ctx->tw, quot.p, M));
+        ctx->launches += 5;
         ctx->sync();
     }
     ctx->stage_end();
@@ -277,19 +535,40 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ch.mix_u64(pow_nonce);
     std::vector<uint32_t> queries = host::queries_generate(ch, m, cfg.n_queries);
 
-    // ---- decommit
+    // ---- decommit: queried LDE values of the trace columns are evaluated from the packed witness like the OODS samples
     ctx->stage_begin("decommit");
     std::vector<uint8_t> fri_bytes = fri_decommit(ctx, fri, cfg, queries);
     std::vector<Hash32> dec1 = merkle_decommit(ctx, tree1, queries), dec2 = merkle_decommit(ctx, tree2, queries);
     const int nq = (int)queries.size();
     std::vector<uint32_t> qv1((size_t)N_COLS * nq), qv2((size_t)8 * nq);
     {
-        DBuf<uint32_t> d_rows(ctx, nq), d_q1(ctx, qv1.size()), d_q2(ctx, qv2.size());
+        DBuf<uint32_t> d_rows(ctx, nq), d_q2(ctx, qv2.size()), d_q1(ctx, (size_t)N_COLS * 4);
+        std::vector<uint32_t> q4((size_t)N_COLS * 4);
+        for (int q0 = 0; q0 < nq; q0 += 4) {
+            uint32_t init[4] = {0, 0, 0, 0};
+            std::vector<std::array<uint32_t, 4>> maps(n);
+            for (int c = 0; c < 4 && q0 + c < nq; c++) {
+                host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(queries[q0 + c], m)));
+                init[c] = 1;
+                maps[0][c] = p.y;
+                uint32_t x = p.x;
+                for (int j = 1; j < n; j++) { maps[j][c] = x; x = sub(mul(2, mul(x, x)), 1); }
+            }
+            for (int c = nq - q0; c < 4; c++)
+                for (int j = 0; j < n; j++) maps[j][c] = 0;
+            CB_CUDA(launch_basis4(st, basis.p, N, n, init, (const uint32_t(*)[4])maps.data()));
+            ColSrc bs{SRC_M31, basis.p, N, 0};
+            CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
+            CB_CUDA(launch_bitcol_dot(st, W.p, N, N_WORDS, wt.p, inv_n, d_q1.p));
+            ctx->launches += n + 3;
+            CB_CUDA(cudaMemcpyAsync(q4.data(), d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
+            ctx->sync();
+            for (int j = 0; j < N_COLS; j++)
+                for (int c = 0; c < 4 && q0 + c < nq; c++) qv1[(size_t)j * nq + q0 + c] = q4[(size_t)j * 4 + c];
+        }
         CB_CUDA(cudaMemcpyAsync(d_rows.p, queries.data(), nq * 4, cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_gather_rows(st, lde.p, M, N_COLS, d_rows.p, nq, d_q1.p));
         CB_CUDA(launch_gather_rows(st, comp_lde.p, M, 8, d_rows.p, nq, d_q2.p));
-        ctx->launches += 2;
-        CB_CUDA(cudaMemcpyAsync(qv1.data(), d_q1.p, qv1.size() * 4, cudaMemcpyDeviceToHost, st));
+        ctx->launches++;
         CB_CUDA(cudaMemcpyAsync(qv2.data(), d_q2.p, qv2.size() * 4, cudaMemcpyDeviceToHost, st));
         ctx->sync();
     }

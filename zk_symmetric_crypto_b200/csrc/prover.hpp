@@ -30,6 +30,7 @@ struct ProveOptions {
     const uint32_t* ct_dev = nullptr;
     const uint8_t* pt_hash = nullptr;
     const uint8_t* ct_hash = nullptr;
+    int max_cached_tiles = -1;         // cap on LDE tiles kept between the commitment and constraint passes (-1 = memory bound)
 };
 
 struct FriProverState {
