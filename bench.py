@@ -135,8 +135,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--log-size", type=int, default=int(os.environ.get("S2C_BENCH_LOG", "16")))
-    ap.add_argument("--cpu-log-size", type=int, default=9, help="size of the bounded CPU-reference sample")
+    ap.add_argument("--log-size", type=int, default=int(os.environ.get("S2C_BENCH_LOG", "20")))
+    ap.add_argument("--cpu-log-size", type=int, default=10, help="size of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -243,24 +243,37 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         N = 1 << L
-        # algorithmic bytes per launch: words moved x 4 B
+        cnt = be.counters()
+        cols_t = 32 * cnt.get("fft_words", 0)           # columns transformed from the packed witness (both passes)
+        n_dep_tiles = 2 * 336                            # adder-sum tiles combined (both passes)
+        tile_b = 32 * 2 * N * 4
+        # ALGORITHMIC bytes per proof of each kernel family: per column, iFFT reads the packed bits
+        # and writes N words, the strided pass reads N and writes 2N, the last pass reads and writes 2N (SURVEY 8d:
+        # 8CN + 12CN); leaves and constraints read every LDE value once.
         alg = {
-            "ifft_low": N_COLS * N * 4 * (1 / 32 + 1),          # read packed bits (1/32 word per value), write N
-            "fft_mid": N_COLS * N * 4 * (1 + 1 + 2),            # read N, write N coefficients, write 2N
-            "fft_low": N_COLS * N * 4 * (2 + 2),                # read 2N, write 2N
-            "fft_small": N_COLS * N * 4 * (1 / 32 + 1 + 2),     # fused small-size kernel: bits in, coeffs + LDE out
-            "trace_merkle_leaves": N_COLS * N * 4 * 2 + 2 * N * 32,
-            "constraints": N_COLS * N * 4 * 2 + 4 * 2 * N * 4,
-            "quotients": (N_COLS + 8) * N * 4 * 2 + 4 * 2 * N * 4,
+            "ifft_low": cols_t * N * (1 / 8 + 4),
+            "fft_mid": cols_t * N * (4 + 8),
+            "fft_low": cols_t * N * (8 + 8),
+            "fft_small": cols_t * N * (1 / 8 + 8),
+            "combine": n_dep_tiles * 4 * tile_b,
+            "trace_merkle_leaves": N_COLS * 2 * N * 4 + 2 * (2 * N * 32) * 85,
+            "constraints": N_COLS * 2 * N * 4 + 2 * (4 * 2 * N * 4) * 85,
         }
+        fft_ms = sum(stages.get(k, 0.0) for k in ("ifft_low", "fft_mid", "fft_low", "fft_small"))
+        fft_bytes = sum(alg[k] for k in ("ifft_low", "fft_mid", "fft_low", "fft_small") if stages.get(k))
         top = max((k for k in stages if k in alg), key=lambda k: stages[k], default=None)
         roofline = None
         if top:
             achieved = alg[top] / (stages[top] / 1000.0) / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": alg[top], "launch_ms": stages[top],
-                        "all_kernels_gbs": {k: alg[k] / (stages[k] / 1000.0) / 1e9 for k in stages if k in alg}}
+                        "algorithmic_bytes_per_proof": alg[top], "kernel_ms_per_proof": stages[top],
+                        "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5 for instruction counts",
+                        "fft_all_passes": {"ms": fft_ms, "GB/s": fft_bytes / (fft_ms / 1000.0) / 1e9 if fft_ms else None,
+                                           "frac": fft_bytes / (fft_ms / 1000.0) / 1e9 / hbm_peak if fft_ms else None,
+                                           "columns_transformed": cols_t},
+                        "all_kernels_gbs": {k: alg[k] / (stages[k] / 1000.0) / 1e9 for k in stages if k in alg and stages[k] > 0},
+                        "counters": cnt}
         value = world * args.steps / (ms / 1000.0)
         e2e_value = world * args.steps / (ms_e2e / 1000.0)
         line = {"metric": "chacha20_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,

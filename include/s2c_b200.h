@@ -134,6 +134,9 @@ int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 /* Per-stage device times (ms) of the last proof on ctx when profiling is enabled: "name=ms;name=ms;..." */
 int cb_set_profile(cb_ctx* ctx, int enable);
 const char* cb_stage_times(cb_ctx* ctx);
+/* Counters of the last streaming proof on ctx: "fft_words=..;cached_tiles=..;transient_tiles=..;" (packed witness words
+ * transformed to LDE tiles over both passes, tiles kept between the passes, transient tile slots). */
+const char* cb_counters(cb_ctx* ctx);
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len);
 int s2c_get_circuits_info(char** json_out, size_t* json_len);

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
     "cb_gen_trace_chacha_stream",
-    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times",
+    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_counters",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
 ]
 
@@ -42,6 +42,7 @@ def lib():
         L = ctypes.CDLL(p)
         L.cb_last_error.restype = ctypes.c_char_p
         L.cb_stage_times.restype = ctypes.c_char_p
+        L.cb_counters.restype = ctypes.c_char_p
         L.cb_launch_count.restype = ctypes.c_uint64
         L.s2c_free.argtypes = [ctypes.c_void_p]
         _LIB = L
@@ -125,6 +126,10 @@ class Backend:
                 k, v = item.split("=")
                 out[k] = out.get(k, 0.0) + float(v)
         return out
+
+    def counters(self):
+        s = self.L.cb_counters(self.ctx).decode()
+        return {k: int(v) for k, v in (item.split("=") for item in s.split(";") if "=" in item)}
 
     # ---- product level
     def prove_chacha20_raw(self, key, nonce, counter, plaintext, ciphertext):

@@ -374,6 +374,15 @@ const char* cb_stage_times(cb_ctx* ctx) {
     return s.c_str();
 }
 
+const char* cb_counters(cb_ctx* ctx) {
+    static thread_local std::string s;
+    s.clear();
+    if (!ctx) return "";
+    s = "fft_words=" + std::to_string(ctx->fft_words) + ";cached_tiles=" + std::to_string(ctx->cached_tiles) +
+        ";transient_tiles=" + std::to_string(ctx->transient_tiles) + ";";
+    return s.c_str();
+}
+
 // ---------------------------------------------------------------------------------------------- product level
 static cb_ctx* default_ctx(std::string& err) {
     static std::mutex mu;

@@ -37,7 +37,10 @@ struct cb_ctx {
     std::vector<StageTime> stages;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
     int max_cached_tiles = -1;  // streaming prover: cap on LDE tiles kept between passes (-1 = as many as memory allows)
-    uint64_t launches = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
+    uint64_t launches = 0;
+    // counters of the last streaming proof: packed words transformed (x32 columns), tiles cached between passes, transient slots
+    uint64_t fft_words = 0;
+    int cached_tiles = 0, transient_tiles = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
 
     void ensure_twiddles(int max_log);
     void* dmalloc(size_t bytes);

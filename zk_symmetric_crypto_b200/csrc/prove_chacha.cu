@@ -342,6 +342,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     DBuf<uint32_t> scratch(ctx, scratch_words);
     Tiles tiles;
     tiles.init(n_cache, peak_trans, tile_words, arena.p);
+    ctx->fft_words = 0;
+    ctx->cached_tiles = n_cache;
+    ctx->transient_tiles = peak_trans;
 
     auto run_pass = [&](int pass, auto&& consume) {
         for (size_t gi = 0; gi < plan.size(); gi++) {
@@ -357,6 +360,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 int nl = 0;
                 CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch.p, hkp, &nl));
                 ctx->launches += nl;
+                ctx->fft_words += src.size();
             }
             if (!g.comb.empty()) {
                 CombineJobs cj{};
