@@ -66,6 +66,8 @@ int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* src, size_t src_str
  * words (src_kind 1: 32 one-bit columns per word, 2: 4 byte columns per word); tiles_out = n_words tiles of
  * [32 or 4][2^(log_size+1)] LDE values.  This is the transform the streaming provers use (coefficients stay on chip). */
 int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out);
+/* Test hook (process-wide): route 13 <= log_size <= 20 through the generic runtime-schedule kernels that serve log_size > 20. */
+int cb_debug_force_generic_fft(int on);
 /* Streaming provers keep as many LDE tiles as device memory allows between the commitment pass and the constraint pass;
  * this caps that number (0 = recompute every tile, -1 = default).  Results do not depend on it. */
 int cb_set_max_cached_tiles(cb_ctx* ctx, int n_tiles);

@@ -64,7 +64,7 @@ def test_interpolate_evaluate(backend, log_n):
         be.free(p)
 
 
-@pytest.mark.parametrize("log_n,kind", [(4, 1), (5, 1), (8, 1), (11, 1), (12, 1), (13, 1), (14, 1), (16, 1), (18, 1), (20, 1),
+@pytest.mark.parametrize("log_n,kind", [(4, 1), (5, 1), (8, 1), (11, 1), (12, 1), (13, 1), (14, 1), (15, 1), (16, 1), (17, 1), (18, 1), (19, 1), (20, 1),
                                         (22, 1), (6, 2), (12, 2), (15, 2)])
 def test_lde_packed(backend, log_n, kind):
     """Packed-witness fused interpolate+extend (the transform of the streaming prover) against the oracle's circle
@@ -91,6 +91,17 @@ def test_lde_packed(backend, log_n, kind):
             assert np.array_equal(tiles[w, c], lde[i]), (w, c)
     be.free(d_w)
     be.free(d_t)
+
+
+def test_lde_packed_generic_kernels(backend):
+    """The runtime-schedule three-pass kernels (used above log 20) on a size the specialised kernels normally serve."""
+    be = backend
+    be.L.cb_debug_force_generic_fft(1)
+    try:
+        test_lde_packed(be, 14, 1)
+        test_lde_packed(be, 17, 1)
+    finally:
+        be.L.cb_debug_force_generic_fft(0)
 
 
 def _witness(be, nb, seed):

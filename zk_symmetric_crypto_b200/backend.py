@@ -14,7 +14,7 @@ EXPORTED_SYMBOLS = [
     "cb_init", "cb_destroy", "cb_last_error", "cb_set_stream", "cb_sync", "cb_launch_count",
     "cb_malloc", "cb_free", "cb_h2d", "cb_d2h", "cb_memset_zero",
     "cb_precompute_twiddles", "cb_interpolate_columns", "cb_evaluate_polynomials", "cb_commit_lde", "cb_lde_packed",
-    "cb_set_max_cached_tiles", "cb_eval_at_point",
+    "cb_set_max_cached_tiles", "cb_debug_force_generic_fft", "cb_eval_at_point",
     "cb_merkle_build_leaves", "cb_merkle_leaves_absorb", "cb_merkle_next_layer",
     "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",

@@ -176,6 +176,12 @@ int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_wo
     CB_CATCH(ctx)
 }
 
+extern int g_force_generic_fft;
+int cb_debug_force_generic_fft(int on) {
+    g_force_generic_fft = on;
+    return 0;
+}
+
 int cb_set_max_cached_tiles(cb_ctx* ctx, int n_tiles) {
     if (!ctx) return 1;
     ctx->max_cached_tiles = n_tiles;

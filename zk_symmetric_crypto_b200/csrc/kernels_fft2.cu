@@ -250,9 +250,286 @@ __global__ void __launch_bounds__(256) fft_low_kernel(Jobs jobs, int log_n, int 
     }
 }
 
+
+// ===================================================================================================================
+// v2 kernels for 13 <= n <= 20: contiguous chunk fixed at 2^12 rows, every step's layer range is a template parameter
+// (shared-memory offsets become immediates, no index arithmetic or integer divisions in the loops), the first and the
+// last register step of every kernel read from / write to global memory directly.
+// Shared-memory layout of a 4096-word column chunk: +4 words per 32 (keeps 16-byte vectors intact) and bank bit 4
+// flipped for odd 256-blocks, which makes all three step patterns (stride 256, stride 16, 16 consecutive as 4 x 128-bit)
+// conflict-free.
+// ===================================================================================================================
+constexpr int K1 = 12, T2 = 4096, COLW = 4608;
+__device__ __forceinline__ int phys(int a) { return (a + ((a >> 5) << 2)) ^ ((a >> 4) & 16); }
+
+// twiddles of R consecutive layers starting at global layer gi0 for the 2^R-point block whose first point has (tile-local)
+// index j0; jg = (tile_hi << jbits) | j0, b = local bit of gi0.  slot (c-1)+t, c = 2^(R-1-l); values pre-doubled.
+template <int R>
+__device__ __forceinline__ void load_tw(uint32_t (&tw)[1 << R], const uint32_t* __restrict__ tabX, const uint32_t* __restrict__ tabY,
+                                        int m, int gi0, uint32_t jg, int b) {
+#pragma unroll
+    for (int l = 0; l < R; l++) {
+        const int gi = gi0 + l;
+        const uint32_t* tab = (gi == 0) ? tabY + (1u << (m - 1)) : tabX + (1u << (m - gi - 1));
+        const uint32_t hb = jg >> (b + l + 1);
+#pragma unroll
+        for (int t = 0; t < (1 << (R - 1 - l)); t++) tw[(1 << (R - 1 - l)) - 1 + t] = __ldg(tab + hb + t) << 1;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void inv_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R]) {
+#pragma unroll
+    for (int l = 0; l < R; l++) {
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & (1 << l)) continue;
+            const uint32_t w2 = tw[(1 << (R - 1 - l)) - 1 + (k >> (l + 1))];
+            uint32_t v0 = v[k], v1 = v[k | (1 << l)];
+            v[k] = addm(v0, v1);
+            v[k | (1 << l)] = mulw(subm(v0, v1), w2);
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void fwd_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R]) {
+#pragma unroll
+    for (int l = R - 1; l >= 0; l--) {
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) {
+            if (k & (1 << l)) continue;
+            const uint32_t w2 = tw[(1 << (R - 1 - l)) - 1 + (k >> (l + 1))];
+            uint32_t v0 = v[k], t = mulw(v[k | (1 << l)], w2);
+            v[k] = addm(v0, t);
+            v[k | (1 << l)] = subm(v0, t);
+        }
+    }
+}
+
+// ---- pass A: expand packed words, inverse layers [0,12) on a 4096-row chunk, NC columns per block ---------------------------
+template <int KIND, int NC>
+__global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, int groups_per_job, int cols_per_job,
+                                                         uint32_t* __restrict__ scratch, FftTables tw) {
+    extern __shared__ uint32_t s[];
+    const uint32_t chunk = blockIdx.x;
+    const int job = blockIdx.y / groups_per_job, c0 = (blockIdx.y % groups_per_job) * NC;
+    const int p = threadIdx.x;
+    const uint32_t scale = 1u << (31 - log_n), scale2 = scale << 1;
+    uint32_t w[16], twr[16], v[16];
+    {
+        const uint4* __restrict__ src = (const uint4*)(jobs.src[job] + (size_t)chunk * T2 + 16 * p);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 x = __ldg(src + i);
+            w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+    }
+    // step (4,0): from registers, 16 consecutive points per thread
+    load_tw<4>(twr, tw.IX, tw.IY, log_n, 0, (chunk << K1) | (uint32_t)(16 * p), 0);
+    int va[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) va[i] = phys(16 * p + 4 * i);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = unpack<KIND>(w[k], c0 + c, scale, scale2);
+        inv_block<4>(v, twr);
+#pragma unroll
+        for (int i = 0; i < 4; i++) *(uint4*)(s + c * COLW + va[i]) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    __syncthreads();
+    // step (4,4)
+    {
+        const int j0 = ((p >> 4) << 8) | (p & 15);
+        load_tw<4>(twr, tw.IX, tw.IY, log_n, 4, (chunk << K1) | (uint32_t)j0, 4);
+        int ad[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ad[k] = phys(j0 + 16 * k);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
+            inv_block<4>(v, twr);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
+        }
+    }
+    __syncthreads();
+    // step (4,8): to global (scratch), 128-byte coalesced per k
+    {
+        load_tw<4>(twr, tw.IX, tw.IY, log_n, 8, (chunk << K1) | (uint32_t)p, 8);
+        int ad[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ad[k] = phys(p + 256 * k);
+        uint32_t* __restrict__ out = scratch + ((size_t)(job * cols_per_job + c0) << log_n) + (size_t)chunk * T2 + p;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
+            inv_block<4>(v, twr);
+#pragma unroll
+            for (int k = 0; k < 16; k++) out[((size_t)c << log_n) + 256 * k] = v[k];
+        }
+    }
+}
+
+// ---- pass C: forward layers [11..0] on 4096-point chunks of the extended column, in place -------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, int groups_per_job, FftTables tw) {
+    extern __shared__ uint32_t s[];
+    const int m = log_n + 1;
+    const uint32_t chunk = blockIdx.x;
+    const int job = blockIdx.y / groups_per_job, c0 = (blockIdx.y % groups_per_job) * NC;
+    uint32_t* __restrict__ data = jobs.out[job] + ((size_t)c0 << m) + (size_t)chunk * T2;
+    const int p = threadIdx.x;
+    uint32_t twr[16], v[16];
+    {
+        load_tw<4>(twr, tw.X, tw.Y, m, 8, (chunk << K1) | (uint32_t)p, 8);
+        int ad[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ad[k] = phys(p + 256 * k);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = data[((size_t)c << m) + p + 256 * k];
+            fwd_block<4>(v, twr);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
+        }
+    }
+    __syncthreads();
+    {
+        const int j0 = ((p >> 4) << 8) | (p & 15);
+        load_tw<4>(twr, tw.X, tw.Y, m, 4, (chunk << K1) | (uint32_t)j0, 4);
+        int ad[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ad[k] = phys(j0 + 16 * k);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
+            fwd_block<4>(v, twr);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
+        }
+    }
+    __syncthreads();
+    {
+        load_tw<4>(twr, tw.X, tw.Y, m, 0, (chunk << K1) | (uint32_t)(16 * p), 0);
+        int va[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) va[i] = phys(16 * p + 4 * i);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 x = *(const uint4*)(s + c * COLW + va[i]);
+                v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            }
+            fwd_block<4>(v, twr);
+            uint4* o = (uint4*)(data + ((size_t)c << m) + 16 * p);
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    }
+}
+
+// ---- pass B: inverse layers [12,n) + forward layers [n-1..12] of both halves; tile = 2^JB x 32, JB = n-12 in [1,8] ----------
+template <int JB>
+__global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job, const uint32_t* __restrict__ scratch, FftTables tw) {
+    extern __shared__ uint32_t s[];
+    constexpr int log_n = K1 + JB, m = log_n + 1;
+    constexpr int RA = JB <= 4 ? JB : (JB + 1) / 2;  // low local bits (first inverse step / last forward step)
+    constexpr int RB = JB - RA;                      // high local bits
+    constexpr int J = 1 << JB;
+    const int q = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t q0 = blockIdx.x * 32;
+    const int job = blockIdx.y / cols_per_job, col = blockIdx.y % cols_per_job;
+    const uint32_t* __restrict__ in = scratch + ((size_t)blockIdx.y << log_n) + q0 + q;
+    uint32_t* __restrict__ out = jobs.out[job] + ((size_t)col << m) + q0 + q;
+    uint32_t twr[1 << RA], v[1 << RA];
+    if (RB == 0) {
+        load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, 0, 0);
+#pragma unroll
+        for (int k = 0; k < J; k++) v[k] = in[(size_t)k << K1];
+        inv_block<RA>(v, twr);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t u[1 << RA];
+#pragma unroll
+            for (int k = 0; k < J; k++) u[k] = v[k];
+            load_tw<RA>(twr, tw.X, tw.Y, m, K1, (uint32_t)h << JB, 0);
+            fwd_block<RA>(u, twr);
+#pragma unroll
+            for (int k = 0; k < J; k++) out[((size_t)h << log_n) + ((size_t)k << K1)] = u[k];
+        }
+        return;
+    }
+    uint32_t* s0 = s;
+    uint32_t* s1 = s + J * 32;
+    // inverse step A: local bits [0,RA), from global
+    for (int pa = wid; pa < (J >> RA); pa += nw) {
+        const int j0 = pa << RA;
+        load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, (uint32_t)j0, 0);
+#pragma unroll
+        for (int k = 0; k < (1 << RA); k++) v[k] = in[(size_t)(j0 + k) << K1];
+        inv_block<RA>(v, twr);
+#pragma unroll
+        for (int k = 0; k < (1 << RA); k++) s0[((j0 + k) << 5) | q] = v[k];
+    }
+    __syncthreads();
+    // inverse step B: local bits [RA,JB) -> coefficients; forward step B of both halves
+    constexpr int RBs = RB > 0 ? RB : 1;
+    for (int pb = wid; pb < (J >> RBs); pb += nw) {
+        uint32_t twb[1 << RBs], c[1 << RBs];
+        load_tw<RBs>(twb, tw.IX, tw.IY, log_n, K1 + RA, (uint32_t)pb, RA);
+#pragma unroll
+        for (int k = 0; k < (1 << RBs); k++) c[k] = s0[((pb + (k << RA)) << 5) | q];
+        inv_block<RBs>(c, twb);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t u[1 << RBs];
+#pragma unroll
+            for (int k = 0; k < (1 << RBs); k++) u[k] = c[k];
+            load_tw<RBs>(twb, tw.X, tw.Y, m, K1 + RA, ((uint32_t)h << JB) | (uint32_t)pb, RA);
+            fwd_block<RBs>(u, twb);
+            uint32_t* sh = h ? s1 : s0;
+#pragma unroll
+            for (int k = 0; k < (1 << RBs); k++) sh[((pb + (k << RA)) << 5) | q] = u[k];
+        }
+    }
+    __syncthreads();
+    // forward step A: local bits [0,RA), to global
+    for (int pa = wid; pa < 2 * (J >> RA); pa += nw) {
+        const int h = pa >= (J >> RA);
+        const int j0 = (pa - h * (J >> RA)) << RA;
+        const uint32_t* sh = h ? s1 : s0;
+        load_tw<RA>(twr, tw.X, tw.Y, m, K1, ((uint32_t)h << JB) | (uint32_t)j0, 0);
+#pragma unroll
+        for (int k = 0; k < (1 << RA); k++) v[k] = sh[((j0 + k) << 5) | q];
+        fwd_block<RA>(v, twr);
+#pragma unroll
+        for (int k = 0; k < (1 << RA); k++) out[((size_t)h << log_n) + ((size_t)(j0 + k) << K1)] = v[k];
+    }
+}
+
+template <int JB>
+static void launch_mid12(cudaStream_t st, const Jobs& jobs, int cpj, const uint32_t* scratch, const FftTables& tw) {
+    constexpr int RA = JB <= 4 ? JB : (JB + 1) / 2;
+    constexpr int RB = JB - RA;
+    constexpr int items = (1 << (JB - RA)) * 32;       // step A items per tile
+    const int threads = RB == 0 ? 32 : (items < 256 ? items : 256);
+    const size_t smem = RB == 0 ? 0 : (size_t)2 * (1 << JB) * 32 * 4;
+    dim3 g(T2 / 32, jobs.n * cpj);
+    mid12_kernel<JB><<<g, threads, smem, st>>>(jobs, cpj, scratch, tw);
+}
+
 constexpr int SMEM_MAX = 72 * 1024;
 
 }  // namespace fft2
+
+int g_force_generic_fft = 0;  // tests: exercise the generic (runtime-schedule) kernels at sizes the v2 kernels cover
 
 void fft2_init_attrs() {
     using namespace fft2;
@@ -263,6 +540,11 @@ void fft2_init_attrs() {
     cudaFuncSetAttribute(mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(fft_low_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    cudaFuncSetAttribute(ifft_low12_kernel<SRC_BITS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
+    cudaFuncSetAttribute(ifft_low12_kernel<SRC_BYTES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
+    cudaFuncSetAttribute(fft_low12_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
+    cudaFuncSetAttribute(mid12_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 32 * 4);
+    cudaFuncSetAttribute(mid12_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 32 * 4);
 }
 
 // words of scratch launch_fft_packed needs for `njobs` jobs at log size n
@@ -296,6 +578,34 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
             else small_kernel<SRC_BYTES><<<jobs.n * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
             HOOK("fft_small", 0);
             nl += 1;
+            continue;
+        }
+        if (log_n <= 20 && !g_force_generic_fft) {
+            constexpr int NC = 4;
+            const int gpj2 = cpj / NC;
+            uint32_t* scr2 = scratch;
+            dim3 gA((1u << log_n) / T2, jobs.n * gpj2);
+            HOOK("ifft_low", 1);
+            if (kind == SRC_BITS) ifft_low12_kernel<SRC_BITS, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
+            else ifft_low12_kernel<SRC_BYTES, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
+            HOOK("ifft_low", 0);
+            HOOK("fft_mid", 1);
+            switch (log_n - K1) {
+                case 1: launch_mid12<1>(st, jobs, cpj, scr2, tw); break;
+                case 2: launch_mid12<2>(st, jobs, cpj, scr2, tw); break;
+                case 3: launch_mid12<3>(st, jobs, cpj, scr2, tw); break;
+                case 4: launch_mid12<4>(st, jobs, cpj, scr2, tw); break;
+                case 5: launch_mid12<5>(st, jobs, cpj, scr2, tw); break;
+                case 6: launch_mid12<6>(st, jobs, cpj, scr2, tw); break;
+                case 7: launch_mid12<7>(st, jobs, cpj, scr2, tw); break;
+                default: launch_mid12<8>(st, jobs, cpj, scr2, tw); break;
+            }
+            HOOK("fft_mid", 0);
+            dim3 gC((2u << log_n) / T2, jobs.n * gpj2);
+            HOOK("fft_low", 1);
+            fft_low12_kernel<NC><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
+            HOOK("fft_low", 0);
+            nl += 3;
             continue;
         }
         int k1 = (log_n + 1) / 2;
