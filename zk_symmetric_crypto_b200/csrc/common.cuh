@@ -26,6 +26,11 @@ struct LeafGroup {
     size_t stride;
     int ncols;
     int log_size;
+    // adder-sum word computed on the fly (streaming prover): when cy != nullptr the group has 32 columns of the lifting size,
+    // value(col) = base[col] + b[col] + cy[col-1] - 2 cy[col] (cy[-1] = 0), which is also stored to res[col] (may alias base)
+    const uint32_t* b;
+    const uint32_t* cy;
+    uint32_t* res;
 };
 #define MAX_LEAF_GROUPS 16
 struct LeafGroups {
@@ -54,14 +59,18 @@ struct CombineJobs {
     CombineJob j[MAX_COMBINE_JOBS];
     int n;
 };
-enum { CJ_BOOL = 0, CJ_XOR = 1, CJ_XORN = 2 };
+enum { CJ_BOOL = 0, CJ_XOR = 1, CJ_XORN = 2, CJ_ADDX = 3 };
 struct ConstraintJob {
-    const uint32_t *t0, *t1, *t2;  // tiles [32][M]
-    int k0;                        // index of the first constraint of the job in the reversed alpha-power table
-    int arg;                       // CJ_BOOL: constraint index step per bit; CJ_XOR*: left rotation
+    const uint32_t *t0, *t1, *t2;  // tiles [32][M]: CJ_BOOL t0; CJ_XOR* r = t0, a = t1, d = t2; CJ_ADDX x = t0 (or null), a = t1, d = t2
+    const uint32_t *t3, *t4;       // CJ_ADDX: second adder operand b = t3, carry word cy = t4
+    uint32_t* res;                 // CJ_ADDX: the adder's sum tile, computed here (a + b + cy[-1] - 2cy) and stored
+    int kx;                        // index (in the reversed alpha-power table) of the xor constraint of bit 0
+    int kb0, kb1, kb2;             // index of the boolean constraint of bit 0 of t0 / t1 (CJ_ADDX: the sum) / t2 (-1 = none)
+    int kbc;                       // CJ_ADDX: index of the boolean constraint of carry bit 0 (step 2)
+    int arg;                       // CJ_BOOL: constraint index step per bit; others: left rotation
     int type;
 };
-#define MAX_CONSTRAINT_JOBS 48
+#define MAX_CONSTRAINT_JOBS 32
 struct ConstraintJobs {
     ConstraintJob j[MAX_CONSTRAINT_JOBS];
     int n;

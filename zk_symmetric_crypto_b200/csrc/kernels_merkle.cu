@@ -9,16 +9,19 @@
 // Columns arrive as groups of equally sized, equally strided columns; leaf state (h[8]) can be carried across calls
 // so that a tree can be absorbed tile by tile while the LDE is streamed (column count per non-final call must be a
 // multiple of 16 = one 64-byte Blake2s block).
+#include <stdlib.h>
 #include "common.cuh"
 #include "blake2s.cuh"
+#include "m31_dev.cuh"
 
 
 namespace merk {
 
 // state: h_state[w * n_leaves + leaf] (SoA) when carrying; bytes_before = bytes absorbed by earlier calls.
+template <bool FMA>
 __global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lifting_log, uint32_t* __restrict__ h_state,
                                                      uint64_t bytes_before, int is_first, int is_final,
-                                                     uint32_t* __restrict__ out) {
+                                                     uint32_t* __restrict__ out, uint32_t one) {
     const uint32_t n_leaves = 1u << lifting_log;
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n_leaves) return;
@@ -44,6 +47,34 @@ __global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lift
         }
         const uint32_t* p = g.base + row;
         int c = 0;
+        if (g.cy != nullptr && k == 0) {
+            // computed adder-sum word: 32 columns = two blocks; operands may have been written by this thread earlier in
+            // this launch (plain loads, not the read-only path)
+            const uint32_t* pb = g.b + row;
+            const uint32_t* pc = g.cy + row;
+            uint32_t* pr = g.res + row;
+            uint32_t cin = 0;
+            for (; c + 16 <= g.ncols; c += 16) {
+                uint32_t bv[16], cv[16];
+#pragma unroll
+                for (int w = 0; w < 16; w++) {  // all loads first: the stores below may alias the operand tiles
+                    const size_t o = (size_t)(c + w) * g.stride;
+                    m[w] = p[o];
+                    bv[w] = pb[o];
+                    cv[w] = pc[o];
+                }
+#pragma unroll
+                for (int w = 0; w < 16; w++) {
+                    const uint32_t v = m31d::subm(m31d::addm(m31d::addm(m[w], bv[w]), cin), m31d::dbl(cv[w]));
+                    pr[(size_t)(c + w) * g.stride] = v;
+                    m[w] = v;
+                    cin = cv[w];
+                }
+                t += 64;
+                bool last = is_final && (done_cols + c + 16 == total_cols);
+                if (FMA) blake2s::compress_fma(h, m, t, last, one); else blake2s::compress(h, m, t, last);
+            }
+        }
         if (k == 0) {
             // fast path: whole 64-byte blocks straight from 16 coalesced column loads
             for (; c + 16 <= g.ncols; c += 16) {
@@ -51,7 +82,7 @@ __global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lift
                 for (int w = 0; w < 16; w++) m[w] = __ldg(p + (size_t)(c + w) * g.stride);
                 t += 64;
                 bool last = is_final && (done_cols + c + 16 == total_cols);
-                blake2s::compress(h, m, t, last);
+                if (FMA) blake2s::compress_fma(h, m, t, last, one); else blake2s::compress(h, m, t, last);
             }
         }
         for (; c < g.ncols; c++) {
@@ -105,8 +136,13 @@ cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int 
     uint32_t n = 1u << lifting_log;
     int threads = n >= 128 * 148 * 2 ? 128 : 64;
     if (n < 64) threads = 32;
-    merk::leaves_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before, is_first,
-                                                                         is_final, out);
+    static const int variant = getenv("S2C_BLAKE_FMA") ? atoi(getenv("S2C_BLAKE_FMA")) : 1;
+    if (variant)
+        merk::leaves_kernel<true><<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before,
+                                                                                   is_first, is_final, out, 1u);
+    else
+        merk::leaves_kernel<false><<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before,
+                                                                                    is_first, is_final, out, 1u);
     return cudaGetLastError();
 }
 

@@ -56,8 +56,9 @@ struct Acc4 {
 };
 
 // acc[row] += sum over jobs of sum_i apr[k] * C(row)   (apr[k] = alpha^(K-1-k), 4 coordinates)
-//   CJ_BOOL: C = b(1-b), b = t0[i], k = k0 + i*step          (constraints_stream.rs:85-101 and the carry booleans :117-120)
-//   CJ_XOR : C = r - a - d + 2ad, r = t0[i], a = t1[s], d = t2[s], s = (i-rot) mod 32, k = k0 + i   (:134-152)
+//   CJ_BOOL: C = b(1-b), b = t0[i], k = kb0 + i*step          (constraints_stream.rs:85-101 and the carry booleans :117-120)
+//   CJ_XOR : C = r - a - d + 2ad, r = t0[i], a = t1[s], d = t2[s], s = (i-rot) mod 32, k = kx + i   (:134-152), plus the
+//            boolean constraints of the operands the job has loaded anyway: r at kb0+i, a at kb1+s, d at kb2+s
 //   CJ_XORN: C = a + d - 2ad - r  (keystream xor plaintext = ciphertext, :60-68)
 __global__ void __launch_bounds__(128) constraints_tiles_kernel(ConstraintJobs jobs, size_t M, const uint4* __restrict__ apr,
                                                                 uint32_t* __restrict__ acc, int first) {
@@ -69,24 +70,68 @@ __global__ void __launch_bounds__(128) constraints_tiles_kernel(ConstraintJobs j
         const ConstraintJob J = jobs.j[j];
         if (J.type == CJ_BOOL) {
             const uint32_t* __restrict__ t = J.t0 + row;
-#pragma unroll 4
+            const uint4* __restrict__ al = apr + J.kb0;
+#pragma unroll 8
             for (int i = 0; i < 32; i++) {
                 uint32_t b = t[(size_t)i * M];
-                uint32_t C = mulm(b, subm(1, b));
-                A.mac(__ldg(apr + J.k0 + i * J.arg), C);
+                A.mac(__ldg(al + i * J.arg), mulm(b, subm(1, b)));
+            }
+        } else if (J.type == CJ_ADDX) {
+            // adder with the sum computed on the fly (and stored for later groups): carry booleans, sum booleans and, when the
+            // sum feeds a xor-rotate, the xor constraints and the result booleans.  Operands are staged 8 bits at a time so
+            // the loads are in flight together (the sum store may alias an operand tile).
+            const uint32_t* x = J.t0 ? J.t0 + row : nullptr;
+            const uint32_t* a = J.t1 + row;
+            const uint32_t* d = J.t2 ? J.t2 + row : nullptr;
+            const uint32_t* b = J.t3 + row;
+            const uint32_t* cy = J.t4 + row;
+            uint32_t* res = J.res + row;
+            uint32_t cin = 0;
+            for (int s0 = 0; s0 < 32; s0 += 8) {
+                uint32_t av[8], bv[8], cv[8], xv[8], dv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int s = s0 + u;
+                    av[u] = a[(size_t)s * M];
+                    bv[u] = b[(size_t)s * M];
+                    cv[u] = cy[(size_t)s * M];
+                    if (x) {
+                        xv[u] = x[(size_t)((s + J.arg) & 31) * M];
+                        dv[u] = d[(size_t)s * M];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int s = s0 + u;
+                    const uint32_t sv = subm(addm(addm(av[u], bv[u]), cin), dbl(cv[u]));
+                    cin = cv[u];
+                    res[(size_t)s * M] = sv;
+                    A.mac(__ldg(apr + J.kbc + 2 * s), mulm(cv[u], subm(1, cv[u])));
+                    A.mac(__ldg(apr + J.kb1 + s), mulm(sv, subm(1, sv)));
+                    if (x) {
+                        const int i = (s + J.arg) & 31;
+                        const uint32_t sd = mulm(sv, dv[u]);
+                        A.mac(__ldg(apr + J.kx + i), addm(subm(subm(xv[u], sv), dv[u]), dbl(sd)));
+                        A.mac(__ldg(apr + J.kb0 + i), mulm(xv[u], subm(1, xv[u])));
+                    }
+                }
             }
         } else {
             const uint32_t* __restrict__ r = J.t0 + row;
             const uint32_t* __restrict__ a = J.t1 + row;
             const uint32_t* __restrict__ d = J.t2 + row;
+            const bool neg = J.type == CJ_XORN;
 #pragma unroll 4
             for (int i = 0; i < 32; i++) {
-                int s = (i + 32 - J.arg) & 31;
-                uint32_t rv = r[(size_t)i * M], av = a[(size_t)s * M], dv = d[(size_t)s * M];
-                uint32_t ad = mulm(av, dv);
+                const int s = (i + 32 - J.arg) & 31;
+                const uint32_t rv = r[(size_t)i * M], av = a[(size_t)s * M], dv = d[(size_t)s * M];
+                const uint32_t ad = mulm(av, dv);
                 uint32_t C = addm(subm(subm(rv, av), dv), dbl(ad));
-                if (J.type == CJ_XORN) C = subm(0, C);
-                A.mac(__ldg(apr + J.k0 + i), C);
+                if (neg) C = subm(0, C);
+                A.mac(__ldg(apr + J.kx + i), C);
+                if (J.kb0 >= 0) A.mac(__ldg(apr + J.kb0 + i), mulm(rv, subm(1, rv)));
+                if (J.kb1 >= 0) A.mac(__ldg(apr + J.kb1 + s), mulm(av, subm(1, av)));
+                if (J.kb2 >= 0) A.mac(__ldg(apr + J.kb2 + s), mulm(dv, subm(1, dv)));
             }
         }
     }

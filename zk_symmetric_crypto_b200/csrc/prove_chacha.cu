@@ -8,6 +8,7 @@
 // Output bytes = bincode(StreamProof{stmt, stark_proof}) exactly as the reference serialises it
 // (air_stream.rs:30-131, wasm_api.rs:588): byte-identical to the reference, checked in tests/.
 #include <array>
+#include <thread>
 #include "prover.hpp"
 
 using namespace m31;
@@ -94,7 +95,7 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
 namespace {
 
 struct Comb { int res, a, b, c; };
-struct CJ { int type, w0, w1, w2, k0, arg; };
+struct CJ { int type, w0, w1, w2, kx, kb0, kb1, kb2, arg, w3, w4, wres, kbc; };
 struct Group {
     std::vector<int> fft;         // independent words transformed in this group
     std::vector<Comb> comb;       // adder sum words, in dependency order
@@ -112,7 +113,7 @@ std::vector<Group> build_plan() {
             state[w] = w;
             g.fft.push_back(w);
             g.hash.push_back(w);
-            g.cons.push_back({CJ_BOOL, w, -1, -1, 32 * w, 1});
+            g.cons.push_back({CJ_BOOL, w, -1, -1, -1, 32 * w, -1, -1, 1, -1, -1, -1, -1});
         }
         plan.push_back(g);
     }
@@ -133,10 +134,11 @@ std::vector<Group> build_plan() {
         const int XD[4] = {state[d], state[b], X1, X2};  // second xor operand (the rotated word's previous value)
         for (int t = 0; t < 4; t++) {
             const int k = kb + 160 * t;
-            g.cons.push_back({CJ_BOOL, S[t], -1, -1, k, 1});
-            g.cons.push_back({CJ_BOOL, C[t], -1, -1, k + 32, 2});
-            g.cons.push_back({CJ_BOOL, X[t], -1, -1, k + 96, 1});
-            g.cons.push_back({CJ_XOR, X[t], S[t], XD[t], k + 128, ROT[t]});
+            // adder t: 32 sum booleans at k, then [carry boolean, adder identity] pairs from k+32 (identity skipped: it is
+            // identically zero, see kernels_stream.cu); xor t: 32 result booleans at k+96, 32 xor constraints at k+128
+            // one fused job per adder + xor-rotate pair; the sum tile S[t] is computed inside it
+            const Comb& cb = g.comb[t];
+            g.cons.push_back({CJ_ADDX, X[t], cb.a, XD[t], k + 128, k + 96, k, -1, ROT[t], cb.b, C[t], S[t], k + 32});
         }
         for (int w : {state[a], state[b], state[c], state[d]})
             if (w >= 16) g.free_after.push_back(w);
@@ -153,8 +155,7 @@ std::vector<Group> build_plan() {
             g.comb.push_back({S, state[i], i, C});
             g.hash.push_back(S);
             g.hash.push_back(C);
-            g.cons.push_back({CJ_BOOL, S, -1, -1, kf + 96 * i, 1});
-            g.cons.push_back({CJ_BOOL, C, -1, -1, kf + 96 * i + 32, 2});
+            g.cons.push_back({CJ_ADDX, -1, state[i], -1, -1, -1, kf + 96 * i, -1, 0, i, C, S, kf + 96 * i + 32});
             if (state[i] >= 16) g.free_after.push_back(state[i]);
             g.free_after.push_back(C);
             g.free_after.push_back(i);  // initial-state tile i is no longer needed
@@ -166,7 +167,6 @@ std::vector<Group> build_plan() {
         for (int i = 0; i < 16; i++) {
             g.fft.push_back(1008 + i);
             g.hash.push_back(1008 + i);
-            g.cons.push_back({CJ_BOOL, 1008 + i, -1, -1, k_pt + 32 * i, 1});
         }
         plan.push_back(g);
     }
@@ -175,8 +175,8 @@ std::vector<Group> build_plan() {
         for (int i = 0; i < 16; i++) {
             g.fft.push_back(1024 + i);
             g.hash.push_back(1024 + i);
-            g.cons.push_back({CJ_BOOL, 1024 + i, -1, -1, k_ct + 32 * i, 1});
-            g.cons.push_back({CJ_XORN, 1024 + i, 976 + 2 * i, 1008 + i, k_eq + 32 * i, 0});
+            // ciphertext = keystream xor plaintext, plus the booleans of the three words involved
+            g.cons.push_back({CJ_XORN, 1024 + i, 976 + 2 * i, 1008 + i, k_eq + 32 * i, k_ct + 32 * i, -1, k_pt + 32 * i, 0, -1, -1, -1, -1});
             g.free_after.push_back(1024 + i);
             g.free_after.push_back(1008 + i);
             g.free_after.push_back(976 + 2 * i);
@@ -260,6 +260,19 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     for (int i = 0; i < 8; i++) key_w[i] = host::load_le32(key + 4 * i);
     for (int i = 0; i < 3; i++) nonce_w[i] = host::load_le32(nonce + 4 * i);
 
+    // ChaChaPublicInputs::new (air_stream.rs:44-53) hashes the whole plaintext and ciphertext on the host; run both hashes on
+    // their own threads so they overlap the GPU's commitment pass
+    Hash32 pth, cth;
+    struct Hashers {
+        std::thread a, b;
+        void join() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
+        ~Hashers() { join(); }
+    } hashers;
+    if (!opt.pt_hash && !opt.empty_public_hashes) {
+        hashers.a = std::thread([&] { pth = host::blake2s_bytes(plaintext, len); });
+        hashers.b = std::thread([&] { cth = host::blake2s_bytes(ciphertext, len); });
+    }
+
     Channel ch;
     std::vector<Hash32> roots;
     // tree 0: empty preprocessed tree -> root = Blake2s("")
@@ -289,29 +302,6 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     if (invalid) return "Ciphertext does not match encryption - invalid witness";
     d_pt.release();
     d_ct.release();
-
-    // ---- statement
-    std::vector<uint8_t> stmt;
-    host::put_u32(stmt, (uint32_t)log_size);
-    host::put_bytes(stmt, nonce, 12);
-    host::put_u32(stmt, counter);
-    Hash32 pth, cth;
-    if (opt.pt_hash) {
-        memcpy(pth.b, opt.pt_hash, 32);
-        memcpy(cth.b, opt.ct_hash, 32);
-    } else if (opt.empty_public_hashes) {
-        pth = host::blake2s_bytes(nullptr, 0);
-        cth = pth;
-    } else {
-        pth = host::blake2s_bytes(plaintext, len);
-        cth = host::blake2s_bytes(ciphertext, len);
-    }
-    host::put_bytes(stmt, pth.b, 32);
-    host::put_bytes(stmt, cth.b, 32);
-    ch.mix_u64((uint64_t)log_size);
-    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[4 + 4 * i]));
-    ch.mix_u64(counter);
-    for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
 
     // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
     static const std::vector<Group> plan = build_plan();
@@ -362,17 +352,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 ctx->launches += nl;
                 ctx->fft_words += src.size();
             }
-            if (!g.comb.empty()) {
-                CombineJobs cj{};
-                for (auto& c : g.comb) {
-                    tiles.acquire(c.res, false, pass);
-                    cj.j[cj.n++] = {tiles.ptr(c.a), tiles.ptr(c.b), tiles.ptr(c.c), tiles.ptr(c.res)};
-                }
-                ctx->stage_begin("combine");
-                CB_CUDA(launch_combine_add(st, cj, M));
-                ctx->stage_end();
-                ctx->launches++;
-            }
+            for (auto& c : g.comb) tiles.acquire(c.res, false, pass);
             consume(gi, g);
             for (int w : g.free_after) tiles.release(w);
         }
@@ -389,7 +369,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         run_pass(1, [&](size_t gi, const Group& g) {
             LeafGroups lg{};
             lg.n = (int)g.hash.size();
-            for (int i = 0; i < lg.n; i++) lg.g[i] = {tiles.ptr(g.hash[i]), M, 32, m};
+            for (int i = 0; i < lg.n; i++) {
+                lg.g[i] = {tiles.ptr(g.hash[i]), M, 32, m, nullptr, nullptr, nullptr};
+                for (auto& c : g.comb)
+                    if (c.res == g.hash[i]) lg.g[i] = {tiles.ptr(c.a), M, 32, m, tiles.ptr(c.b), tiles.ptr(c.c), tiles.ptr(c.res)};
+            }
             ctx->stage_begin("trace_merkle_leaves");
             CB_CUDA(launch_merkle_leaves(st, lg, m, hstate.p, bytes_before, gi == 0, gi + 1 == plan.size(), tree1.nodes.p));
             ctx->stage_end();
@@ -404,8 +388,28 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         }
         ctx->stage_end();
         CB_CUDA(cudaMemcpyAsync(tree1.root.b, tree1.nodes.p + tree1.layer_offset(m) * 8, 32, cudaMemcpyDeviceToHost, st));
-        ctx->sync();
     }
+    // ---- statement (the two public-input hashes were computed on host threads while the GPU ran pass 1)
+    std::vector<uint8_t> stmt;
+    host::put_u32(stmt, (uint32_t)log_size);
+    host::put_bytes(stmt, nonce, 12);
+    host::put_u32(stmt, counter);
+    hashers.join();
+    if (opt.pt_hash) {
+        memcpy(pth.b, opt.pt_hash, 32);
+        memcpy(cth.b, opt.ct_hash, 32);
+    } else if (opt.empty_public_hashes) {
+        pth = host::blake2s_bytes(nullptr, 0);
+        cth = pth;
+    }
+    host::put_bytes(stmt, pth.b, 32);
+    host::put_bytes(stmt, cth.b, 32);
+    ch.mix_u64((uint64_t)log_size);
+    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[4 + 4 * i]));
+    ch.mix_u64(counter);
+    for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
+
+    ctx->sync();
     roots.push_back(tree1.root);
     ch.mix_root(tree1.root);
 
@@ -427,8 +431,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     run_pass(2, [&](size_t gi, const Group& g) {
         ConstraintJobs cj{};
         for (auto& c : g.cons)
-            cj.j[cj.n++] = {tiles.ptr(c.w0), c.w1 >= 0 ? tiles.ptr(c.w1) : nullptr, c.w2 >= 0 ? tiles.ptr(c.w2) : nullptr, c.k0, c.arg,
-                            c.type};
+            cj.j[cj.n++] = {c.w0 >= 0 ? tiles.ptr(c.w0) : nullptr, c.w1 >= 0 ? tiles.ptr(c.w1) : nullptr,
+                            c.w2 >= 0 ? tiles.ptr(c.w2) : nullptr, c.w3 >= 0 ? tiles.ptr(c.w3) : nullptr,
+                            c.w4 >= 0 ? tiles.ptr(c.w4) : nullptr, c.wres >= 0 ? tiles.ptr(c.wres) : nullptr,
+                            c.kx, c.kb0, c.kb1, c.kb2, c.kbc, c.arg, c.type};
+        if (cj.n == 0) return;
         ctx->stage_begin("constraints");
         CB_CUDA(launch_constraints_tiles(st, cj, M, apr.p, acc.p, gi == 0));
         ctx->stage_end();
