@@ -40,81 +40,102 @@ __global__ void __launch_bounds__(256) combine_add_kernel(CombineJobs jobs, size
     }
 }
 
-struct Acc4 {
-    uint64_t a[4];
-    int pending;
-    __device__ __forceinline__ void init() { a[0] = a[1] = a[2] = a[3] = 0; pending = 0; }
-    __device__ __forceinline__ void fold() {
+// Accumulator of sum_k alpha_k * C_k with alpha_k in QM31 (4 coordinates) and C_k in M31.  Every coordinate of alpha_k is
+// pre-split into 16-bit halves (two tables), so each product C * half < 2^48 and 2^16 products fit a 64-bit accumulator
+// without intermediate reduction: a multiply-accumulate is 8 IMAD.WIDE on the FMA pipe and nothing on the ALU pipe, which is
+// the pipe every other instruction of this kernel needs.  C may be any 32-bit representative (not necessarily < p).
+struct AccSplit {
+    uint64_t lo[4], hi[4];
+    __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int c = 0; c < 4; c++) a[c] = (a[c] & P) + (a[c] >> 31);
-        pending = 0;
+        for (int c = 0; c < 4; c++) lo[c] = hi[c] = 0;
     }
-    __device__ __forceinline__ void mac(uint4 al, uint32_t C) {
-        a[0] += (uint64_t)C * al.x; a[1] += (uint64_t)C * al.y; a[2] += (uint64_t)C * al.z; a[3] += (uint64_t)C * al.w;
-        if (++pending == 4) fold();  // 4*(p-1)^2 + fold residual < 2^64
+    __device__ __forceinline__ void mac(const uint4* __restrict__ tlo, const uint4* __restrict__ thi, int k, uint32_t C) {
+        const uint4 l = __ldg(tlo + k), h = __ldg(thi + k);
+        lo[0] += (uint64_t)C * l.x; lo[1] += (uint64_t)C * l.y; lo[2] += (uint64_t)C * l.z; lo[3] += (uint64_t)C * l.w;
+        hi[0] += (uint64_t)C * h.x; hi[1] += (uint64_t)C * h.y; hi[2] += (uint64_t)C * h.z; hi[3] += (uint64_t)C * h.w;
     }
+    __device__ __forceinline__ uint32_t result(int c) const { return addm(mulm(red64(hi[c]), 1u << 16), red64(lo[c])); }
 };
 
-// acc[row] += sum over jobs of sum_i apr[k] * C(row)   (apr[k] = alpha^(K-1-k), 4 coordinates)
-//   CJ_BOOL: C = b(1-b), b = t0[i], k = kb0 + i*step          (constraints_stream.rs:85-101 and the carry booleans :117-120)
-//   CJ_XOR : C = r - a - d + 2ad, r = t0[i], a = t1[s], d = t2[s], s = (i-rot) mod 32, k = kx + i   (:134-152), plus the
-//            boolean constraints of the operands the job has loaded anyway: r at kb0+i, a at kb1+s, d at kb2+s
-//   CJ_XORN: C = a + d - 2ad - r  (keystream xor plaintext = ciphertext, :60-68)
-__global__ void __launch_bounds__(128) constraints_tiles_kernel(ConstraintJobs jobs, size_t M, const uint4* __restrict__ apr,
-                                                                uint32_t* __restrict__ acc, int first) {
+// lazily reduced helpers: inputs canonical, outputs any representative < 2^32 unless noted
+// b - b^2 + p  in (0, 2p):  b2 = 2b (unreduced)
+__device__ __forceinline__ uint32_t bool_c(uint32_t b, uint32_t b2) {
+    const uint64_t v = (uint64_t)b * b2;
+    const uint32_t sq = redp((uint32_t)(v >> 32) + (((uint32_t)v) >> 1));
+    return b + P - sq;
+}
+
+// acc[row] += sum over jobs of sum_i apr[k] * C(row)   (apr[k] = alpha^(K-1-k), 4 coordinates, split in 16-bit halves)
+//   CJ_BOOL: C = b(1-b), b = t0[i], k = kb0 + i*step          (constraints_stream.rs:85-101)
+//   CJ_ADDX: one 32-bit adder (:104-131) and, optionally, the xor-rotate that consumes its sum (:134-152): the sum word
+//            s = a + b + carry_in - 2 carry is computed here (the adder identity itself is identically zero on the extended
+//            domain, kernels_stream.cu header) and stored for later groups; constraints: carry booleans at kbc + 2s, sum
+//            booleans at kb1 + s, xor x_i - s_j - d_j + 2 s_j d_j at kx + i (j = i - rot mod 32), result booleans at kb0 + i
+//   CJ_XORN: C = a + d - 2ad - r  (keystream xor plaintext = ciphertext, :60-68) with the booleans of r (kb0) and d (kb2)
+template <bool HAS_X>
+__device__ __forceinline__ void addx_job(const ConstraintJob& J, size_t row, size_t M, const uint4* __restrict__ tlo,
+                                         const uint4* __restrict__ thi, AccSplit& A) {
+    const uint32_t* x = HAS_X ? J.t0 + row : nullptr;
+    const uint32_t* a = J.t1 + row;
+    const uint32_t* d = HAS_X ? J.t2 + row : nullptr;
+    const uint32_t* b = J.t3 + row;
+    const uint32_t* cy = J.t4 + row;
+    uint32_t* res = J.res + row;
+    uint32_t cin = 0;
+    for (int s0 = 0; s0 < 32; s0 += 8) {
+        uint32_t av[8], bv[8], cv[8], xv[8], dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {  // all loads of the 8 bits first (the sum store may alias an operand tile)
+            const int s = s0 + u;
+            av[u] = a[(size_t)s * M];
+            bv[u] = b[(size_t)s * M];
+            cv[u] = cy[(size_t)s * M];
+            if (HAS_X) {
+                xv[u] = x[(size_t)((s + J.arg) & 31) * M];
+                dv[u] = d[(size_t)s * M];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int s = s0 + u;
+            const uint32_t c2 = cv[u] + cv[u];
+            const uint32_t sv = subm(redp(redp(av[u] + bv[u]) + cin), redp(c2));
+            cin = cv[u];
+            res[(size_t)s * M] = sv;
+            const uint32_t s2 = sv + sv;
+            A.mac(tlo, thi, J.kbc + 2 * s, bool_c(cv[u], c2));
+            A.mac(tlo, thi, J.kb1 + s, bool_c(sv, s2));
+            if (HAS_X) {
+                const int i = (s + J.arg) & 31;
+                const uint64_t v = (uint64_t)dv[u] * s2;  // d * (2s) / 2 = s d (mulw form)
+                const uint32_t sd = redp((uint32_t)(v >> 32) + (((uint32_t)v) >> 1));
+                const uint32_t up = redp(redp(xv[u] + sd) + sd), dn = redp(sv + dv[u]);
+                A.mac(tlo, thi, J.kx + i, up + P - dn);
+                A.mac(tlo, thi, J.kb0 + i, bool_c(xv[u], xv[u] + xv[u]));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) constraints_tiles_kernel(ConstraintJobs jobs, size_t M, const uint4* __restrict__ tlo,
+                                                                const uint4* __restrict__ thi, uint32_t* __restrict__ acc,
+                                                                int first) {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= M) return;
-    Acc4 A;
+    AccSplit A;
     A.init();
     for (int j = 0; j < jobs.n; j++) {
-        const ConstraintJob J = jobs.j[j];
-        if (J.type == CJ_BOOL) {
+        const ConstraintJob& J = jobs.j[j];
+        if (J.type == CJ_ADDX) {
+            if (J.t0) addx_job<true>(J, row, M, tlo, thi, A);
+            else addx_job<false>(J, row, M, tlo, thi, A);
+        } else if (J.type == CJ_BOOL) {
             const uint32_t* __restrict__ t = J.t0 + row;
-            const uint4* __restrict__ al = apr + J.kb0;
 #pragma unroll 8
             for (int i = 0; i < 32; i++) {
-                uint32_t b = t[(size_t)i * M];
-                A.mac(__ldg(al + i * J.arg), mulm(b, subm(1, b)));
-            }
-        } else if (J.type == CJ_ADDX) {
-            // adder with the sum computed on the fly (and stored for later groups): carry booleans, sum booleans and, when the
-            // sum feeds a xor-rotate, the xor constraints and the result booleans.  Operands are staged 8 bits at a time so
-            // the loads are in flight together (the sum store may alias an operand tile).
-            const uint32_t* x = J.t0 ? J.t0 + row : nullptr;
-            const uint32_t* a = J.t1 + row;
-            const uint32_t* d = J.t2 ? J.t2 + row : nullptr;
-            const uint32_t* b = J.t3 + row;
-            const uint32_t* cy = J.t4 + row;
-            uint32_t* res = J.res + row;
-            uint32_t cin = 0;
-            for (int s0 = 0; s0 < 32; s0 += 8) {
-                uint32_t av[8], bv[8], cv[8], xv[8], dv[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int s = s0 + u;
-                    av[u] = a[(size_t)s * M];
-                    bv[u] = b[(size_t)s * M];
-                    cv[u] = cy[(size_t)s * M];
-                    if (x) {
-                        xv[u] = x[(size_t)((s + J.arg) & 31) * M];
-                        dv[u] = d[(size_t)s * M];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int s = s0 + u;
-                    const uint32_t sv = subm(addm(addm(av[u], bv[u]), cin), dbl(cv[u]));
-                    cin = cv[u];
-                    res[(size_t)s * M] = sv;
-                    A.mac(__ldg(apr + J.kbc + 2 * s), mulm(cv[u], subm(1, cv[u])));
-                    A.mac(__ldg(apr + J.kb1 + s), mulm(sv, subm(1, sv)));
-                    if (x) {
-                        const int i = (s + J.arg) & 31;
-                        const uint32_t sd = mulm(sv, dv[u]);
-                        A.mac(__ldg(apr + J.kx + i), addm(subm(subm(xv[u], sv), dv[u]), dbl(sd)));
-                        A.mac(__ldg(apr + J.kb0 + i), mulm(xv[u], subm(1, xv[u])));
-                    }
-                }
+                const uint32_t b = t[(size_t)i * M];
+                A.mac(tlo, thi, J.kb0 + i * J.arg, bool_c(b, b + b));
             }
         } else {
             const uint32_t* __restrict__ r = J.t0 + row;
@@ -128,21 +149,29 @@ __global__ void __launch_bounds__(128) constraints_tiles_kernel(ConstraintJobs j
                 const uint32_t ad = mulm(av, dv);
                 uint32_t C = addm(subm(subm(rv, av), dv), dbl(ad));
                 if (neg) C = subm(0, C);
-                A.mac(__ldg(apr + J.kx + i), C);
-                if (J.kb0 >= 0) A.mac(__ldg(apr + J.kb0 + i), mulm(rv, subm(1, rv)));
-                if (J.kb1 >= 0) A.mac(__ldg(apr + J.kb1 + s), mulm(av, subm(1, av)));
-                if (J.kb2 >= 0) A.mac(__ldg(apr + J.kb2 + s), mulm(dv, subm(1, dv)));
+                A.mac(tlo, thi, J.kx + i, C);
+                if (J.kb0 >= 0) A.mac(tlo, thi, J.kb0 + i, bool_c(rv, rv + rv));
+                if (J.kb1 >= 0) A.mac(tlo, thi, J.kb1 + s, bool_c(av, av + av));
+                if (J.kb2 >= 0) A.mac(tlo, thi, J.kb2 + s, bool_c(dv, dv + dv));
             }
         }
     }
-    A.fold();
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        uint32_t v = red64(A.a[c]);
+        uint32_t v = A.result(c);
         uint32_t* o = acc + (size_t)c * M + row;
         if (!first) v = addm(v, *o);
         *o = v;
     }
+}
+
+// split a table of QM31 values (4 words each) into 16-bit halves
+__global__ void split16_kernel(const uint4* __restrict__ t, int n, uint4* __restrict__ lo, uint4* __restrict__ hi) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint4 v = t[k];
+    lo[k] = make_uint4(v.x & 0xffffu, v.y & 0xffffu, v.z & 0xffffu, v.w & 0xffffu);
+    hi[k] = make_uint4(v.x >> 16, v.y >> 16, v.z >> 16, v.w >> 16);
 }
 
 // acc[c][row] *= den_inv[row >> trace_log]
@@ -246,11 +275,17 @@ cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr, uint32_t* acc,
-                                     int first) {
+// apr_lo / apr_hi: the reversed alpha-power table split by launch_split16
+cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
+                                     const uint32_t* apr_hi, uint32_t* acc, int first) {
     int threads = M >= 128 * 148 ? 128 : 32;
-    strm::constraints_tiles_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(jobs, M, (const uint4*)apr, acc,
-                                                                                               first);
+    strm::constraints_tiles_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
+        jobs, M, (const uint4*)apr_lo, (const uint4*)apr_hi, acc, first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi) {
+    strm::split16_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint4*)table, n, (uint4*)lo, (uint4*)hi);
     return cudaGetLastError();
 }
 

@@ -416,8 +416,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- composition polynomial (pass 2): constraint quotients accumulated tile by tile
     QM31 random_coeff = ch.draw_secure_felt();
     DBuf<uint32_t> apr(ctx, (size_t)N_CONSTRAINTS * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, 4 * M);
+    DBuf<uint32_t> apr_lo(ctx, (size_t)N_CONSTRAINTS * 4), apr_hi(ctx, (size_t)N_CONSTRAINTS * 4);
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
-    ctx->launches++;
+    CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
+    ctx->launches += 2;
     {
         std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);
         for (uint32_t i = 0; i < den.size(); i++) {
@@ -437,7 +439,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                             c.kx, c.kb0, c.kb1, c.kb2, c.kbc, c.arg, c.type};
         if (cj.n == 0) return;
         ctx->stage_begin("constraints");
-        CB_CUDA(launch_constraints_tiles(st, cj, M, apr.p, acc.p, gi == 0));
+        CB_CUDA(launch_constraints_tiles(st, cj, M, apr_lo.p, apr_hi.p, acc.p, gi == 0));
         ctx->stage_end();
         ctx->launches++;
     });
