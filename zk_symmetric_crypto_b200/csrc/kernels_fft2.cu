@@ -131,6 +131,7 @@ __device__ __forceinline__ void apply_layers(uint32_t* s, int ncol, int colstrid
 
 struct Jobs {
     int n;                    // jobs in this launch (<= MAX_FFT_JOBS)
+    uint32_t one, mone;       // run-time 1 and -1: x*one+y compiles to IMAD, moving butterfly additions to the FMA pipe
     const uint32_t* src[MAX_FFT_JOBS];  // packed witness word row (2^n words)
     uint32_t* out[MAX_FFT_JOBS];        // LDE tile [cols_per_job][2^(n+1)]
 };
@@ -277,8 +278,15 @@ __device__ __forceinline__ void load_tw(uint32_t (&tw)[1 << R], const uint32_t* 
     }
 }
 
+// a + b and a - b issued as IMAD (FMA pipe) instead of IADD3 (ALU pipe): the butterflies are ALU-pipe bound otherwise
+__device__ __forceinline__ uint32_t addf(uint32_t a, uint32_t b, uint32_t one) { return redp(a * one + b); }
+__device__ __forceinline__ uint32_t subf(uint32_t a, uint32_t b, uint32_t mone) {
+    uint32_t d = b * mone + a;
+    return __viaddmin_u32(d, P, d);
+}
+
 template <int R>
-__device__ __forceinline__ void inv_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R]) {
+__device__ __forceinline__ void inv_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R], uint32_t one, uint32_t mone) {
 #pragma unroll
     for (int l = 0; l < R; l++) {
 #pragma unroll
@@ -286,14 +294,14 @@ __device__ __forceinline__ void inv_block(uint32_t (&v)[1 << R], const uint32_t 
             if (k & (1 << l)) continue;
             const uint32_t w2 = tw[(1 << (R - 1 - l)) - 1 + (k >> (l + 1))];
             uint32_t v0 = v[k], v1 = v[k | (1 << l)];
-            v[k] = addm(v0, v1);
-            v[k | (1 << l)] = mulw(subm(v0, v1), w2);
+            v[k] = addf(v0, v1, one);
+            v[k | (1 << l)] = mulw(subf(v0, v1, mone), w2);
         }
     }
 }
 
 template <int R>
-__device__ __forceinline__ void fwd_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R]) {
+__device__ __forceinline__ void fwd_block(uint32_t (&v)[1 << R], const uint32_t (&tw)[1 << R], uint32_t one, uint32_t mone) {
 #pragma unroll
     for (int l = R - 1; l >= 0; l--) {
 #pragma unroll
@@ -301,8 +309,8 @@ __device__ __forceinline__ void fwd_block(uint32_t (&v)[1 << R], const uint32_t 
             if (k & (1 << l)) continue;
             const uint32_t w2 = tw[(1 << (R - 1 - l)) - 1 + (k >> (l + 1))];
             uint32_t v0 = v[k], t = mulw(v[k | (1 << l)], w2);
-            v[k] = addm(v0, t);
-            v[k | (1 << l)] = subm(v0, t);
+            v[k] = addf(v0, t, one);
+            v[k | (1 << l)] = subf(v0, t, mone);
         }
     }
 }
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
     for (int c = 0; c < NC; c++) {
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = unpack<KIND>(w[k], c0 + c, scale, scale2);
-        inv_block<4>(v, twr);
+        inv_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
         for (int i = 0; i < 4; i++) *(uint4*)(s + c * COLW + va[i]) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
-            inv_block<4>(v, twr);
+            inv_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
         }
@@ -367,7 +375,7 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
-            inv_block<4>(v, twr);
+            inv_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < 16; k++) out[((size_t)c << log_n) + 256 * k] = v[k];
         }
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = data[((size_t)c << m) + p + 256 * k];
-            fwd_block<4>(v, twr);
+            fwd_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
         }
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
         for (int c = 0; c < NC; c++) {
 #pragma unroll
             for (int k = 0; k < 16; k++) v[k] = s[c * COLW + ad[k]];
-            fwd_block<4>(v, twr);
+            fwd_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
         }
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
                 uint4 x = *(const uint4*)(s + c * COLW + va[i]);
                 v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             }
-            fwd_block<4>(v, twr);
+            fwd_block<4>(v, twr, jobs.one, jobs.mone);
             uint4* o = (uint4*)(data + ((size_t)c << m) + 16 * p);
 #pragma unroll
             for (int i = 0; i < 4; i++) o[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -453,14 +461,14 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
         load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, 0, 0);
 #pragma unroll
         for (int k = 0; k < J; k++) v[k] = in[(size_t)k << K1];
-        inv_block<RA>(v, twr);
+        inv_block<RA>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             uint32_t u[1 << RA];
 #pragma unroll
             for (int k = 0; k < J; k++) u[k] = v[k];
             load_tw<RA>(twr, tw.X, tw.Y, m, K1, (uint32_t)h << JB, 0);
-            fwd_block<RA>(u, twr);
+            fwd_block<RA>(u, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < J; k++) out[((size_t)h << log_n) + ((size_t)k << K1)] = u[k];
         }
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
         load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, (uint32_t)j0, 0);
 #pragma unroll
         for (int k = 0; k < (1 << RA); k++) v[k] = in[(size_t)(j0 + k) << K1];
-        inv_block<RA>(v, twr);
+        inv_block<RA>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
         for (int k = 0; k < (1 << RA); k++) s0[((j0 + k) << 5) | q] = v[k];
     }
@@ -486,14 +494,14 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
         load_tw<RBs>(twb, tw.IX, tw.IY, log_n, K1 + RA, (uint32_t)pb, RA);
 #pragma unroll
         for (int k = 0; k < (1 << RBs); k++) c[k] = s0[((pb + (k << RA)) << 5) | q];
-        inv_block<RBs>(c, twb);
+        inv_block<RBs>(c, twb, jobs.one, jobs.mone);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             uint32_t u[1 << RBs];
 #pragma unroll
             for (int k = 0; k < (1 << RBs); k++) u[k] = c[k];
             load_tw<RBs>(twb, tw.X, tw.Y, m, K1 + RA, ((uint32_t)h << JB) | (uint32_t)pb, RA);
-            fwd_block<RBs>(u, twb);
+            fwd_block<RBs>(u, twb, jobs.one, jobs.mone);
             uint32_t* sh = h ? s1 : s0;
 #pragma unroll
             for (int k = 0; k < (1 << RBs); k++) sh[((pb + (k << RA)) << 5) | q] = u[k];
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
         load_tw<RA>(twr, tw.X, tw.Y, m, K1, ((uint32_t)h << JB) | (uint32_t)j0, 0);
 #pragma unroll
         for (int k = 0; k < (1 << RA); k++) v[k] = sh[((j0 + k) << 5) | q];
-        fwd_block<RA>(v, twr);
+        fwd_block<RA>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
         for (int k = 0; k < (1 << RA); k++) out[((size_t)h << log_n) + ((size_t)(j0 + k) << K1)] = v[k];
     }
@@ -529,7 +537,8 @@ constexpr int SMEM_MAX = 72 * 1024;
 
 }  // namespace fft2
 
-int g_force_generic_fft = 0;  // tests: exercise the generic (runtime-schedule) kernels at sizes the v2 kernels cover
+int g_force_generic_fft = 0;
+int g_fft_fma_adds = 1;  // tests: exercise the generic (runtime-schedule) kernels at sizes the v2 kernels cover
 
 void fft2_init_attrs() {
     using namespace fft2;
@@ -564,6 +573,8 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
     for (int j0 = 0; j0 < njobs; j0 += MAX_FFT_JOBS) {
         Jobs jobs;
         jobs.n = njobs - j0 < MAX_FFT_JOBS ? njobs - j0 : MAX_FFT_JOBS;
+        jobs.one = 1u;
+        jobs.mone = 0xffffffffu;
         for (int j = 0; j < jobs.n; j++) { jobs.src[j] = src[j0 + j]; jobs.out[j] = out[j0 + j]; }
         if (log_n <= 12) {
             const int big = 2 << log_n;
