@@ -50,6 +50,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
+    ctx->release_arena();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

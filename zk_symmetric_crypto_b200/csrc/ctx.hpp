@@ -42,6 +42,12 @@ struct cb_ctx {
     uint64_t fft_words = 0;
     int cached_tiles = 0, transient_tiles = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
 
+    // persistent work arena of the streaming provers (LDE tile slots): allocated once with cudaMalloc and kept between
+    // proofs -- re-allocating ~170 GB from the stream-ordered pool per proof costs up to 0.3 s when the pool has fragmented
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    void* ensure_arena(size_t bytes);
+    void release_arena();
     void ensure_twiddles(int max_log);
     void* dmalloc(size_t bytes);
     void dfree(void* p);

@@ -317,7 +317,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         uint64_t reserved = 0, used = 0;
         CB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
         CB_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
-        const size_t avail = free_b + (size_t)(reserved - used);
+        const size_t avail = free_b + (size_t)(reserved - used) + ctx->arena_bytes;  // the arena is re-used (or re-made)
         // everything else this proof allocates: scratch, leaf state + tree (24 M words), accumulators / composition /
         // quotient / FRI columns (~48 M words), plus slack for the allocator
         const size_t other = (scratch_words + 96 * M) * 4 + ((size_t)3 << 30);
@@ -328,10 +328,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         if (cap >= 0 && n_cache > cap) n_cache = cap;
         if ((size_t)n_cache > can - peak_trans) n_cache = (int)(can - peak_trans);
     }
-    DBuf<uint32_t> arena(ctx, (size_t)(n_cache + peak_trans) * tile_words);
-    DBuf<uint32_t> scratch(ctx, scratch_words);
+    // tile slots + FFT scratch live in the context's persistent arena
+    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_words;
+    uint32_t* arena_p;
+    if (ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30))
+        arena_p = (uint32_t*)ctx->arena;
+    else {
+        ctx->release_arena();
+        arena_p = (uint32_t*)ctx->ensure_arena(arena_words * 4);
+    }
+    uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words;
     Tiles tiles;
-    tiles.init(n_cache, peak_trans, tile_words, arena.p);
+    tiles.init(n_cache, peak_trans, tile_words, arena_p);
     ctx->fft_words = 0;
     ctx->cached_tiles = n_cache;
     ctx->transient_tiles = peak_trans;
@@ -348,7 +356,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 }
             if (!src.empty()) {
                 int nl = 0;
-                CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch.p, hkp, &nl));
+                CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl));
                 ctx->launches += nl;
                 ctx->fft_words += src.size();
             }
@@ -445,8 +453,6 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     });
     CB_CUDA(launch_scale_rows(st, acc.p, M, n, d_den.p));
     ctx->launches++;
-    arena.release();
-    scratch.release();
 
     ctx->stage_begin("composition_commit");
     // interpolate the 4 coordinate columns (log m), split into halves, evaluate each half (log n) on the LDE domain

@@ -17,6 +17,27 @@ void cb_ctx::ensure_twiddles(int max_log) {
     sync();
 }
 
+void* cb_ctx::ensure_arena(size_t bytes) {
+    if (arena && arena_bytes >= bytes) return arena;
+    release_arena();
+    // give cached pool memory back to the device before the big allocation
+    cudaMemPool_t pool;
+    CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    sync();
+    CB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    CB_CUDA(cudaMalloc(&arena, bytes));
+    arena_bytes = bytes;
+    return arena;
+}
+void cb_ctx::release_arena() {
+    if (arena) {
+        sync();
+        cudaFree(arena);
+    }
+    arena = nullptr;
+    arena_bytes = 0;
+}
+
 void* cb_ctx::dmalloc(size_t bytes) {
     void* p = nullptr;
     CB_CUDA(cudaMallocAsync(&p, bytes, stream));
