@@ -165,10 +165,12 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("S2C_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import numpy as np
     import torch
     import torch.distributed as dist
     import zk_symmetric_crypto_b200 as z
+    from zk_symmetric_crypto_b200 import sharding
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -210,11 +212,8 @@ def main():
         wall = time.perf_counter() - t0
         dev_ms = e0.elapsed_time(e1)
         ms = dev_ms  # device clock on the launching stream (the proof call is host-synchronous, so this is the step time)
-        if world > 1:
-            t = torch.tensor([ms, wall * 1000.0], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1]) / 1000.0
-        return ms, wall, proof
+        ms, wall_ms = sharding.max_over_ranks([ms, wall * 1000.0], device="cuda")  # multi-GPU numbers: max over ranks
+        return ms, wall_ms / 1000.0, proof
 
     for _ in range(max(args.warmup, 3)):
         proof = step_dev()
