@@ -30,6 +30,10 @@ int cb_init(int device, cb_ctx** out) {
         ctx->device = device;
         CB_CUDA(cudaSetDevice(device));
         CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        // measured on B200 at log 18/20: no gain (both kernels fill the GPU; the block scheduler runs them back to back), so
+        // the second stream is opt-in
+        ctx->overlap = getenv("S2C_OVERLAP") && atoi(getenv("S2C_OVERLAP"));
         cudaMemPool_t pool;
         CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thr = UINT64_MAX;
@@ -51,6 +55,8 @@ void cb_destroy(cb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
     ctx->release_arena();
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -28,6 +28,11 @@ struct cb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    // producer stream of the streaming provers: LDE tiles of group g+1 are transformed here while `stream` consumes group g
+    cudaStream_t stream2 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;  // timing-disabled events for the producer/consumer hand-off
+    cudaEvent_t event(size_t i);
+    bool overlap = true;
     std::string err;
     // twiddles (device) for canonic domains up to tw.max_log
     FftTables tw{nullptr, nullptr, nullptr, nullptr, 0};

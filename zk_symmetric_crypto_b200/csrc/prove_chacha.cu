@@ -193,6 +193,10 @@ struct Tiles {
     size_t tile_words = 0;
     uint32_t* arena = nullptr;
     std::vector<int> slot_of, cache_slot, free_trans;
+    // slots released while group g is processed become reusable `lag` groups later (lag 2 when tiles are produced on a second
+    // stream: the producer of group g only waits for the consumer of group g-2)
+    std::vector<std::vector<int>> pending;
+    int lag = 0, group = 0;
     int in_use = 0, peak = 0;
     void init(int cache, int trans, size_t tw_, uint32_t* mem) {
         n_cache = cache; n_trans = trans; tile_words = tw_; arena = mem; cache_used = 0;
@@ -201,6 +205,23 @@ struct Tiles {
         free_trans.clear();
         for (int i = trans - 1; i >= 0; i--) free_trans.push_back(i);
         in_use = peak = 0;
+        pending.clear();
+        group = 0;
+    }
+    void begin_group(int g) {
+        group = g;
+        if ((int)pending.size() <= g) pending.resize(g + 1);
+        if (g - lag >= 0)
+            for (int s = 0; s <= g - lag; s++) {
+                for (int x : pending[s]) { free_trans.push_back(x); in_use--; }
+                pending[s].clear();
+            }
+    }
+    void flush() {  // all work using the released slots has completed
+        for (auto& v : pending) {
+            for (int x : v) { free_trans.push_back(x); in_use--; }
+            v.clear();
+        }
     }
     uint32_t* ptr(int w) const {
         if (slot_of[w] < 0) throw CbError("internal: tile of word " + std::to_string(w) + " is not live");
@@ -218,15 +239,21 @@ struct Tiles {
     }
     void release(int w) {
         if (slot_of[w] < 0) return;
-        if (slot_of[w] >= n_cache) { free_trans.push_back(slot_of[w] - n_cache); in_use--; }
+        if (slot_of[w] >= n_cache) {
+            if ((int)pending.size() <= group) pending.resize(group + 1);
+            pending[group].push_back(slot_of[w] - n_cache);
+        }
         slot_of[w] = -1;
     }
 };
 
-int plan_peak_transient(const std::vector<Group>& plan) {
+int plan_peak_transient(const std::vector<Group>& plan, int lag) {
     Tiles t;
     t.init(0, N_WORDS, 0, nullptr);
+    t.lag = lag;
+    int gi = 0;
     for (auto& g : plan) {
+        t.begin_group(gi++);
         for (int w : g.fft) t.acquire(w, true, 1);
         for (auto& c : g.comb) t.acquire(c.res, false, 1);
         for (int w : g.free_after) t.release(w);
@@ -305,7 +332,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
     static const std::vector<Group> plan = build_plan();
-    static const int peak_trans = plan_peak_transient(plan);
+    // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
+    const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr;
+    const int lag = overlap ? 2 : 0;
+    static const int peak_trans_lag[3] = {plan_peak_transient(plan, 0), 0, plan_peak_transient(plan, 2)};
+    const int peak_trans = peak_trans_lag[lag];
+    cudaStream_t sf = overlap ? ctx->stream2 : st;
     const size_t tile_words = 32 * M;
     const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, MAX_FFT_JOBS, n);
     int n_cache = N_INDEP_WORDS;
@@ -340,13 +372,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words;
     Tiles tiles;
     tiles.init(n_cache, peak_trans, tile_words, arena_p);
+    tiles.lag = lag;
     ctx->fft_words = 0;
     ctx->cached_tiles = n_cache;
     ctx->transient_tiles = peak_trans;
 
     auto run_pass = [&](int pass, auto&& consume) {
-        for (size_t gi = 0; gi < plan.size(); gi++) {
+        const size_t G = plan.size();
+        tiles.flush();
+        for (size_t gi = 0; gi < G; gi++) {
             const Group& g = plan[gi];
+            tiles.begin_group((int)gi);
             std::vector<const uint32_t*> src;
             std::vector<uint32_t*> out;
             for (int w : g.fft)
@@ -355,16 +391,24 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     out.push_back(tiles.ptr(w));
                 }
             if (!src.empty()) {
+                // producer: may overwrite slots released two groups ago -> wait for that group's consumer
+                if (overlap && gi >= 2) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(G + gi - 2), 0));
                 int nl = 0;
-                CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl));
+                CB_CUDA(launch_fft_packed(sf, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl));
                 ctx->launches += nl;
                 ctx->fft_words += src.size();
+                if (overlap) {
+                    CB_CUDA(cudaEventRecord(ctx->event(gi), sf));
+                    CB_CUDA(cudaStreamWaitEvent(st, ctx->event(gi), 0));
+                }
             }
             for (auto& c : g.comb) tiles.acquire(c.res, false, pass);
             consume(gi, g);
+            if (overlap) CB_CUDA(cudaEventRecord(ctx->event(G + gi), st));
             for (int w : g.free_after) tiles.release(w);
         }
         for (int w = 0; w < N_WORDS; w++) tiles.release(w);
+        if (overlap) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(2 * G - 1), 0));  // next pass's producer starts after this pass
     };
 
     // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree

@@ -17,6 +17,15 @@ void cb_ctx::ensure_twiddles(int max_log) {
     sync();
 }
 
+cudaEvent_t cb_ctx::event(size_t i) {
+    while (ev_pool.size() <= i) {
+        cudaEvent_t e;
+        CB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev_pool.push_back(e);
+    }
+    return ev_pool[i];
+}
+
 void* cb_ctx::ensure_arena(size_t bytes) {
     if (arena && arena_bytes >= bytes) return arena;
     release_arena();
