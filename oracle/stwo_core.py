@@ -571,7 +571,10 @@ class MerkleTree:
         n = 1 << L
         mat = np.empty((n, len(columns)), dtype="<u4")
         idx = np.arange(n)
-        for j, (c, lg) in enumerate(zip(columns, logs)):
+        # columns of different sizes enter the leaf hash sorted by size, smallest first, original order within a size
+        # (pinned against the reference binary on an AES-CTR proof at log 9, whose trees mix log-8 table columns)
+        order = sorted(range(len(columns)), key=lambda j: logs[j])
+        for j, (c, lg) in enumerate(zip([columns[k] for k in order], [logs[k] for k in order])):
             if lg == L:
                 mat[:, j] = c
             else:
