@@ -125,6 +125,18 @@ int cb_gen_trace_chacha_stream(cb_ctx* ctx, const uint8_t key[32], const uint8_t
 int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
                                 uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
                                 size_t ciphertext_len, char** json_out, size_t* json_len);
+/* wasm_api.rs:652-772 / 776-896: AES-128 / AES-256 CTR proofs (16-byte blocks, counter big-endian in the counter block);
+ * JSON {"success":true,"blocks":N,"algorithm":"aes128-ctr"|"aes256-ctr","proof":"<base64 bincode AESCtrProof>",
+ * "proof_size_bytes":S} or {"error":"..."} with the reference's messages. */
+int s2c_generate_aes128_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                  uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                                  size_t ciphertext_len, char** json_out, size_t* json_len);
+int s2c_generate_aes256_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                  uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                                  size_t ciphertext_len, char** json_out, size_t* json_len);
+/* Raw form: proof bytes (bincode AESCtrProof); key_len selects AES-128 (16) or AES-256 (32). */
+int s2c_prove_aes_ctr_raw(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter,
+                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, uint8_t** proof_out, size_t* proof_len);
 /* Raw form used by the benchmark and tests: proof bytes (bincode StreamProof) instead of base64-in-JSON. */
 int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            const uint8_t* ciphertext, size_t len, uint8_t** proof_out, size_t* proof_len);

@@ -284,3 +284,49 @@ def test_reference_verifier_accepts_gpu_proofs(backend, nb):
     assert ref_wasm.verify_chacha20_proof(res["proof"], nonce, counter, bytes(bad), ct)["valid"] is False
     if nb <= 512:
         assert ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof"] == res["proof"]
+
+
+# ---------------------------------------------------------------------------------------------------- AES-CTR
+import aes_api as oracle_aes
+from make_golden_aes import aes_case_inputs
+AES_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "aes_ctr_golden.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", AES_GOLDEN, ids=lambda c: c["name"])
+def test_aes_proof_bytes_match_golden(backend, case):
+    """AES-128/256-CTR proofs byte-identical to the reference's (fixtures generated by the reference binary): log 8 (all
+    columns one size), log 9 / 10 (lifted S-box table columns), invalid witness."""
+    key, nonce, counter, pt, ct = aes_case_inputs(case["key_len"], case["n_blocks"], case["seed"], case["corrupt"])
+    fn = backend.generate_aes128_ctr_proof if case["key_len"] == 16 else backend.generate_aes256_ctr_proof
+    res = fn(key, nonce, counter, pt, ct)
+    if "error" in case:
+        assert res == {"error": case["error"]}
+        return
+    assert res["success"] is True and res["blocks"] == case["blocks"] and res["algorithm"] == case["algorithm"]
+    assert res["proof_size_bytes"] == case["proof_size_bytes"]
+    assert hashlib.sha256(res["proof"].encode()).hexdigest() == case["b64_sha256"]
+
+
+def test_aes_proof_matches_oracle_bytes(backend):
+    key, nonce, counter, pt, ct = aes_case_inputs(16, 7, 77)
+    want = oracle_aes.generate_aes128_ctr_proof(key, nonce, counter, pt, ct)["proof_bytes"]
+    assert backend.prove_aes_ctr_raw(key, nonce, counter, pt, ct) == want
+
+
+def test_aes_error_behaviour(backend):
+    z = bytes(16)
+    assert backend.generate_aes128_ctr_proof(bytes(15), bytes(12), 0, z, z) == {"error": "Key must be 16 bytes, got 15"}
+    assert backend.generate_aes256_ctr_proof(bytes(16), bytes(12), 0, z, z) == {"error": "Key must be 32 bytes, got 16"}
+    assert backend.generate_aes128_ctr_proof(bytes(16), bytes(12), 0, z, z) == \
+        {"error": "Ciphertext does not match encryption - invalid witness"}
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not on this box")
+def test_reference_verifier_accepts_gpu_aes_proofs(backend):
+    """A size beyond the golden set (log 12, 4,096 blocks): the reference's verifier is the acceptance test."""
+    key, nonce, counter, pt, ct = aes_case_inputs(32, 4096, 99)
+    res = backend.generate_aes256_ctr_proof(key, nonce, counter, pt, ct)
+    assert res.get("success") is True, res
+    assert ref_wasm.verify_aes_ctr_proof(res["proof"], nonce, counter, pt, ct) == {"algorithm": "aes256-ctr", "valid": True}
+    bad = bytearray(ct); bad[3] ^= 1
+    assert ref_wasm.verify_aes_ctr_proof(res["proof"], nonce, counter, pt, bytes(bad))["valid"] is False

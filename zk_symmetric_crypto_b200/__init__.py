@@ -7,8 +7,9 @@ argument meaning and JSON results.  There is NO CPU fallback: importing works wi
 raises `BackendError` if libs2c_b200.so or a CUDA device is missing.
 """
 from .backend import (BackendError, Backend, lib, lib_path, generate_chacha20_proof, prove_chacha20_raw,
+                      generate_aes128_ctr_proof, generate_aes256_ctr_proof,
                       debug_chacha20_keystream, get_circuits_info, EXPORTED_SYMBOLS)
 from .operator import make_stwo_zk_operator
 
-__all__ = ["BackendError", "Backend", "lib", "lib_path", "generate_chacha20_proof", "prove_chacha20_raw",
+__all__ = ["BackendError", "Backend", "lib", "lib_path", "generate_chacha20_proof", "prove_chacha20_raw", "generate_aes128_ctr_proof", "generate_aes256_ctr_proof",
            "debug_chacha20_keystream", "get_circuits_info", "make_stwo_zk_operator", "EXPORTED_SYMBOLS"]

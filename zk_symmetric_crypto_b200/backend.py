@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = [
     "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
     "cb_gen_trace_chacha_stream",
-    "s2c_generate_chacha20_proof", "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_counters",
+    "s2c_generate_chacha20_proof", "s2c_generate_aes128_ctr_proof", "s2c_generate_aes256_ctr_proof", "s2c_prove_aes_ctr_raw",
+    "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_counters",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
 ]
 
@@ -181,6 +182,35 @@ class Backend:
         return _take_json(self.L, out, n)
 
 
+    def _generate_aes(self, fn, key, nonce, counter, plaintext, ciphertext):
+        key, nonce, pb, cbuf = bytes(key), bytes(nonce), bytes(plaintext), bytes(ciphertext)
+        out = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        rc = fn(self.ctx, key, ctypes.c_size_t(len(key)), nonce, ctypes.c_size_t(len(nonce)), ctypes.c_uint32(counter & 0xFFFFFFFF),
+                pb, ctypes.c_size_t(len(pb)), cbuf, ctypes.c_size_t(len(cbuf)), ctypes.byref(out), ctypes.byref(n))
+        if not out:
+            raise BackendError("AES-CTR proof call failed with status %d" % rc)
+        return _take_json(self.L, out, n)
+
+    def generate_aes128_ctr_proof(self, key, nonce, counter, plaintext, ciphertext):
+        """wasm_api.rs:652 generate_aes128_ctr_proof -> dict (same keys as the reference's JSON)."""
+        return self._generate_aes(self.L.s2c_generate_aes128_ctr_proof, key, nonce, counter, plaintext, ciphertext)
+
+    def generate_aes256_ctr_proof(self, key, nonce, counter, plaintext, ciphertext):
+        """wasm_api.rs:776 generate_aes256_ctr_proof."""
+        return self._generate_aes(self.L.s2c_generate_aes256_ctr_proof, key, nonce, counter, plaintext, ciphertext)
+
+    def prove_aes_ctr_raw(self, key, nonce, counter, plaintext, ciphertext):
+        key, nonce, pb, cbuf = bytes(key), bytes(nonce), bytes(plaintext), bytes(ciphertext)
+        out = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self._ck(self.L.s2c_prove_aes_ctr_raw(self.ctx, len(key), key, nonce, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,
+                                              ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n)))
+        proof = ctypes.string_at(out, n.value)
+        self.L.s2c_free(out)
+        return proof
+
+
 _DEFAULT = None
 
 
@@ -198,6 +228,14 @@ def generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext):
 
 def prove_chacha20_raw(key, nonce, counter, plaintext, ciphertext):
     return _default().prove_chacha20_raw(key, nonce, counter, plaintext, ciphertext)
+
+
+def generate_aes128_ctr_proof(key, nonce, counter, plaintext, ciphertext):
+    return _default().generate_aes128_ctr_proof(key, nonce, counter, plaintext, ciphertext)
+
+
+def generate_aes256_ctr_proof(key, nonce, counter, plaintext, ciphertext):
+    return _default().generate_aes256_ctr_proof(key, nonce, counter, plaintext, ciphertext)
 
 
 def debug_chacha20_keystream(key, nonce, counter):

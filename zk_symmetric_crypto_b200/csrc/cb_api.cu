@@ -508,6 +508,73 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
     return ret_json(js, json_out, json_len);
 }
 
+static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const uint8_t* key, size_t key_len, const uint8_t* nonce,
+                        size_t nonce_len, uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len,
+                        char** json_out, size_t* json_len) {
+    // validation order and messages: wasm_api.rs:660-678 / 784-802
+    if (key_len != (size_t)key_bytes)
+        return ret_json(json_error("Key must be " + std::to_string(key_bytes) + " bytes, got " + std::to_string(key_len)), json_out, json_len);
+    if (nonce_len != 12) return ret_json(json_error("Nonce must be 12 bytes, got " + std::to_string(nonce_len)), json_out, json_len);
+    if (pt_len == 0 || pt_len % 16 != 0)
+        return ret_json(json_error("Plaintext must be non-empty multiple of 16 bytes, got " + std::to_string(pt_len)), json_out, json_len);
+    if (ct_len != pt_len)
+        return ret_json(json_error("Ciphertext must be same length as plaintext, got " + std::to_string(ct_len) + " vs " +
+                                   std::to_string(pt_len)), json_out, json_len);
+    size_t num_blocks = pt_len / 16;
+    if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
+        return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
+                                   " blocks would exceed u32::MAX"), json_out, json_len);
+    std::string derr;
+    if (!ctx) ctx = default_ctx(derr);
+    if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
+    std::vector<uint8_t> proof;
+    std::string e;
+    try {
+        CB_CUDA(cudaSetDevice(ctx->device));
+        e = prove_aes_ctr(ctx, key_bytes, key, nonce, counter, pt, ct, pt_len, proof);
+    } catch (const std::exception& ex) {
+        ctx->err = ex.what();
+        ret_json(json_error(std::string("backend failure: ") + ex.what()), json_out, json_len);
+        return 1;
+    }
+    if (!e.empty()) return ret_json(json_error(e), json_out, json_len);
+    std::string b64 = host::base64_encode(proof.data(), proof.size());
+    std::string js = std::string("{\"algorithm\":\"") + algorithm + "\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
+                     "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 136)) +
+                     ",\"success\":true}";
+    return ret_json(js, json_out, json_len);
+}
+
+int s2c_generate_aes128_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                  uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
+                                  size_t* json_len) {
+    return aes_generate(ctx, 16, "aes128-ctr", key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+int s2c_generate_aes256_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                  uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
+                                  size_t* json_len) {
+    return aes_generate(ctx, 32, "aes256-ctr", key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+
+int s2c_prove_aes_ctr_raw(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                          const uint8_t* ct, size_t len, uint8_t** proof_out, size_t* proof_len) {
+    std::string derr;
+    if (!ctx) ctx = default_ctx(derr);
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (key_len != 16 && key_len != 32) throw CbError("key_len must be 16 or 32");
+    if (len == 0 || len % 16) throw CbError("Plaintext must be non-empty multiple of 16 bytes, got " + std::to_string(len));
+    std::vector<uint8_t> proof;
+    std::string e = prove_aes_ctr(ctx, key_len, key, nonce, counter, pt, ct, len, proof);
+    if (!e.empty()) throw CbError(e);
+    uint8_t* p = (uint8_t*)malloc(proof.size());
+    memcpy(p, proof.data(), proof.size());
+    *proof_out = p;
+    *proof_len = proof.size();
+    CB_CATCH(ctx)
+}
+
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len) {
     // wasm_api.rs:953-990: native block function (chacha/block.rs:95), hex of the 64 keystream bytes

@@ -46,6 +46,10 @@ struct QuotBatch {
     const uint32_t* coefs;         // device [n_cols][4] = alpha_j * c_j
     const uint32_t* col_idx;       // device [n_cols] column indices (nullptr = identity)
     int n_cols;
+    // optional per-entry column pointers (device array of n_cols pointers) with the log size of each column, for trees that
+    // mix column sizes: entry j reads col_ptr[j][lift(row)] where lift maps the row of the 2^m domain to the smaller column
+    const uint32_t* const* col_ptr;
+    const uint8_t* col_log;
 };
 
 // ---- streaming prover job lists (passed to kernels by value) ----
@@ -75,6 +79,40 @@ struct ConstraintJobs {
     ConstraintJob j[MAX_CONSTRAINT_JOBS];
     int n;
 };
+
+// ---- AES-CTR AIR kernels (kernels_aes.cu); plain-data mirrors of the kernel argument structs
+struct AesConsArgs {
+    const uint32_t* lde;
+    size_t stride;
+    const uint32_t* inter;
+    size_t i_stride;
+    const uint32_t *apr_lo, *apr_hi;
+    const uint32_t* apr;
+    const uint32_t* den_inv;
+    const int *lk_in, *lk_out;
+    m31::QM31 z, alpha, shift;
+    int eval_log, trace_log, n_rounds, n_lookups;
+    uint32_t* out;
+    size_t out_stride;
+};
+struct AesTableArgs {
+    const uint32_t *pre_in, *pre_out, *mult;
+    const uint32_t* inter;
+    size_t i_stride;
+    m31::QM31 z, alpha, shift, apow;
+    const uint32_t* den_inv;
+    int eval_log, trace_log;
+    uint32_t* out;
+};
+cudaError_t aes_upload_sbox(const uint8_t sbox[256]);
+cudaError_t launch_aes_witness(cudaStream_t st, const uint8_t* rk, int n_rounds, const uint8_t nonce[12], uint32_t counter,
+                               uint32_t num_blocks, uint32_t n_active_rows, const uint8_t* pt, const uint8_t* ct, int log_size,
+                               uint32_t* T, size_t stride, unsigned int* mults, int* invalid);
+cudaError_t launch_aes_interaction(cudaStream_t st, const uint32_t* T, size_t stride, int log_size, const int* lk_in, const int* lk_out,
+                                   int n_lookups, m31::QM31 z, m31::QM31 alpha, uint32_t* I, size_t i_stride);
+cudaError_t launch_aes_constraints(cudaStream_t st, const AesConsArgs& a);
+cudaError_t launch_aes_table_constraint(cudaStream_t st, const AesTableArgs& a);
+cudaError_t launch_lift_accumulate(cudaStream_t st, uint32_t* big, size_t big_stride, int big_log, const uint32_t* small, int small_log);
 
 // optional per-kernel profiling callback (begin=1 before a launch, begin=0 after it)
 struct StageHook {

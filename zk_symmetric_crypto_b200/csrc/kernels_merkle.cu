@@ -75,6 +75,21 @@ __global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lift
                 if (FMA) blake2s::compress_fma(h, m, t, last, one); else blake2s::compress(h, m, t, last);
             }
         }
+        // a group that starts in the middle of a 64-byte block (mixed-size trees: a few small columns hashed first) is
+        // brought to the block boundary column by column, then takes the fast path
+        for (; c < g.ncols && k != 0; c++) {
+            uint32_t v = __ldg(p + (size_t)c * g.stride);
+#pragma unroll
+            for (int w = 0; w < 16; w++)
+                if (w == k) m[w] = v;
+            k++;
+            if (k == 16) {
+                t += 64;
+                bool last = is_final && (done_cols + c + 1 == total_cols);
+                blake2s::compress(h, m, t, last);
+                k = 0;
+            }
+        }
         if (k == 0) {
             // fast path: whole 64-byte blocks straight from 16 coalesced column loads
             for (; c + 16 <= g.ncols; c += 16) {

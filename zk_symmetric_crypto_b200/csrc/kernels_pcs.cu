@@ -79,8 +79,15 @@ __global__ void __launch_bounds__(256) quotients_kernel(const uint32_t* __restri
         int pend = 0;
         const uint4* cf = (const uint4*)B.coefs;
         for (int j = 0; j < B.n_cols; j++) {
-            int ci = B.col_idx ? B.col_idx[j] : j;
-            uint32_t v = ci < n_main ? __ldg(cols + (size_t)ci * stride + row) : __ldg(extra + (size_t)(ci - n_main) * extra_stride + row);
+            uint32_t v;
+            if (B.col_ptr) {
+                const int sh = m - (int)B.col_log[j];
+                const uint32_t r = sh ? (((row >> (sh + 1)) << 1) | (row & 1)) : row;
+                v = __ldg(B.col_ptr[j] + r);
+            } else {
+                int ci = B.col_idx ? B.col_idx[j] : j;
+                v = ci < n_main ? __ldg(cols + (size_t)ci * stride + row) : __ldg(extra + (size_t)(ci - n_main) * extra_stride + row);
+            }
             uint4 c4 = __ldg(cf + j);
             a[0] += (uint64_t)v * c4.x; a[1] += (uint64_t)v * c4.y; a[2] += (uint64_t)v * c4.z; a[3] += (uint64_t)v * c4.w;
             if (++pend == 4) { fold4(a); pend = 0; }

@@ -43,32 +43,6 @@ __global__ void __launch_bounds__(256) combine_add_kernel(CombineJobs jobs, size
     }
 }
 
-// Accumulator of sum_k alpha_k * C_k with alpha_k in QM31 (4 coordinates) and C_k in M31.  Every coordinate of alpha_k is
-// pre-split into 16-bit halves (two tables), so each product C * half < 2^48 and 2^16 products fit a 64-bit accumulator
-// without intermediate reduction: a multiply-accumulate is 8 IMAD.WIDE on the FMA pipe and nothing on the ALU pipe, which is
-// the pipe every other instruction of this kernel needs.  C may be any 32-bit representative (not necessarily < p).
-struct AccSplit {
-    uint64_t lo[4], hi[4];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int c = 0; c < 4; c++) lo[c] = hi[c] = 0;
-    }
-    __device__ __forceinline__ void mac(const uint4* __restrict__ tlo, const uint4* __restrict__ thi, int k, uint32_t C) {
-        const uint4 l = __ldg(tlo + k), h = __ldg(thi + k);
-        lo[0] += (uint64_t)C * l.x; lo[1] += (uint64_t)C * l.y; lo[2] += (uint64_t)C * l.z; lo[3] += (uint64_t)C * l.w;
-        hi[0] += (uint64_t)C * h.x; hi[1] += (uint64_t)C * h.y; hi[2] += (uint64_t)C * h.z; hi[3] += (uint64_t)C * h.w;
-    }
-    __device__ __forceinline__ uint32_t result(int c) const { return addm(mulm(red64(hi[c]), 1u << 16), red64(lo[c])); }
-};
-
-// lazily reduced helpers: inputs canonical, outputs any representative < 2^32 unless noted
-// b - b^2 + p  in (0, 2p):  b2 = 2b (unreduced)
-__device__ __forceinline__ uint32_t bool_c(uint32_t b, uint32_t b2) {
-    const uint64_t v = (uint64_t)b * b2;
-    const uint32_t sq = redp((uint32_t)(v >> 32) + (((uint32_t)v) >> 1));
-    return b + P - sq;
-}
-
 // acc[row] += sum over jobs of sum_i apr[k] * C(row)   (apr[k] = alpha^(K-1-k), 4 coordinates, split in 16-bit halves)
 //   CJ_BOOL: C = b(1-b), b = t0[i], k = kb0 + i*step          (constraints_stream.rs:85-101)
 //   CJ_ADDX: one 32-bit adder (:104-131) and, optionally, the xor-rotate that consumes its sum (:134-152): the sum word

@@ -49,3 +49,7 @@ size_t stark_proof_size_estimate(const uint8_t* p, size_t len, size_t stark_off)
 
 std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof, ProveOptions opt = ProveOptions());
+
+// AES-128/256-CTR (prove_aes.cu): key_len 16 or 32; len = multiple of 16 bytes.  Returns "" or the reference's error string.
+std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter,
+                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof);

@@ -8,9 +8,11 @@ from . import backend
 
 
 def make_stwo_zk_operator(algorithm="chacha20", device=0):
-    if algorithm != "chacha20":
+    if algorithm not in ("chacha20", "aes-128-ctr", "aes-256-ctr"):
         raise backend.BackendError("algorithm %r not available in this build" % algorithm)
     be = backend.Backend(device)
+    prove = {"chacha20": be.generate_chacha20_proof, "aes-128-ctr": be.generate_aes128_ctr_proof,
+             "aes-256-ctr": be.generate_aes256_ctr_proof}[algorithm]
 
     class _Op:
         def generate_witness(self, inp):
@@ -24,8 +26,8 @@ def make_stwo_zk_operator(algorithm="chacha20", device=0):
         def groth16_prove(self, witness):
             """operator.ts:97-133 (name kept from the ZKOperator interface)."""
             w = json.loads(bytes(witness).decode())
-            res = be.generate_chacha20_proof(base64.b64decode(w["key"]), base64.b64decode(w["nonce"]), w["counter"],
-                                             base64.b64decode(w["plaintext"]), base64.b64decode(w["ciphertext"]))
+            res = prove(base64.b64decode(w["key"]), base64.b64decode(w["nonce"]), w["counter"],
+                        base64.b64decode(w["plaintext"]), base64.b64decode(w["ciphertext"]))
             if "error" in res:
                 raise backend.BackendError(res["error"])
             return {"proof": res["proof"]}
