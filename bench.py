@@ -129,6 +129,162 @@ def cpu_reference_run(log_sample, steps, warmup):
     return sum(times) / len(times)
 
 
+def synth_aes_inputs(key_len, log_n, rank):
+    """Deterministic AES-CTR workload (numpy AES, test data only): key/nonce from a seeded rng, counter 1."""
+    import numpy as np
+    sbox = np.zeros(256, dtype=np.uint8)   # FIPS-197 S-box from the field inverse + affine map
+    p = q = 1
+    while True:
+        p = (p ^ ((p << 1) & 0xFF) ^ (0x1B if p & 0x80 else 0)) & 0xFF
+        q ^= q << 1; q ^= q << 2; q ^= q << 4; q &= 0xFF
+        if q & 0x80:
+            q ^= 0x09
+        x = q ^ ((q << 1 | q >> 7) & 0xFF) ^ ((q << 2 | q >> 6) & 0xFF) ^ ((q << 3 | q >> 5) & 0xFF) ^ ((q << 4 | q >> 4) & 0xFF)
+        sbox[p] = (x ^ 0x63) & 0xFF
+        if p == 1:
+            break
+    sbox[0] = 0x63
+
+    def expand_key(key):
+        nk = len(key) // 4; nrr = nk + 6
+        w = [list(key[4 * i:4 * i + 4]) for i in range(nk)]
+        rc = 1
+        for i in range(nk, 4 * (nrr + 1)):
+            t = list(w[i - 1])
+            if i % nk == 0:
+                t = [int(sbox[b]) for b in t[1:] + t[:1]]
+                t[0] ^= rc
+                rc = ((rc << 1) & 0xFF) ^ (0x1B if rc & 0x80 else 0)
+            elif nk > 6 and i % nk == 4:
+                t = [int(sbox[b]) for b in t]
+            w.append([a ^ b for a, b in zip(w[i - nk], t)])
+        return [sum(w[4 * r:4 * r + 4], []) for r in range(nrr + 1)]
+    SR = [0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 1, 6, 11]
+    nb = 1 << log_n
+    rng = np.random.default_rng(2000 + rank)
+    key = rng.bytes(key_len); nonce = rng.bytes(12); counter = 1
+    pt = np.frombuffer(rng.bytes(16 * nb), dtype=np.uint8).reshape(nb, 16)
+    rk = np.array(expand_key(key), dtype=np.uint8)
+    nr = rk.shape[0] - 1
+    blk = np.zeros((nb, 16), dtype=np.uint8)
+    blk[:, :12] = np.frombuffer(nonce, dtype=np.uint8)
+    ctrs = (counter + np.arange(nb, dtype=np.uint64)) & np.uint64(0xFFFFFFFF)
+    for i in range(4):
+        blk[:, 12 + i] = (ctrs >> np.uint64(8 * (3 - i))) & np.uint64(0xFF)
+
+    def xt(a):
+        return ((a << 1) ^ ((a >> 7) * 0x1B)).astype(np.uint8)
+    s = blk ^ rk[0]
+    for r in range(1, nr + 1):
+        s = sbox[s][:, SR]
+        if r < nr:
+            o = np.empty_like(s)
+            for c in range(4):
+                a0, a1, a2, a3 = (s[:, 4 * c + j] for j in range(4))
+                o[:, 4 * c] = xt(a0) ^ xt(a1) ^ a1 ^ a2 ^ a3
+                o[:, 4 * c + 1] = a0 ^ xt(a1) ^ xt(a2) ^ a2 ^ a3
+                o[:, 4 * c + 2] = a0 ^ a1 ^ xt(a2) ^ xt(a3) ^ a3
+                o[:, 4 * c + 3] = xt(a0) ^ a0 ^ a1 ^ a2 ^ xt(a3)
+            s = o
+        s = s ^ rk[r]
+    ct = s ^ pt
+    return key, nonce, counter, pt.tobytes(), ct.tobytes()
+
+
+def aes_main(args, rank, local_rank, world):
+    """BASELINE configs[2]: AES-128/256-CTR AIR proofs.  Inputs are 16 bytes per row, so the only meaningful figure is the
+    end-to-end one through the host-buffer C ABI (reported as both value and e2e)."""
+    key_len = 16 if args.workload == "aes128" else 32
+    L = args.log_size if "--log-size" in " ".join(sys.argv) else 16
+    cols, cons = (24480, 34464) if key_len == 16 else (34784, 49024)
+    config = {"workload": "%s_ctr log_n_rows=%d blowup=2 (one proof of %d 16-byte blocks per GPU per step)" % (args.workload, L, 1 << L),
+              "log_n_rows": L, "columns": cols, "constraints": cons, "pcs": "pow_bits=10,n_queries=3,log_blowup=1,last_layer=0",
+              "l2": "inputs larger than L2 (LDE %.1f GB)" % (cols * (2 << L) * 4 / 1e9),
+              "sharding": "independent proofs, one per rank, no data-path collective"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_wasm
+        S = min(L, 9)
+        key, nonce, counter, pt, ct = synth_aes_inputs(key_len, S, 0)
+        fn = ref_wasm.generate_aes128_ctr_proof if key_len == 16 else ref_wasm.generate_aes256_ctr_proof
+        t0 = time.perf_counter()
+        res = fn(key, nonce, counter, pt, ct)
+        sec = time.perf_counter() - t0
+        assert res.get("success") is True, res
+        scaled = 1.0 / (sec * (1 << (L - S)))
+        print(json.dumps({"impl": "reference", "metric": "%s_ctr_proofs_per_sec" % args.workload, "value": scaled, "unit": "proofs/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / scaled,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32(M31)", "data": "synthetic",
+                          "config": config,
+                          "cpu_baseline": {"value": scaled, "unit": "proofs/s", "cores": 1, "kind": "reference",
+                                           "sample": "reference prover on 2^%d blocks: %.3f s/proof, linearly scaled to 2^%d" % (S, sec, L)},
+                          "e2e": {"value": scaled, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    os.environ["NCCL_DEBUG"] = os.environ.get("S2C_NCCL_DEBUG", "WARN")
+    import torch
+    import torch.distributed as dist
+    import zk_symmetric_crypto_b200 as z
+    from zk_symmetric_crypto_b200 import sharding
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = z.Backend(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    be.set_stream(stream.cuda_stream)
+    key, nonce, counter, pt, ct = synth_aes_inputs(key_len, L, rank)
+
+    def step():
+        return be.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
+    for _ in range(max(args.warmup, 3)):
+        proof = step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = be.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        proof = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sharding.max_over_ranks([e0.elapsed_time(e1)], device="cuda")[0]
+    launches = be.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    be.set_profile(True)
+    step()
+    stages = be.stage_times()
+    if rank == 0:
+        value = world * args.steps / (ms / 1000.0)
+        N = 1 << L
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        lde_ms = stages.get("trace_lde", 0.0)
+        alg = (cols + 1) * N * 20
+        print(json.dumps({"metric": "%s_ctr_proofs_per_sec" % args.workload, "value": value, "unit": "proofs/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u32(M31)", "data": "synthetic", "config": config,
+                          "clocks": clocks, "gpu_launches": launches,
+                          "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 2 * len(pt), "d2h_bytes_per_step": len(proof)},
+                          "stage_ms": stages,
+                          "roofline": {"kernel": "trace_lde", "bound": "hbm", "achieved": alg / (lde_ms / 1000.0) / 1e9 if lde_ms else None,
+                                       "peak": hbm_peak, "unit": "GB/s", "frac": alg / (lde_ms / 1000.0) / 1e9 / hbm_peak if lde_ms else None,
+                                       "traffic": None, "algorithmic_bytes_per_proof": alg}}))
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,10 +294,14 @@ def main():
     ap.add_argument("--log-size", type=int, default=int(os.environ.get("S2C_BENCH_LOG", "20")))
     ap.add_argument("--cpu-log-size", type=int, default=10, help="size of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="chacha20", choices=["chacha20", "aes128", "aes256"],
+                    help="chacha20 (BASELINE configs[1], the headline) or an AES-CTR AIR (configs[2])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload != "chacha20":
+        return aes_main(args, rank, local_rank, world)
     L = args.log_size
     workload = "chacha20_stream log_n_rows=%d blowup=2 (one proof of %d blocks per GPU per step)" % (L, 1 << L)
     config = {"workload": workload, "log_n_rows": L, "columns": N_COLS, "constraints": N_CONSTRAINTS,
