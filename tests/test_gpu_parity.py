@@ -330,3 +330,18 @@ def test_reference_verifier_accepts_gpu_aes_proofs(backend):
     assert ref_wasm.verify_aes_ctr_proof(res["proof"], nonce, counter, pt, ct) == {"algorithm": "aes256-ctr", "valid": True}
     bad = bytearray(ct); bad[3] ^= 1
     assert ref_wasm.verify_aes_ctr_proof(res["proof"], nonce, counter, pt, bytes(bad))["valid"] is False
+
+
+def test_pool_of_contexts_gives_identical_proofs(backend):
+    """Throughput mode: several contexts on one GPU driven by host threads; every proof equals the single-context proof."""
+    from zk_symmetric_crypto_b200.pool import ProverPool
+    c = case_inputs(2, 0)
+    a = aes_case_inputs(16, 5, None)
+    want_c = backend.generate_chacha20_proof(*c)
+    want_a = backend.generate_aes128_ctr_proof(*a)
+    pool = ProverPool(0, 4)
+    try:
+        out = pool.prove_many([("chacha20",) + tuple(c), ("aes-128-ctr",) + tuple(a)] * 4)
+    finally:
+        pool.close()
+    assert out[0::2] == [want_c] * 4 and out[1::2] == [want_a] * 4
