@@ -65,7 +65,7 @@ def test_interpolate_evaluate(backend, log_n):
 
 
 @pytest.mark.parametrize("log_n,kind", [(4, 1), (5, 1), (8, 1), (11, 1), (12, 1), (13, 1), (14, 1), (15, 1), (16, 1), (17, 1), (18, 1), (19, 1), (20, 1),
-                                        (22, 1), (6, 2), (12, 2), (15, 2)])
+                                        (22, 1), (6, 2), (12, 2), (15, 2), (5, 0), (12, 0), (14, 0), (17, 0)])
 def test_lde_packed(backend, log_n, kind):
     """Packed-witness fused interpolate+extend (the transform of the streaming prover) against the oracle's circle
     iFFT/FFT, for every kernel schedule: whole-column (<=12), three-pass (>=13), padded strided tiles (>=22)."""
@@ -74,15 +74,20 @@ def test_lde_packed(backend, log_n, kind):
     n, m = 1 << log_n, 2 << log_n
     n_words = 3 if log_n <= 16 else 1
     cpj = 32 if kind == 1 else 4
-    words = rng.integers(0, 1 << 32, size=(n_words, n), dtype=np.uint64).astype(np.uint32)
+    if kind == 0:   # a job = 4 plain M31 columns
+        words = rng.integers(0, sc.P, size=(n_words * 4, n), dtype=np.uint64).astype(np.uint32)
+    else:
+        words = rng.integers(0, 1 << 32, size=(n_words, n), dtype=np.uint64).astype(np.uint32)
     d_w = be.upload(words)
     d_t = be.malloc(n_words * cpj * m * 4)
     be._ck(be.L.cb_lde_packed(be.ctx, kind, d_w, n_words, log_n, d_t))
     tiles = be.download(d_t, (n_words, cpj, m))
     check_cols = range(cpj) if log_n <= 14 else ([0, 13, 31] if kind == 1 else [0, 3])
     for w in range(n_words):
-        wv = words[w].astype(np.uint64)
-        if kind == 1:
+        wv = words[w].astype(np.uint64) if kind else None
+        if kind == 0:
+            cols = np.stack([words[4 * w + c].astype(np.uint64) for c in check_cols])
+        elif kind == 1:
             cols = np.stack([(wv >> np.uint64(c)) & np.uint64(1) for c in check_cols])
         else:
             cols = np.stack([(wv >> np.uint64(8 * c)) & np.uint64(0xFF) for c in check_cols])

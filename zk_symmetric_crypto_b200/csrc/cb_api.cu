@@ -160,7 +160,8 @@ int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* srcp, size_t src_st
 
 int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out) {
     CB_TRY(ctx)
-    if (src_kind != SRC_BITS && src_kind != SRC_BYTES) throw CbError("cb_lde_packed: src_kind must be 1 (bits) or 2 (bytes)");
+    if (src_kind != SRC_BITS && src_kind != SRC_BYTES && src_kind != SRC_M31)
+        throw CbError("cb_lde_packed: src_kind must be 0 (4 M31 columns per job), 1 (bits) or 2 (bytes)");
     if (log_size < 1 || log_size > 24) throw CbError("cb_lde_packed: log_size out of range");
     ctx->ensure_twiddles(log_size + 1);
     const int cpj = src_kind == SRC_BITS ? 32 : 4;
@@ -169,7 +170,7 @@ int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_wo
     std::vector<const uint32_t*> src(n_words);
     std::vector<uint32_t*> out(n_words);
     for (int w = 0; w < n_words; w++) {
-        src[w] = src_words + ((size_t)w << log_size);
+        src[w] = src_words + (((size_t)w * (src_kind == SRC_M31 ? 4 : 1)) << log_size);
         out[w] = tiles_out + (((size_t)w * cpj) << (log_size + 1));
     }
     int nl = 0;

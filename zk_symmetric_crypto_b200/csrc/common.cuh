@@ -136,5 +136,7 @@ cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trac
 cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
                               uint32_t* out);
 cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g);
+cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t stride, int ncols, size_t N, const uint32_t* coefs,
+                               uint32_t* g, int accumulate);
 cudaError_t launch_basis4(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const uint32_t init[4],
                           const uint32_t (*maps)[4]);

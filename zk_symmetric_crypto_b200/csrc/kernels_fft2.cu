@@ -153,8 +153,12 @@ __global__ void __launch_bounds__(256) small_kernel(Jobs jobs, int log_n, int nc
     const uint32_t* __restrict__ src = jobs.src[job];
     const uint32_t scale = 1u << (31 - log_n), scale2 = scale << 1;
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
-        uint32_t w = __ldg(src + r);
-        for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = unpack<KIND>(w, c0 + c, scale, scale2);
+        if (KIND == SRC_M31) {  // job = cols_per_job plain M31 columns, n words apart
+            for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = mulw(__ldg(src + (size_t)(c0 + c) * n + r), scale2);
+        } else {
+            uint32_t w = __ldg(src + r);
+            for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = unpack<KIND>(w, c0 + c, scale, scale2);
+        }
     }
     __syncthreads();
     apply_layers<true, true>(s, nc, colstride, log_n, 0, 0, log_n, tw.IX, tw.IY, log_n, 0, 0);
@@ -183,8 +187,12 @@ __global__ void __launch_bounds__(256) ifft_low_kernel(Jobs jobs, int log_n, int
     const uint32_t* __restrict__ src = jobs.src[job] + (size_t)chunk * T;
     const uint32_t scale = 1u << (31 - log_n), scale2 = scale << 1;
     for (int r = threadIdx.x; r < T; r += blockDim.x) {
-        uint32_t w = __ldg(src + r);
-        for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = unpack<KIND>(w, c0 + c, scale, scale2);
+        if (KIND == SRC_M31) {
+            for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = mulw(__ldg(src + ((size_t)(c0 + c) << log_n) + r), scale2);
+        } else {
+            uint32_t w = __ldg(src + r);
+            for (int c = 0; c < nc; c++) s[c * colstride + padi(r)] = unpack<KIND>(w, c0 + c, scale, scale2);
+        }
     }
     __syncthreads();
     apply_layers<true, true>(s, nc, colstride, k1, 0, 0, k1, tw.IX, tw.IY, log_n, 0, chunk);
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
     const int p = threadIdx.x;
     const uint32_t scale = 1u << (31 - log_n), scale2 = scale << 1;
     uint32_t w[16], twr[16], v[16];
-    {
+    if (KIND != SRC_M31) {
         const uint4* __restrict__ src = (const uint4*)(jobs.src[job] + (size_t)chunk * T2 + 16 * p);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -341,7 +349,17 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
 #pragma unroll
     for (int c = 0; c < NC; c++) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = unpack<KIND>(w[k], c0 + c, scale, scale2);
+        if (KIND == SRC_M31) {  // plain M31 columns: 16 consecutive values of column c0+c
+            const uint4* __restrict__ src = (const uint4*)(jobs.src[job] + ((size_t)(c0 + c) << log_n) + (size_t)chunk * T2 + 16 * p);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 x = __ldg(src + i);
+                v[4 * i] = mulw(x.x, scale2); v[4 * i + 1] = mulw(x.y, scale2); v[4 * i + 2] = mulw(x.z, scale2); v[4 * i + 3] = mulw(x.w, scale2);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = unpack<KIND>(w[k], c0 + c, scale, scale2);
+        }
         inv_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
         for (int i = 0; i < 4; i++) *(uint4*)(s + c * COLW + va[i]) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -544,6 +562,9 @@ void fft2_init_attrs() {
     using namespace fft2;
     cudaFuncSetAttribute(small_kernel<SRC_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(small_kernel<SRC_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    cudaFuncSetAttribute(small_kernel<SRC_M31>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    cudaFuncSetAttribute(ifft_low_kernel<SRC_M31>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    cudaFuncSetAttribute(ifft_low12_kernel<SRC_M31, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
     cudaFuncSetAttribute(ifft_low_kernel<SRC_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(ifft_low_kernel<SRC_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
@@ -562,7 +583,8 @@ size_t fft_packed_scratch_words(int kind, int njobs, int log_n) {
     return ((size_t)njobs * (kind == SRC_BITS ? 32 : 4)) << log_n;
 }
 
-// kind: SRC_BITS (32 columns per job) or SRC_BYTES (4 columns per job).  src[j]: packed word row of job j (2^log_n words);
+// kind: SRC_BITS (32 columns per job), SRC_BYTES (4 columns per job) or SRC_M31 (4 plain M31 columns per job, 2^log_n words
+// apart, src[j] -> the first of them).  src[j]: packed word row of job j (2^log_n words);
 // out[j]: tile [cols][2^(log_n+1)].  Returns the number of kernels launched through *launches.
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
                               const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches) {
@@ -586,7 +608,8 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
             int threads = (nc * big / 16) < 256 ? ((nc * big / 16) < 32 ? 32 : nc * big / 16) : 256;
             HOOK("fft_small", 1);
             if (kind == SRC_BITS) small_kernel<SRC_BITS><<<jobs.n * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
-            else small_kernel<SRC_BYTES><<<jobs.n * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
+            else if (kind == SRC_BYTES) small_kernel<SRC_BYTES><<<jobs.n * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
+            else small_kernel<SRC_M31><<<jobs.n * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
             HOOK("fft_small", 0);
             nl += 1;
             continue;
@@ -598,7 +621,8 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
             dim3 gA((1u << log_n) / T2, jobs.n * gpj2);
             HOOK("ifft_low", 1);
             if (kind == SRC_BITS) ifft_low12_kernel<SRC_BITS, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
-            else ifft_low12_kernel<SRC_BYTES, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
+            else if (kind == SRC_BYTES) ifft_low12_kernel<SRC_BYTES, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
+            else ifft_low12_kernel<SRC_M31, NC><<<gA, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, cpj, scr2, tw);
             HOOK("ifft_low", 0);
             HOOK("fft_mid", 1);
             switch (log_n - K1) {
@@ -635,7 +659,8 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         dim3 gA((1u << log_n) / T, jobs.n * gpj);
         HOOK("ifft_low", 1);
         if (kind == SRC_BITS) ifft_low_kernel<SRC_BITS><<<gA, 256, smem_ac, st>>>(jobs, log_n, k1, nc, gpj, cpj, scr, tw);
-        else ifft_low_kernel<SRC_BYTES><<<gA, 256, smem_ac, st>>>(jobs, log_n, k1, nc, gpj, cpj, scr, tw);
+        else if (kind == SRC_BYTES) ifft_low_kernel<SRC_BYTES><<<gA, 256, smem_ac, st>>>(jobs, log_n, k1, nc, gpj, cpj, scr, tw);
+        else ifft_low_kernel<SRC_M31><<<gA, 256, smem_ac, st>>>(jobs, log_n, k1, nc, gpj, cpj, scr, tw);
         HOOK("ifft_low", 0);
         dim3 gB(T / Q, jobs.n * cpj);
         const size_t tile = (size_t)1 << (jb + qbits);

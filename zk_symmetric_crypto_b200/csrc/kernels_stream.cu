@@ -236,6 +236,41 @@ __global__ void __launch_bounds__(1024) bitrow_comb_kernel(const uint32_t* __res
     }
 }
 
+// g[c][r] (+)= sum_j vals[j][r] * coefs[j][c] for plain M31 columns (row-wise QM31 combination of trace-domain values: the FRI
+// quotient numerator of a group of columns is the extension of this combination).  block = 64 rows x PARTS column slices.
+__global__ void __launch_bounds__(1024) rowcomb_m31_kernel(const uint32_t* __restrict__ vals, size_t stride, int ncols, size_t N,
+                                                           const uint4* __restrict__ coefs, uint32_t* __restrict__ g, int accumulate) {
+    const int rl = threadIdx.x & 63, part = threadIdx.x >> 6, parts = blockDim.x >> 6;
+    const size_t r = (size_t)blockIdx.x * 64 + rl;
+    uint64_t acc[4] = {0, 0, 0, 0};
+    if (r < N) {
+        int pend = 0;
+        for (int j = part; j < ncols; j += parts) {
+            const uint32_t v = __ldg(vals + (size_t)j * stride + r);
+            const uint4 c4 = __ldg(coefs + j);
+            acc[0] += (uint64_t)v * c4.x; acc[1] += (uint64_t)v * c4.y; acc[2] += (uint64_t)v * c4.z; acc[3] += (uint64_t)v * c4.w;
+            if (++pend == 4) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[c] = (acc[c] & P) + (acc[c] >> 31);
+                pend = 0;
+            }
+        }
+    }
+    __shared__ uint32_t red[16][4][64];
+#pragma unroll
+    for (int c = 0; c < 4; c++) red[part][c][rl] = red64(acc[c]);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const int c = threadIdx.x >> 6;
+        uint32_t v = 0;
+        for (int p = 0; p < parts; p++) v = addm(v, red[p][c][rl]);
+        if (r < N) {
+            if (accumulate) v = addm(v, g[(size_t)c * N + r]);
+            g[(size_t)c * N + r] = v;
+        }
+    }
+}
+
 // component-wise basis doubling for up to 4 base-field points at once: b[c][half+k] = b[c][k] * f[c]
 __global__ void basis4_step_kernel(uint32_t* b, size_t stride, uint32_t half, uint4 f) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,6 +318,14 @@ cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int 
 cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g) {
     int parts = N >= 8192 ? 4 : 16;
     strm::bitrow_comb_kernel<<<(unsigned)((N + 63) / 64), 64 * parts, 0, st>>>(W, N, n_words, (const uint4*)coefs, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t stride, int ncols, size_t N, const uint32_t* coefs,
+                               uint32_t* g, int accumulate) {
+    int parts = N >= 65536 ? 4 : 16;
+    strm::rowcomb_m31_kernel<<<(unsigned)((N + 63) / 64), 64 * parts, 0, st>>>(vals, stride, ncols, N, (const uint4*)coefs, g,
+                                                                             accumulate);
     return cudaGetLastError();
 }
 

@@ -243,6 +243,26 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         ctx->launches += (lg + 1 <= 13) ? 1 : 3;
     };
 
+    // large groups: values stay in place (their out-of-domain samples are taken from the values, not from coefficients) and the
+    // LDE comes from the register-radix kernels of kernels_fft2.cu, 4 columns per job
+    const StageHook hk = ctx->hook();
+    auto transform_fast = [&](const uint32_t* vals, int ncols, uint32_t* lde) {
+        if (m <= 13) {  // whole columns fit shared memory: one launch of the generic kernel for all columns
+            ColSrc src{SRC_M31, vals, N, 0};
+            CB_CUDA(launch_fft(st, src, ncols, n, 1, 1 | 4, nullptr, 0, lde, M, ctx->tw, nullptr, 0));
+            ctx->launches++;
+            return;
+        }
+        const int njobs = ncols / 4;
+        DBuf<uint32_t> scratch(ctx, fft_packed_scratch_words(SRC_M31, njobs < MAX_FFT_JOBS ? njobs : MAX_FFT_JOBS, n));
+        std::vector<const uint32_t*> src(njobs);
+        std::vector<uint32_t*> out(njobs);
+        for (int j = 0; j < njobs; j++) { src[j] = vals + (size_t)4 * j * N; out[j] = lde + (size_t)4 * j * M; }
+        int nl = 0;
+        CB_CUDA(launch_fft_packed(st, SRC_M31, src.data(), out.data(), njobs, n, ctx->tw, scratch.p, ctx->profile ? &hk : nullptr, &nl));
+        ctx->launches += nl;
+    };
+
     // ---- tree 0: preprocessed S-box table (aes/sbox_table.rs:35-48)
     DBuf<uint32_t> pre(ctx, 2 * 256), pre_lde(ctx, 2 * 512);
     {
@@ -272,17 +292,12 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     ch.mix_u64(counter);
     for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[24 + 4 * i]));
 
-    // ---- tree 1: main trace + S-box multiplicities.  The (input, output) columns of the lookups are kept aside before the
-    //      trace is transformed in place.
-    DBuf<uint32_t> LK(ctx, (size_t)2 * NL * N), lde1(ctx, (size_t)C * M), mult(ctx, 256), mult_lde(ctx, 512);
-    for (int k = 0; k < NL; k++) {
-        CB_CUDA(cudaMemcpyAsync(LK.p + (size_t)(2 * k) * N, T.p + (size_t)lay.lk_in[k] * N, N * 4, cudaMemcpyDeviceToDevice, st));
-        CB_CUDA(cudaMemcpyAsync(LK.p + (size_t)(2 * k + 1) * N, T.p + (size_t)lay.lk_out[k] * N, N * 4, cudaMemcpyDeviceToDevice, st));
-    }
+    // ---- tree 1: main trace + S-box multiplicities
+    DBuf<uint32_t> lde1(ctx, (size_t)C * M), mult(ctx, 256), mult_lde(ctx, 512);
     CB_CUDA(cudaMemcpyAsync(mult.p, mults.data(), 256 * 4, cudaMemcpyHostToDevice, st));
     ctx->sync();
     ctx->stage_begin("trace_lde");
-    transform(T.p, C, n, lde1.p);
+    transform_fast(T.p, C, lde1.p);
     transform(mult.p, 1, 8, mult_lde.p);
     ctx->stage_end();
     trees[1].groups = {{T.p, lde1.p, C, n}, {mult.p, mult_lde.p, 1, 8}};
@@ -296,12 +311,10 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     DBuf<uint32_t> I(ctx, (size_t)NI * N), inter_lde(ctx, (size_t)NI * M), tinter(ctx, 4 * 256), tinter_lde(ctx, 4 * 512);
     QM31 csum, tsum;
     {
-        std::vector<int> idx_in(NL), idx_out(NL);
-        for (int k = 0; k < NL; k++) { idx_in[k] = 2 * k; idx_out[k] = 2 * k + 1; }
         DBuf<int> d_in(ctx, NL), d_out(ctx, NL);
-        CB_CUDA(cudaMemcpyAsync(d_in.p, idx_in.data(), NL * 4, cudaMemcpyHostToDevice, st));
-        CB_CUDA(cudaMemcpyAsync(d_out.p, idx_out.data(), NL * 4, cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_aes_interaction(st, LK.p, N, n, d_in.p, d_out.p, NL, z, alpha, I.p, N));
+        CB_CUDA(cudaMemcpyAsync(d_in.p, lay.lk_in.data(), NL * 4, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(d_out.p, lay.lk_out.data(), NL * 4, cudaMemcpyHostToDevice, st));
+        CB_CUDA(launch_aes_interaction(st, T.p, N, n, d_in.p, d_out.p, NL, z, alpha, I.p, N));
         ctx->launches++;
         std::vector<uint32_t> last(4 * N);
         CB_CUDA(cudaMemcpyAsync(last.data(), I.p + (size_t)(NI - 4) * N, 4 * N * 4, cudaMemcpyDeviceToHost, st));
@@ -321,14 +334,13 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         CB_CUDA(cudaMemcpyAsync(tinter.p, tcol.data(), 4 * 256 * 4, cudaMemcpyHostToDevice, st));
         ctx->sync();
     }
-    LK.release();
     ctx->stage_end();
     {
         QM31 sums[2] = {csum, tsum};
         ch.mix_felts(sums, 2);
     }
     ctx->stage_begin("interaction_lde");
-    transform(I.p, NI, n, inter_lde.p);
+    transform_fast(I.p, NI, inter_lde.p);
     transform(tinter.p, 4, 8, tinter_lde.p);
     ctx->stage_end();
     trees[2].groups = {{I.p, inter_lde.p, NI, n}, {tinter.p, tinter_lde.p, 4, 8}};
@@ -423,16 +435,36 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         CB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)ncols * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
     };
+    // columns kept as trace-domain VALUES: f(p) = 2^-lg <values, w(p)>, w(p) = forward butterflies with inverse twiddles applied
+    // to basis(p) (the transpose of the inverse transform; kernels_stream.cu fact 2)
+    const FftTables tw_t{ctx->tw.IX, ctx->tw.IY, ctx->tw.X, ctx->tw.Y, ctx->tw.max_log};
+    auto eval_vals = [&](const uint32_t* vals, size_t stride, int ncols, int lg, const PtQ& pt, QM31* out) {
+        const size_t nn = (size_t)1 << lg;
+        std::vector<QM31> maps(lg);
+        maps[0] = pt.y;
+        QM31 x = pt.x;
+        for (int j = 1; j < lg; j++) { maps[j] = x; x = qsub(qmul_m(qmul(x, x), 2), qone()); }
+        DBuf<uint32_t> basis(ctx, 4 * nn), wt(ctx, 4 * nn), d_out(ctx, (size_t)ncols * 4);
+        CB_CUDA(launch_basis(st, basis.p, nn, lg, maps.data()));
+        ColSrc bs{SRC_M31, basis.p, nn, 0};
+        CB_CUDA(launch_fft(st, bs, 4, lg, 0, 4, nullptr, 0, wt.p, nn, tw_t, nullptr, 0));
+        CB_CUDA(launch_oods_dot(st, vals, stride, ncols, lg, wt.p, nn, d_out.p));
+        ctx->launches += lg + 3;
+        CB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)ncols * 16, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
+        const uint32_t inv_n = 1u << (31 - lg);
+        for (int j = 0; j < ncols; j++) out[j] = qmul_m(out[j], inv_n);
+    };
     // samples[tree][col] = list of (point, value) in mask order
     struct Sample { PtQ pt; QM31 val; };
     std::vector<std::vector<std::vector<Sample>>> samples(4);
     {
         std::vector<QM31> v0(2), v1(C), vm(1), vi(NI), vip(4), vt(4), vtp(4), vc(8);
         eval_cols(pre.p, 256, 2, 8, Z8, v0.data());
-        eval_cols(T.p, N, C, n, Z, v1.data());
+        eval_vals(T.p, N, C, n, Z, v1.data());
         eval_cols(mult.p, 256, 1, 8, Z8, vm.data());
-        eval_cols(I.p, N, NI, n, Z, vi.data());
-        eval_cols(I.p + (size_t)(NI - 4) * N, N, 4, n, Zp, vip.data());
+        eval_vals(I.p, N, NI, n, Z, vi.data());
+        eval_vals(I.p + (size_t)(NI - 4) * N, N, 4, n, Zp, vip.data());
         eval_cols(tinter.p, 256, 4, 8, Z8, vt.data());
         eval_cols(tinter.p, 256, 4, 8, Z8p, vtp.data());
         for (int half = 0; half < 2; half++) eval_cols(comp_coef.p + half * N, M, 4, n, Z, vc.data() + 4 * half);
@@ -493,6 +525,14 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
                 }
                 ci++;
             }
+        // Columns of the two big groups (main trace, CTR interaction trace) enter the batch of point z only through
+        // G(p) = sum_j coef_j f_j(p), which is the extension of the row-wise combination of their trace-domain values
+        // (extension is linear): one pass over the values + 4 column transforms instead of reading their LDE.
+        const int big0 = 2, big1 = 2 + C, big2 = 2 + C + 1, big3 = big2 + NI;   // [big0,big1) = main trace, [big2,big3) = CTR interaction
+        auto is_big = [&](int c) { return (c >= big0 && c < big1) || (c >= big2 && c < big3); };
+        const auto zkey = pt_key(Z);
+        std::vector<uint32_t> gcoef((size_t)(C + NI) * 4, 0);
+        DBuf<uint32_t> g(ctx, 4 * N), g_lde(ctx, 4 * M), d_gcoef(ctx, gcoef.size());
         std::vector<QuotBatch> qbs;
         std::vector<DBuf<uint32_t>> keep32;
         std::vector<DBuf<const uint32_t*>> keep_ptr;
@@ -500,20 +540,32 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         for (auto& kv : batches) {
             const PtQ& pt = kv.second.first;
             const std::vector<Entry>& es = kv.second.second;
-            std::vector<uint32_t> coefs(es.size() * 4);
-            std::vector<const uint32_t*> ptrs(es.size());
-            std::vector<uint8_t> logs(es.size());
+            const bool is_z = kv.first == zkey;
+            std::vector<uint32_t> coefs;
+            std::vector<const uint32_t*> ptrs;
+            std::vector<uint8_t> logs;
             QM31 lin_a = qzero(), lin_b = qzero();
             const QM31 c = qsub(qconj(pt.y), pt.y);
+            if (is_z)
+                for (int k = 0; k < 4; k++) {  // the 4 coordinate columns of G with unit coefficients
+                    for (int q = 0; q < 4; q++) coefs.push_back(q == k ? 1u : 0u);
+                    ptrs.push_back(g_lde.p + (size_t)k * M);
+                    logs.push_back((uint8_t)m);
+                }
             for (size_t j = 0; j < es.size(); j++) {
                 const QM31 a = qsub(qconj(es[j].val), es[j].val);
                 const QM31 b = qsub(qmul(es[j].val, c), qmul(a, pt.y));
                 lin_a = qadd(lin_a, qmul(es[j].apow, a));
                 lin_b = qadd(lin_b, qmul(es[j].apow, b));
                 const QM31 ac = qmul(es[j].apow, c);
-                for (int k = 0; k < 4; k++) coefs[j * 4 + k] = ac.v[k];
-                ptrs[j] = col_ptr[es[j].ci];
-                logs[j] = col_log[es[j].ci];
+                if (is_z && is_big(es[j].ci)) {
+                    const size_t gi = es[j].ci < big1 ? (size_t)(es[j].ci - big0) : (size_t)C + (es[j].ci - big2);
+                    for (int k = 0; k < 4; k++) gcoef[gi * 4 + k] = add(gcoef[gi * 4 + k], ac.v[k]);
+                    continue;
+                }
+                for (int k = 0; k < 4; k++) coefs.push_back(ac.v[k]);
+                ptrs.push_back(col_ptr[es[j].ci]);
+                logs.push_back(col_log[es[j].ci]);
             }
             keep32.emplace_back(ctx, coefs.size());
             keep_ptr.emplace_back(ctx, ptrs.size());
@@ -526,10 +578,18 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
             qb.prx = {pt.x.v[0], pt.x.v[1]}; qb.pix = {pt.x.v[2], pt.x.v[3]};
             qb.pry = {pt.y.v[0], pt.y.v[1]}; qb.piy = {pt.y.v[2], pt.y.v[3]};
             qb.lin_a = lin_a; qb.lin_b = lin_b; qb.batch_coeff = qone();  // batches are summed
-            qb.coefs = keep32.back().p; qb.col_idx = nullptr; qb.n_cols = (int)es.size();
+            qb.coefs = keep32.back().p; qb.col_idx = nullptr; qb.n_cols = (int)ptrs.size();
             qb.col_ptr = keep_ptr.back().p; qb.col_log = keep8.back().p;
             qbs.push_back(qb);
         }
+        CB_CUDA(cudaMemcpyAsync(d_gcoef.p, gcoef.data(), gcoef.size() * 4, cudaMemcpyHostToDevice, st));
+        CB_CUDA(launch_rowcomb_m31(st, T.p, N, C, N, d_gcoef.p, g.p, 0));
+        CB_CUDA(launch_rowcomb_m31(st, I.p, N, NI, N, d_gcoef.p + (size_t)C * 4, g.p, 1));
+        {
+            ColSrc gs{SRC_M31, g.p, N, 0};
+            CB_CUDA(launch_fft(st, gs, 4, n, 1, 1 | 4, nullptr, 0, g_lde.p, M, ctx->tw, g.p, N));
+        }
+        ctx->launches += 5;
         DBuf<QuotBatch> d_qb(ctx, qbs.size());
         CB_CUDA(cudaMemcpyAsync(d_qb.p, qbs.data(), qbs.size() * sizeof(QuotBatch), cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_quotients(st, nullptr, 0, 0, nullptr, 0, d_qb.p, (int)qbs.size(), m, ctx->tw, quot.p, M));
