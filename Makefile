@@ -15,7 +15,7 @@ build/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
 oracle-ref:
 	$(MAKE) -C oracle ref

@@ -66,6 +66,16 @@ int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* src, size_t src_str
  * words (src_kind 1: 32 one-bit columns per word, 2: 4 byte columns per word); tiles_out = n_words tiles of
  * [32 or 4][2^(log_size+1)] LDE values.  This is the transform the streaming provers use (coefficients stay on chip). */
 int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out);
+/* ---- one large trace on several GPUs (BASELINE cfg-5) --------------------------------------------------
+ * The ranks of a communicator prove ONE ChaCha20 trace together: every rank calls s2c_prove_chacha20_raw/_dev with the same
+ * inputs; each rank transforms its share of the witness words (whole columns), the LDE tiles are exchanged with an NCCL
+ * grouped send/recv all-to-all so that every rank hashes / evaluates constraints on its row range of all columns, and
+ * rank 0 finishes the proof (ranks > 0 return an empty proof).  The proof bytes are those of the single-GPU prover.
+ * cb_comm_unique_id: 128-byte NCCL id created on one rank and distributed by the caller (e.g. torch.distributed broadcast).
+ * Needs libnccl.so.2 at run time (resolved with dlopen; never touched otherwise) and log_size >= 16. */
+int cb_comm_unique_id(uint8_t id_out[128]);
+int cb_comm_init(cb_ctx* ctx, int rank, int world, const uint8_t id[128]);
+int cb_comm_destroy(cb_ctx* ctx);
 /* Test hook (process-wide): route 13 <= log_size <= 20 through the generic runtime-schedule kernels that serve log_size > 20. */
 int cb_debug_force_generic_fft(int on);
 /* Streaming provers keep as many LDE tiles as device memory allows between the commitment pass and the constraint pass;

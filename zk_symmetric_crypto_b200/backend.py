@@ -14,7 +14,7 @@ EXPORTED_SYMBOLS = [
     "cb_init", "cb_destroy", "cb_last_error", "cb_set_stream", "cb_sync", "cb_launch_count",
     "cb_malloc", "cb_free", "cb_h2d", "cb_d2h", "cb_memset_zero",
     "cb_precompute_twiddles", "cb_interpolate_columns", "cb_evaluate_polynomials", "cb_commit_lde", "cb_lde_packed",
-    "cb_set_max_cached_tiles", "cb_debug_force_generic_fft", "cb_eval_at_point",
+    "cb_comm_unique_id", "cb_comm_init", "cb_comm_destroy", "cb_set_max_cached_tiles", "cb_debug_force_generic_fft", "cb_eval_at_point",
     "cb_merkle_build_leaves", "cb_merkle_leaves_absorb", "cb_merkle_next_layer",
     "cb_generate_secure_powers_rev", "cb_eval_constraints_chacha_stream",
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
@@ -59,6 +59,14 @@ def _take_json(L, out, n):
     s = ctypes.string_at(out.value, n.value).decode()
     L.s2c_free(out)
     return json.loads(s)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (create on one rank, broadcast to the others)."""
+    buf = (ctypes.c_uint8 * 128)()
+    if lib().cb_comm_unique_id(buf) != 0:
+        raise BackendError("NCCL is not available (libnccl.so.2 could not be loaded)")
+    return bytes(buf)
 
 
 class Backend:
@@ -127,6 +135,14 @@ class Backend:
                 k, v = item.split("=")
                 out[k] = out.get(k, 0.0) + float(v)
         return out
+
+    def comm_init(self, rank, world, unique_id):
+        """Join the communicator of the ranks that prove one trace together (unique_id: 128 bytes from comm_unique_id())."""
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.cb_comm_init(self.ctx, int(rank), int(world), buf))
+
+    def comm_destroy(self):
+        self._ck(self.L.cb_comm_destroy(self.ctx))
 
     def counters(self):
         s = self.L.cb_counters(self.ctx).decode()

@@ -55,6 +55,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
     ctx->release_arena();
+    try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -188,6 +189,29 @@ extern int g_force_generic_fft;
 int cb_debug_force_generic_fft(int on) {
     g_force_generic_fft = on;
     return 0;
+}
+
+int cb_comm_unique_id(uint8_t id_out[128]) {
+    try {
+        comm_unique_id(id_out);
+    } catch (const std::exception&) {
+        return 1;
+    }
+    return 0;
+}
+int cb_comm_init(cb_ctx* ctx, int rank, int world, const uint8_t id[128]) {
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (world < 1 || (world & (world - 1))) throw CbError("cb_comm_init: world size must be a power of two");
+    comm_destroy(ctx->comm);
+    if (world > 1) comm_init(ctx->comm, rank, world, id);
+    CB_CATCH(ctx)
+}
+int cb_comm_destroy(cb_ctx* ctx) {
+    CB_TRY(ctx)
+    ctx->sync();
+    comm_destroy(ctx->comm);
+    CB_CATCH(ctx)
 }
 
 int cb_set_max_cached_tiles(cb_ctx* ctx, int n_tiles) {

@@ -1,0 +1,97 @@
+// NCCL through dlopen (see comm.hpp).
+#include <dlfcn.h>
+#include <string.h>
+#include <stdexcept>
+#include <string>
+#include "comm.hpp"
+
+namespace {
+struct UniqueId { char internal[128]; };
+typedef int (*fn_get_id)(UniqueId*);
+typedef int (*fn_init_rank)(void**, int, UniqueId, int);
+typedef int (*fn_destroy)(void*);
+typedef int (*fn_void)();
+typedef int (*fn_sendrecv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+
+struct Api {
+    fn_get_id get_id = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_void group_start = nullptr, group_end = nullptr;
+    fn_sendrecv send = nullptr, recv = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_errstr errstr = nullptr;
+};
+
+Api& api() {
+    static Api a;
+    static bool loaded = false;
+    if (!loaded) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) throw std::runtime_error(std::string("NCCL not available: ") + dlerror());
+        a.get_id = (fn_get_id)dlsym(h, "ncclGetUniqueId");
+        a.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
+        a.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+        a.group_start = (fn_void)dlsym(h, "ncclGroupStart");
+        a.group_end = (fn_void)dlsym(h, "ncclGroupEnd");
+        a.send = (fn_sendrecv)dlsym(h, "ncclSend");
+        a.recv = (fn_sendrecv)dlsym(h, "ncclRecv");
+        a.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+        a.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+        if (!a.get_id || !a.init_rank || !a.destroy || !a.group_start || !a.group_end || !a.send || !a.recv || !a.allreduce)
+            throw std::runtime_error("NCCL symbols missing");
+        loaded = true;
+    }
+    return a;
+}
+
+void ck(int rc, const char* what) {
+    if (rc != 0) {
+        const char* s = api().errstr ? api().errstr(rc) : "?";
+        throw std::runtime_error(std::string(what) + ": NCCL error " + std::to_string(rc) + " (" + s + ")");
+    }
+}
+constexpr int kUint32 = 3, kInt32 = 2, kMin = 3;  // ncclUint32, ncclInt32, ncclMin (nccl.h)
+}  // namespace
+
+void comm_unique_id(uint8_t out[128]) {
+    UniqueId id;
+    ck(api().get_id(&id), "ncclGetUniqueId");
+    memcpy(out, id.internal, 128);
+}
+void comm_init(Comm& c, int rank, int world, const uint8_t idb[128]) {
+    UniqueId id;
+    memcpy(id.internal, idb, 128);
+    ck(api().init_rank(&c.comm, world, id, rank), "ncclCommInitRank");
+    c.rank = rank;
+    c.world = world;
+}
+void comm_destroy(Comm& c) {
+    if (c.comm) api().destroy(c.comm);
+    c.comm = nullptr;
+    c.rank = 0;
+    c.world = 1;
+}
+void comm_group_start() { ck(api().group_start(), "ncclGroupStart"); }
+void comm_group_end() { ck(api().group_end(), "ncclGroupEnd"); }
+void comm_send_u32(const Comm& c, const uint32_t* p, size_t words, int peer, cudaStream_t st) {
+    ck(api().send((void*)p, words, kUint32, peer, c.comm, st), "ncclSend");
+}
+void comm_recv_u32(const Comm& c, uint32_t* p, size_t words, int peer, cudaStream_t st) {
+    ck(api().recv((void*)p, words, kUint32, peer, c.comm, st), "ncclRecv");
+}
+int comm_min_int(const Comm& c, int v, cudaStream_t st) {
+    if (!c.active()) return v;
+    int* d = nullptr;
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
+    cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, st);
+    ck(api().allreduce(d, d, 1, kInt32, kMin, c.comm, st), "ncclAllReduce");
+    cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(d);
+    return v;
+}

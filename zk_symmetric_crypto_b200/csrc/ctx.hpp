@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include "common.cuh"
 #include "host_util.hpp"
+#include "comm.hpp"
 
 struct CbError : std::runtime_error {
     using std::runtime_error::runtime_error;
@@ -33,6 +34,8 @@ struct cb_ctx {
     std::vector<cudaEvent_t> ev_pool;  // timing-disabled events for the producer/consumer hand-off
     cudaEvent_t event(size_t i);
     bool overlap = true;
+    // row-sharded single-proof mode: NCCL communicator over the ranks that prove ONE trace together (world 1 = off)
+    Comm comm;
     std::string err;
     // twiddles (device) for canonic domains up to tw.max_log
     FftTables tw{nullptr, nullptr, nullptr, nullptr, 0};

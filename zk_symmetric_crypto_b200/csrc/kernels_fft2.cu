@@ -25,6 +25,11 @@ using namespace m31d;
 
 __device__ __forceinline__ int padi(int a) { return a + (a >> 4); }
 
+// word offset of (column c, row r) in an output tile of `cpj` columns stored as [row shards][cpj][2^lr rows]
+__device__ __forceinline__ size_t soff(int lr, int cpj, int c, size_t r) {
+    return ((((r >> lr) * cpj) + c) << lr) | (r & (((size_t)1 << lr) - 1));
+}
+
 // One register-radix step over shared memory: local bits [b, b+R) of the j index of a tile [ncol][2^jbits][2^qbits].
 // Local bit b is global butterfly layer i0+b of a domain of log size m; tile_hi = global index bits above the tile's j bits.
 template <int R, bool INV, bool PAD>
@@ -132,6 +137,8 @@ __device__ __forceinline__ void apply_layers(uint32_t* s, int ncol, int colstrid
 struct Jobs {
     int n;                    // jobs in this launch (<= MAX_FFT_JOBS)
     uint32_t one, mone;       // run-time 1 and -1: x*one+y compiles to IMAD, moving butterfly additions to the FMA pipe
+    int shard_log;            // log2 of the rows per row-shard of the output tile (= log_n+1 when the tile is not sharded):
+                              // tile layout [shards][cols][2^shard_log], so that a rank's row range of all columns is contiguous
     const uint32_t* src[MAX_FFT_JOBS];  // packed witness word row (2^n words)
     uint32_t* out[MAX_FFT_JOBS];        // LDE tile [cols_per_job][2^(n+1)]
 };
@@ -229,13 +236,13 @@ __global__ void __launch_bounds__(256) mid_kernel(Jobs jobs, int log_n, int k1, 
     __syncthreads();
     apply_layers<false, PAD>(s0, 1, 0, jb, qbits, 0, jb, tw.X, tw.Y, log_n + 1, k1, 0);
     apply_layers<false, PAD>(s1, 1, 0, jb, qbits, 0, jb, tw.X, tw.Y, log_n + 1, k1, 1);
-    uint32_t* __restrict__ out = jobs.out[job] + ((size_t)col << (log_n + 1));
+    uint32_t* __restrict__ out = jobs.out[job];
     for (int idx = threadIdx.x; idx < tile; idx += blockDim.x) {
         int q = idx & (Q - 1), j = idx >> qbits;
         int a = PAD ? padi(idx) : idx;
         size_t o = ((size_t)j << k1) + q0 + q;
-        out[o] = s0[a];
-        out[o + ((size_t)1 << log_n)] = s1[a];
+        out[soff(jobs.shard_log, cols_per_job, col, o)] = s0[a];
+        out[soff(jobs.shard_log, cols_per_job, col, o + ((size_t)1 << log_n))] = s1[a];
     }
 }
 
@@ -246,16 +253,18 @@ __global__ void __launch_bounds__(256) fft_low_kernel(Jobs jobs, int log_n, int 
     const int colstride = padi(T);
     const uint32_t chunk = blockIdx.x;
     const int job = blockIdx.y / groups_per_job, c0 = (blockIdx.y % groups_per_job) * nc;
-    uint32_t* __restrict__ data = jobs.out[job] + ((size_t)c0 << m) + (size_t)chunk * T;
+    uint32_t* __restrict__ data = jobs.out[job];
+    const int cpj = groups_per_job * nc;
+    (void)m;
     for (int idx = threadIdx.x; idx < nc * T; idx += blockDim.x) {
         int c = idx >> k1, r = idx & (T - 1);
-        s[c * colstride + padi(r)] = data[((size_t)c << m) + r];
+        s[c * colstride + padi(r)] = data[soff(jobs.shard_log, cpj, c0 + c, (size_t)chunk * T + r)];
     }
     __syncthreads();
     apply_layers<false, true>(s, nc, colstride, k1, 0, 0, k1, tw.X, tw.Y, m, 0, chunk);
     for (int idx = threadIdx.x; idx < nc * T; idx += blockDim.x) {
         int c = idx >> k1, r = idx & (T - 1);
-        data[((size_t)c << m) + r] = s[c * colstride + padi(r)];
+        data[soff(jobs.shard_log, cpj, c0 + c, (size_t)chunk * T + r)] = s[c * colstride + padi(r)];
     }
 }
 
@@ -407,7 +416,9 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
     const int m = log_n + 1;
     const uint32_t chunk = blockIdx.x;
     const int job = blockIdx.y / groups_per_job, c0 = (blockIdx.y % groups_per_job) * NC;
-    uint32_t* __restrict__ data = jobs.out[job] + ((size_t)c0 << m) + (size_t)chunk * T2;
+    // a 4096-row chunk lies inside one row shard (shards hold >= 4096 rows); column stride inside a shard = 2^lr
+    const int lr = jobs.shard_log, cpj = groups_per_job * NC;
+    uint32_t* __restrict__ data = jobs.out[job] + soff(lr, cpj, c0, (size_t)chunk * T2);
     const int p = threadIdx.x;
     uint32_t twr[16], v[16];
     {
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
 #pragma unroll
         for (int c = 0; c < NC; c++) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = data[((size_t)c << m) + p + 256 * k];
+            for (int k = 0; k < 16; k++) v[k] = data[((size_t)c << lr) + p + 256 * k];
             fwd_block<4>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
             for (int k = 0; k < 16; k++) s[c * COLW + ad[k]] = v[k];
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
                 v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             }
             fwd_block<4>(v, twr, jobs.one, jobs.mone);
-            uint4* o = (uint4*)(data + ((size_t)c << m) + 16 * p);
+            uint4* o = (uint4*)(data + ((size_t)c << lr) + 16 * p);
 #pragma unroll
             for (int i = 0; i < 4; i++) o[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
@@ -473,7 +484,9 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
     const uint32_t q0 = blockIdx.x * 32;
     const int job = blockIdx.y / cols_per_job, col = blockIdx.y % cols_per_job;
     const uint32_t* __restrict__ in = scratch + ((size_t)blockIdx.y << log_n) + q0 + q;
-    uint32_t* __restrict__ out = jobs.out[job] + ((size_t)col << m) + q0 + q;
+    uint32_t* __restrict__ out = jobs.out[job];
+    const int lr = jobs.shard_log;
+    const size_t rq = (size_t)q0 + q;
     uint32_t twr[1 << RA], v[1 << RA];
     if (RB == 0) {
         load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, 0, 0);
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
             load_tw<RA>(twr, tw.X, tw.Y, m, K1, (uint32_t)h << JB, 0);
             fwd_block<RA>(u, twr, jobs.one, jobs.mone);
 #pragma unroll
-            for (int k = 0; k < J; k++) out[((size_t)h << log_n) + ((size_t)k << K1)] = u[k];
+            for (int k = 0; k < J; k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)k << K1) + rq)] = u[k];
         }
         return;
     }
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
         for (int k = 0; k < (1 << RA); k++) v[k] = sh[((j0 + k) << 5) | q];
         fwd_block<RA>(v, twr, jobs.one, jobs.mone);
 #pragma unroll
-        for (int k = 0; k < (1 << RA); k++) out[((size_t)h << log_n) + ((size_t)(j0 + k) << K1)] = v[k];
+        for (int k = 0; k < (1 << RA); k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)(j0 + k) << K1) + rq)] = v[k];
     }
 }
 
@@ -587,7 +600,7 @@ size_t fft_packed_scratch_words(int kind, int njobs, int log_n) {
 // apart, src[j] -> the first of them).  src[j]: packed word row of job j (2^log_n words);
 // out[j]: tile [cols][2^(log_n+1)].  Returns the number of kernels launched through *launches.
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
-                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches) {
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log) {
     using namespace fft2;
 #define HOOK(name, b) do { if (hook) hook->fn(hook->user, name, b); } while (0)
     const int cpj = kind == SRC_BITS ? 32 : 4;
@@ -596,6 +609,7 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         Jobs jobs;
         jobs.n = njobs - j0 < MAX_FFT_JOBS ? njobs - j0 : MAX_FFT_JOBS;
         jobs.one = 1u;
+        jobs.shard_log = (shard_log > 0 && shard_log < log_n + 1) ? shard_log : log_n + 1;
         jobs.mone = 0xffffffffu;
         for (int j = 0; j < jobs.n; j++) { jobs.src[j] = src[j0 + j]; jobs.out[j] = out[j0 + j]; }
         if (log_n <= 12) {

@@ -152,10 +152,11 @@ __global__ void split16_kernel(const uint4* __restrict__ t, int n, uint4* __rest
 }
 
 // acc[c][row] *= den_inv[row >> trace_log]
-__global__ void scale_rows_kernel(uint32_t* __restrict__ acc, size_t M, int trace_log, const uint32_t* __restrict__ den_inv) {
+__global__ void scale_rows_kernel(uint32_t* __restrict__ acc, size_t M, int trace_log, const uint32_t* __restrict__ den_inv,
+                                  size_t row0) {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= M) return;
-    const uint32_t d = __ldg(den_inv + (row >> trace_log));
+    const uint32_t d = __ldg(den_inv + ((row0 + row) >> trace_log));  // row0: first global row of this rank's row shard
 #pragma unroll
     for (int c = 0; c < 4; c++) acc[(size_t)c * M + row] = mulm(acc[(size_t)c * M + row], d);
 }
@@ -304,8 +305,8 @@ cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32
     return cudaGetLastError();
 }
 
-cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv) {
-    strm::scale_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(acc, M, trace_log, den_inv);
+cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0) {
+    strm::scale_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(acc, M, trace_log, den_inv, row0);
     return cudaGetLastError();
 }
 

@@ -277,6 +277,14 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const size_t N = (size_t)1 << n, M = (size_t)1 << m;
     const uint32_t rows_needed = (num_blocks + 15) / 16;
     const uint32_t inv_n = 1u << (31 - n);
+    // row-sharded mode (several ranks prove this one trace): each rank holds rows [rank*Mr, (rank+1)*Mr) of every LDE tile
+    const Comm& cm = ctx->comm;
+    const int G = cm.world, R = cm.rank;
+    int logG = 0;
+    while ((1 << logG) < G) logG++;
+    if (G > 1 && n < 16) return "sharded proving needs log_size >= 16 (got " + std::to_string(n) + ")";
+    const int lr = m - logG;             // log2 of the rows per shard
+    const size_t Mr = M >> logG;
     cudaStream_t st = ctx->stream;
     ctx->ensure_twiddles(m);
     ctx->pending_events.clear();
@@ -333,13 +341,16 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
     static const std::vector<Group> plan = build_plan();
     // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
-    const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr;
+    const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr && G == 1;
     const int lag = overlap ? 2 : 0;
     static const int peak_trans_lag[3] = {plan_peak_transient(plan, 0), 0, plan_peak_transient(plan, 2)};
     const int peak_trans = peak_trans_lag[lag];
     cudaStream_t sf = overlap ? ctx->stream2 : st;
-    const size_t tile_words = 32 * M;
+    const size_t tile_words = 32 * Mr;
     const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, MAX_FFT_JOBS, n);
+    // sharded mode: whole transformed tiles ([G][32][Mr]) wait here for the all-to-all; at most ceil(16/G) jobs per rank and group
+    const int n_stage = G > 1 ? (16 + G - 1) / G : 0;
+    const size_t stage_words = (size_t)n_stage * 32 * M;
     int n_cache = N_INDEP_WORDS;
     {
         size_t free_b = 0, total_b = 0;
@@ -352,16 +363,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         const size_t avail = free_b + (size_t)(reserved - used) + ctx->arena_bytes;  // the arena is re-used (or re-made)
         // everything else this proof allocates: scratch, leaf state + tree (24 M words), accumulators / composition /
         // quotient / FRI columns (~48 M words), plus slack for the allocator
-        const size_t other = (scratch_words + 96 * M) * 4 + ((size_t)3 << 30);
+        const size_t other = (scratch_words + stage_words + 96 * M) * 4 + ((size_t)3 << 30);
         const size_t tile_bytes = tile_words * 4;
         const size_t can = avail > other ? (avail - other) / tile_bytes : 0;
         if (can < (size_t)peak_trans) throw CbError("not enough device memory for the tile arena at log_size " + std::to_string(n));
         const int cap = opt.max_cached_tiles >= 0 ? opt.max_cached_tiles : ctx->max_cached_tiles;
         if (cap >= 0 && n_cache > cap) n_cache = cap;
         if ((size_t)n_cache > can - peak_trans) n_cache = (int)(can - peak_trans);
+        n_cache = comm_min_int(cm, n_cache, st);  // every rank must take the same caching decisions
     }
     // tile slots + FFT scratch live in the context's persistent arena
-    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_words;
+    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_words + stage_words;
     uint32_t* arena_p;
     if (ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30))
         arena_p = (uint32_t*)ctx->arena;
@@ -370,6 +382,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         arena_p = (uint32_t*)ctx->ensure_arena(arena_words * 4);
     }
     uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words;
+    uint32_t* stage_p = scratch_p + scratch_words;
     Tiles tiles;
     tiles.init(n_cache, peak_trans, tile_words, arena_p);
     tiles.lag = lag;
@@ -378,21 +391,60 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ctx->transient_tiles = peak_trans;
 
     auto run_pass = [&](int pass, auto&& consume) {
-        const size_t G = plan.size();
+        const size_t NG = plan.size();
         tiles.flush();
-        for (size_t gi = 0; gi < G; gi++) {
+        for (size_t gi = 0; gi < NG; gi++) {
             const Group& g = plan[gi];
             tiles.begin_group((int)gi);
             std::vector<const uint32_t*> src;
             std::vector<uint32_t*> out;
+            std::vector<int> jobs_w;
             for (int w : g.fft)
-                if (tiles.acquire(w, true, pass)) {
+                if (tiles.acquire(w, true, pass)) jobs_w.push_back(w);
+            if (G > 1 && !jobs_w.empty()) {
+                // column-sharded transform: job j of the group belongs to rank j mod G, which transforms the whole columns
+                // into a staging tile laid out [G][32][Mr]; then the grouped send/recv all-to-all hands every rank its row
+                // shard of every tile of the group
+                int k = 0;
+                for (size_t j = 0; j < jobs_w.size(); j++)
+                    if ((int)(j % G) == R) {
+                        src.push_back(W.p + (size_t)jobs_w[j] * N);
+                        out.push_back(stage_p + (size_t)(k++) * 32 * M);
+                    }
+                if (!src.empty()) {
+                    int nl = 0;
+                    CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl, lr));
+                    ctx->launches += nl;
+                    ctx->fft_words += src.size();
+                }
+                ctx->stage_begin("all_to_all");
+                comm_group_start();
+                k = 0;
+                for (size_t j = 0; j < jobs_w.size(); j++) {
+                    const int owner = (int)(j % G);
+                    uint32_t* slot = tiles.ptr(jobs_w[j]);
+                    if (owner == R) {
+                        const uint32_t* stg = stage_p + (size_t)(k++) * 32 * M;
+                        for (int r = 0; r < G; r++)
+                            if (r != R) comm_send_u32(cm, stg + (size_t)r * tile_words, tile_words, r, st);
+                        CB_CUDA(cudaMemcpyAsync(slot, stg + (size_t)R * tile_words, tile_words * 4, cudaMemcpyDeviceToDevice, st));
+                    } else {
+                        comm_recv_u32(cm, slot, tile_words, owner, st);
+                    }
+                }
+                comm_group_end();
+                ctx->stage_end();
+                src.clear();
+                out.clear();
+            } else {
+                for (int w : jobs_w) {
                     src.push_back(W.p + (size_t)w * N);
                     out.push_back(tiles.ptr(w));
                 }
+            }
             if (!src.empty()) {
                 // producer: may overwrite slots released two groups ago -> wait for that group's consumer
-                if (overlap && gi >= 2) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(G + gi - 2), 0));
+                if (overlap && gi >= 2) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(NG + gi - 2), 0));
                 int nl = 0;
                 CB_CUDA(launch_fft_packed(sf, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl));
                 ctx->launches += nl;
@@ -404,42 +456,77 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             }
             for (auto& c : g.comb) tiles.acquire(c.res, false, pass);
             consume(gi, g);
-            if (overlap) CB_CUDA(cudaEventRecord(ctx->event(G + gi), st));
+            if (overlap) CB_CUDA(cudaEventRecord(ctx->event(NG + gi), st));
             for (int w : g.free_after) tiles.release(w);
         }
         for (int w = 0; w < N_WORDS; w++) tiles.release(w);
-        if (overlap) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(2 * G - 1), 0));  // next pass's producer starts after this pass
+        if (overlap) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(2 * NG - 1), 0));  // next pass's producer starts after this pass
     };
 
-    // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree
+    // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree.  Sharded mode: every rank builds
+    //      the subtree over its Mr leaves; rank 0 collects the layers, adds the top log2(G) layers and broadcasts the root.
     DevMerkle tree1;
     tree1.log_leaves = m;
-    tree1.nodes = DBuf<uint32_t>(ctx, (((size_t)2 << m) - 1) * 8);
+    if (R == 0) tree1.nodes = DBuf<uint32_t>(ctx, (((size_t)2 << m) - 1) * 8);
     {
-        DBuf<uint32_t> hstate(ctx, 8 * M);
+        DevMerkle local;
+        local.log_leaves = lr;
+        DBuf<uint32_t> local_nodes;
+        if (G > 1) local_nodes = DBuf<uint32_t>(ctx, (((size_t)2 << lr) - 1) * 8);
+        uint32_t* ln = G > 1 ? local_nodes.p : tree1.nodes.p;  // unsharded: the local subtree IS the tree
+        DBuf<uint32_t> hstate(ctx, 8 * Mr);
         uint64_t bytes_before = 0;
         run_pass(1, [&](size_t gi, const Group& g) {
             LeafGroups lg{};
             lg.n = (int)g.hash.size();
             for (int i = 0; i < lg.n; i++) {
-                lg.g[i] = {tiles.ptr(g.hash[i]), M, 32, m, nullptr, nullptr, nullptr};
+                lg.g[i] = {tiles.ptr(g.hash[i]), Mr, 32, lr, nullptr, nullptr, nullptr};
                 for (auto& c : g.comb)
-                    if (c.res == g.hash[i]) lg.g[i] = {tiles.ptr(c.a), M, 32, m, tiles.ptr(c.b), tiles.ptr(c.c), tiles.ptr(c.res)};
+                    if (c.res == g.hash[i]) lg.g[i] = {tiles.ptr(c.a), Mr, 32, lr, tiles.ptr(c.b), tiles.ptr(c.c), tiles.ptr(c.res)};
             }
             ctx->stage_begin("trace_merkle_leaves");
-            CB_CUDA(launch_merkle_leaves(st, lg, m, hstate.p, bytes_before, gi == 0, gi + 1 == plan.size(), tree1.nodes.p));
+            CB_CUDA(launch_merkle_leaves(st, lg, lr, hstate.p, bytes_before, gi == 0, gi + 1 == plan.size(), ln));
             ctx->stage_end();
             ctx->launches++;
             bytes_before += 128ull * g.hash.size();
         });
         ctx->stage_begin("merkle_nodes");
-        for (int l = 0; l < m; l++) {
-            CB_CUDA(launch_merkle_nodes(st, tree1.nodes.p + tree1.layer_offset(l) * 8, 1u << (m - l - 1),
-                                        tree1.nodes.p + tree1.layer_offset(l + 1) * 8));
+        for (int l = 0; l < lr; l++) {
+            CB_CUDA(launch_merkle_nodes(st, ln + local.layer_offset(l) * 8, 1u << (lr - l - 1), ln + local.layer_offset(l + 1) * 8));
             ctx->launches++;
         }
+        if (G > 1) {
+            comm_group_start();
+            for (int l = 0; l <= lr; l++) {
+                const size_t cnt = ((size_t)Mr >> l) * 8;
+                if (R == 0) {
+                    CB_CUDA(cudaMemcpyAsync(tree1.nodes.p + tree1.layer_offset(l) * 8, ln + local.layer_offset(l) * 8, cnt * 4,
+                                            cudaMemcpyDeviceToDevice, st));
+                    for (int r = 1; r < G; r++) comm_recv_u32(cm, tree1.nodes.p + tree1.layer_offset(l) * 8 + (size_t)r * cnt, cnt, r, st);
+                } else {
+                    comm_send_u32(cm, ln + local.layer_offset(l) * 8, cnt, 0, st);
+                }
+            }
+            comm_group_end();
+            DBuf<uint32_t> d_root(ctx, 8);
+            if (R == 0) {
+                for (int l = lr; l < m; l++) {
+                    CB_CUDA(launch_merkle_nodes(st, tree1.nodes.p + tree1.layer_offset(l) * 8, 1u << (m - l - 1),
+                                                tree1.nodes.p + tree1.layer_offset(l + 1) * 8));
+                    ctx->launches++;
+                }
+                CB_CUDA(cudaMemcpyAsync(d_root.p, tree1.nodes.p + tree1.layer_offset(m) * 8, 32, cudaMemcpyDeviceToDevice, st));
+            }
+            comm_group_start();
+            if (R == 0) for (int r = 1; r < G; r++) comm_send_u32(cm, d_root.p, 8, r, st);
+            else comm_recv_u32(cm, d_root.p, 8, 0, st);
+            comm_group_end();
+            CB_CUDA(cudaMemcpyAsync(tree1.root.b, d_root.p, 32, cudaMemcpyDeviceToHost, st));
+            ctx->sync();
+        } else {
+            CB_CUDA(cudaMemcpyAsync(tree1.root.b, tree1.nodes.p + tree1.layer_offset(m) * 8, 32, cudaMemcpyDeviceToHost, st));
+        }
         ctx->stage_end();
-        CB_CUDA(cudaMemcpyAsync(tree1.root.b, tree1.nodes.p + tree1.layer_offset(m) * 8, 32, cudaMemcpyDeviceToHost, st));
     }
     // ---- statement (the two public-input hashes were computed on host threads while the GPU ran pass 1)
     std::vector<uint8_t> stmt;
@@ -467,7 +554,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- composition polynomial (pass 2): constraint quotients accumulated tile by tile
     QM31 random_coeff = ch.draw_secure_felt();
-    DBuf<uint32_t> apr(ctx, (size_t)N_CONSTRAINTS * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, 4 * M);
+    DBuf<uint32_t> apr(ctx, (size_t)N_CONSTRAINTS * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, R == 0 ? 4 * M : 4);
+    DBuf<uint32_t> acc_local;
+    if (G > 1) acc_local = DBuf<uint32_t>(ctx, 4 * Mr);
+    uint32_t* accp = G > 1 ? acc_local.p : acc.p;  // this rank's rows of the 4 accumulator columns
     DBuf<uint32_t> apr_lo(ctx, (size_t)N_CONSTRAINTS * 4), apr_hi(ctx, (size_t)N_CONSTRAINTS * 4);
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
     CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
@@ -491,12 +581,31 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                             c.kx, c.kb0, c.kb1, c.kb2, c.kbc, c.arg, c.type};
         if (cj.n == 0) return;
         ctx->stage_begin("constraints");
-        CB_CUDA(launch_constraints_tiles(st, cj, M, apr_lo.p, apr_hi.p, acc.p, gi == 0));
+        CB_CUDA(launch_constraints_tiles(st, cj, Mr, apr_lo.p, apr_hi.p, accp, gi == 0));
         ctx->stage_end();
         ctx->launches++;
     });
-    CB_CUDA(launch_scale_rows(st, acc.p, M, n, d_den.p));
+    CB_CUDA(launch_scale_rows(st, accp, Mr, n, d_den.p, (size_t)R * Mr));
     ctx->launches++;
+    if (G > 1) {
+        // the row shards of the accumulator go to rank 0, which finishes the proof alone (4-8 columns from here on)
+        comm_group_start();
+        for (int c = 0; c < 4; c++) {
+            if (R == 0) {
+                CB_CUDA(cudaMemcpyAsync(acc.p + (size_t)c * M, accp + (size_t)c * Mr, Mr * 4, cudaMemcpyDeviceToDevice, st));
+                for (int r = 1; r < G; r++) comm_recv_u32(cm, acc.p + (size_t)c * M + (size_t)r * Mr, Mr, r, st);
+            } else {
+                comm_send_u32(cm, accp + (size_t)c * Mr, Mr, 0, st);
+            }
+        }
+        comm_group_end();
+        ctx->sync();
+        if (R != 0) {
+            proof.clear();
+            ctx->collect_stages();
+            return "";
+        }
+    }
 
     ctx->stage_begin("composition_commit");
     // interpolate the 4 coordinate columns (log m), split into halves, evaluate each half (log n) on the LDE domain
