@@ -17,6 +17,8 @@ from zk_symmetric_crypto_b200 import backend
 
 def main():
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    check = sys.argv[2] if len(sys.argv) > 2 else "single"     # "single": compare with the single-GPU proof; "ref": the
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3       # reference's own verifier accepts it (sizes one GPU cannot hold)
     rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -29,7 +31,7 @@ def main():
     key, nonce, counter, pt, ct = bench.synth_inputs(L, 0)       # same inputs on every rank
     ptb, ctb = pt.tobytes(), ct.tobytes()
     times = []
-    for it in range(3):
+    for it in range(iters):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -37,7 +39,16 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         times.append(time.perf_counter() - t0)
-    if rank == 0:
+    if rank == 0 and check == "ref":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import base64
+        import ref_wasm
+        t0 = time.perf_counter()
+        v = ref_wasm.verify_chacha20_proof(base64.b64encode(proof).decode(), nonce, counter, ptb, ctb)
+        assert v == {"algorithm": "chacha20", "valid": True}, v
+        print("SHARDED_OK log_n_rows=%d ranks=%d proof_bytes=%d sharded_ms=%s reference_verifier=accepted (%.1f s)" %
+              (L, world, len(proof), ["%.1f" % (t * 1e3) for t in times], time.perf_counter() - t0))
+    elif rank == 0:
         single = z.Backend(local_rank)
         want = single.prove_chacha20_raw(key, nonce, counter, ptb, ctb)
         t0 = time.perf_counter()

@@ -347,9 +347,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const int peak_trans = peak_trans_lag[lag];
     cudaStream_t sf = overlap ? ctx->stream2 : st;
     const size_t tile_words = 32 * Mr;
-    const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, MAX_FFT_JOBS, n);
     // sharded mode: whole transformed tiles ([G][32][Mr]) wait here for the all-to-all; at most ceil(16/G) jobs per rank and group
     const int n_stage = G > 1 ? (16 + G - 1) / G : 0;
+    const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, G > 1 ? n_stage : MAX_FFT_JOBS, n);
     const size_t stage_words = (size_t)n_stage * 32 * M;
     int n_cache = N_INDEP_WORDS;
     {
