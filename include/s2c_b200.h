@@ -161,6 +161,35 @@ const char* cb_stage_times(cb_ctx* ctx);
 /* Counters of the last streaming proof on ctx: "fft_words=..;cached_tiles=..;transient_tiles=..;" (packed witness words
  * transformed to LDE tiles over both passes, tiles kept between the passes, transient tile slots). */
 const char* cb_counters(cb_ctx* ctx);
+/* ---- verification and prove+verify (wasm_api.rs:609-648 verify_chacha20_proof, :904-946 verify_aes_ctr_proof,
+ * :61-188 prove_chacha20_encrypt, :210-330 prove_aes128_ctr_encrypt, :343-463 prove_aes256_ctr_encrypt).
+ * Verification is host work (csrc/verify.cu: air_stream.rs:284-421, air_ctr.rs:619-714 + upstream verify) and needs no
+ * CUDA context.  JSON as the reference: {"valid":true,"algorithm":A} | {"valid":false,"error":"<VerificationError {:?}>"} |
+ * {"error":"Proof payload too large" | "Nonce must be 12 bytes, got N" | "Invalid base64: ..." | "Invalid proof format: ..."}.
+ * verify_aes_ctr_proof serves both key sizes (read from the proof's statement). */
+int s2c_verify_chacha20_proof(const char* proof_b64, size_t proof_b64_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                              const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext, size_t ciphertext_len,
+                              char** json_out, size_t* json_len);
+int s2c_verify_aes_ctr_proof(const char* proof_b64, size_t proof_b64_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                             const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext, size_t ciphertext_len,
+                             char** json_out, size_t* json_len);
+/* Raw forms: bincode proof bytes in; 0 = valid, 1 = rejected or malformed, with the reference's error rendering in *error_out
+ * (s2c_free; NULL when valid). */
+int s2c_verify_chacha20_raw(const uint8_t* proof, size_t proof_len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                            size_t plaintext_len, const uint8_t* ciphertext, size_t ciphertext_len, char** error_out);
+int s2c_verify_aes_ctr_raw(const uint8_t* proof, size_t proof_len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           size_t plaintext_len, const uint8_t* ciphertext, size_t ciphertext_len, char** error_out);
+/* Prove on the GPU, verify on the host: {"success":true,"blocks":N,"algorithm":A} | {"error":"..."} (validation and prover
+ * errors as the generate_* calls; "Verification failed: <VerificationError {:?}>" if the fresh proof does not verify). */
+int s2c_prove_chacha20_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                               uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                               size_t ciphertext_len, char** json_out, size_t* json_len);
+int s2c_prove_aes128_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                 uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                                 size_t ciphertext_len, char** json_out, size_t* json_len);
+int s2c_prove_aes256_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                 uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
+                                 size_t ciphertext_len, char** json_out, size_t* json_len);
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len);
 int s2c_get_circuits_info(char** json_out, size_t* json_len);

@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = [
     "cb_gen_trace_chacha_stream",
     "s2c_generate_chacha20_proof", "s2c_generate_aes128_ctr_proof", "s2c_generate_aes256_ctr_proof", "s2c_prove_aes_ctr_raw",
     "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_counters",
+    "s2c_verify_chacha20_proof", "s2c_verify_aes_ctr_proof", "s2c_verify_chacha20_raw", "s2c_verify_aes_ctr_raw",
+    "s2c_prove_chacha20_encrypt", "s2c_prove_aes128_ctr_encrypt", "s2c_prove_aes256_ctr_encrypt",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
 ]
 
@@ -216,6 +218,18 @@ class Backend:
         """wasm_api.rs:776 generate_aes256_ctr_proof."""
         return self._generate_aes(self.L.s2c_generate_aes256_ctr_proof, key, nonce, counter, plaintext, ciphertext)
 
+    def prove_chacha20_encrypt(self, key, nonce, counter, plaintext, ciphertext):
+        """wasm_api.rs:61 prove_chacha20_encrypt: prove on the GPU, verify on the host -> {"success", "blocks", "algorithm"}."""
+        return self._generate_aes(self.L.s2c_prove_chacha20_encrypt, key, nonce, counter, plaintext, ciphertext)
+
+    def prove_aes128_ctr_encrypt(self, key, nonce, counter, plaintext, ciphertext):
+        """wasm_api.rs:210 prove_aes128_ctr_encrypt."""
+        return self._generate_aes(self.L.s2c_prove_aes128_ctr_encrypt, key, nonce, counter, plaintext, ciphertext)
+
+    def prove_aes256_ctr_encrypt(self, key, nonce, counter, plaintext, ciphertext):
+        """wasm_api.rs:343 prove_aes256_ctr_encrypt."""
+        return self._generate_aes(self.L.s2c_prove_aes256_ctr_encrypt, key, nonce, counter, plaintext, ciphertext)
+
     def prove_aes_ctr_raw(self, key, nonce, counter, plaintext, ciphertext):
         key, nonce, pb, cbuf = bytes(key), bytes(nonce), bytes(plaintext), bytes(ciphertext)
         out = ctypes.POINTER(ctypes.c_uint8)()
@@ -252,6 +266,66 @@ def generate_aes128_ctr_proof(key, nonce, counter, plaintext, ciphertext):
 
 def generate_aes256_ctr_proof(key, nonce, counter, plaintext, ciphertext):
     return _default().generate_aes256_ctr_proof(key, nonce, counter, plaintext, ciphertext)
+
+
+def _verify_json(name, proof_b64, nonce, counter, plaintext, ciphertext):
+    L = lib()
+    pb64 = proof_b64.encode() if isinstance(proof_b64, str) else bytes(proof_b64)
+    nonce, pb, cbuf = bytes(nonce), bytes(plaintext), bytes(ciphertext)
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    rc = getattr(L, name)(pb64, ctypes.c_size_t(len(pb64)), nonce, ctypes.c_size_t(len(nonce)), ctypes.c_uint32(counter & 0xFFFFFFFF),
+                          pb, ctypes.c_size_t(len(pb)), cbuf, ctypes.c_size_t(len(cbuf)), ctypes.byref(out), ctypes.byref(n))
+    if not out:
+        raise BackendError("%s failed with status %d" % (name, rc))
+    return _take_json(L, out, n)
+
+
+def verify_chacha20_proof(proof_b64, nonce, counter, plaintext, ciphertext):
+    """wasm_api.rs:609 verify_chacha20_proof -> {"valid": True, "algorithm": ...} | {"valid": False, "error": ...} | {"error": ...}.
+    Host-side (csrc/verify.cu); needs no GPU."""
+    return _verify_json("s2c_verify_chacha20_proof", proof_b64, nonce, counter, plaintext, ciphertext)
+
+
+def verify_aes_ctr_proof(proof_b64, nonce, counter, plaintext, ciphertext):
+    """wasm_api.rs:904 verify_aes_ctr_proof (AES-128 and AES-256)."""
+    return _verify_json("s2c_verify_aes_ctr_proof", proof_b64, nonce, counter, plaintext, ciphertext)
+
+
+def _verify_raw(name, proof, nonce, counter, plaintext, ciphertext):
+    L = lib()
+    proof, nonce, pb, cbuf = bytes(proof), bytes(nonce), bytes(plaintext), bytes(ciphertext)
+    if len(nonce) != 12:
+        raise BackendError("Nonce must be 12 bytes, got %d" % len(nonce))
+    err = ctypes.c_void_p()
+    rc = getattr(L, name)(proof, ctypes.c_size_t(len(proof)), nonce, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, ctypes.c_size_t(len(pb)),
+                          cbuf, ctypes.c_size_t(len(cbuf)), ctypes.byref(err))
+    msg = None
+    if err:
+        msg = ctypes.string_at(err.value).decode()
+        L.s2c_free(err)
+    return rc == 0, msg
+
+
+def verify_chacha20_raw(proof, nonce, counter, plaintext, ciphertext):
+    """bincode StreamProof bytes -> (valid, error rendering or None)."""
+    return _verify_raw("s2c_verify_chacha20_raw", proof, nonce, counter, plaintext, ciphertext)
+
+
+def verify_aes_ctr_raw(proof, nonce, counter, plaintext, ciphertext):
+    return _verify_raw("s2c_verify_aes_ctr_raw", proof, nonce, counter, plaintext, ciphertext)
+
+
+def prove_chacha20_encrypt(key, nonce, counter, plaintext, ciphertext):
+    return _default().prove_chacha20_encrypt(key, nonce, counter, plaintext, ciphertext)
+
+
+def prove_aes128_ctr_encrypt(key, nonce, counter, plaintext, ciphertext):
+    return _default().prove_aes128_ctr_encrypt(key, nonce, counter, plaintext, ciphertext)
+
+
+def prove_aes256_ctr_encrypt(key, nonce, counter, plaintext, ciphertext):
+    return _default().prove_aes256_ctr_encrypt(key, nonce, counter, plaintext, ciphertext)
 
 
 def debug_chacha20_keystream(key, nonce, counter):

@@ -496,11 +496,11 @@ int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     CB_CATCH(ctx)
 }
 
-// StarkProof::size_estimate() of the reference is reported as proof_size_bytes; see estimate in prove driver notes.
-int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
-                                uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
-                                size_t* json_len) {
-    // validation order and messages: wasm_api.rs:475-493
+// Validation + proving shared by generate_chacha20_proof and prove_chacha20_encrypt (wasm_api.rs:68-86 == :475-493).
+// Returns -1 with the proof bytes in `proof`, or the value the caller must return (the error JSON is already written).
+static int chacha_prove_checked(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len,
+                                std::vector<uint8_t>& proof, size_t& num_blocks, char** json_out, size_t* json_len) {
     if (key_len != 32) return ret_json(json_error("Key must be 32 bytes, got " + std::to_string(key_len)), json_out, json_len);
     if (nonce_len != 12) return ret_json(json_error("Nonce must be 12 bytes, got " + std::to_string(nonce_len)), json_out, json_len);
     if (pt_len == 0 || pt_len % 64 != 0)
@@ -508,14 +508,13 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
     if (ct_len != pt_len)
         return ret_json(json_error("Ciphertext must be same length as plaintext, got " + std::to_string(ct_len) + " vs " +
                                    std::to_string(pt_len)), json_out, json_len);
-    size_t num_blocks = pt_len / 64;
+    num_blocks = pt_len / 64;
     if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
         return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
                                    " blocks would exceed u32::MAX"), json_out, json_len);
     std::string derr;
     if (!ctx) ctx = default_ctx(derr);
     if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
-    std::vector<uint8_t> proof;
     std::string e;
     try {
         CB_CUDA(cudaSetDevice(ctx->device));
@@ -526,6 +525,18 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
         return 1;
     }
     if (!e.empty()) return ret_json(json_error(e), json_out, json_len);
+    return -1;
+}
+
+// StarkProof::size_estimate() of the reference is reported as proof_size_bytes; see estimate in prove driver notes.
+int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                                uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
+                                size_t* json_len) {
+    std::vector<uint8_t> proof;
+    size_t num_blocks = 0;
+    const int rc = chacha_prove_checked(ctx, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks, json_out,
+                                        json_len);
+    if (rc != -1) return rc;
     std::string b64 = host::base64_encode(proof.data(), proof.size());
     std::string js = "{\"algorithm\":\"chacha20\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
                      "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 84)) +
@@ -533,9 +544,10 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
     return ret_json(js, json_out, json_len);
 }
 
-static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const uint8_t* key, size_t key_len, const uint8_t* nonce,
-                        size_t nonce_len, uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len,
-                        char** json_out, size_t* json_len) {
+// Validation + proving shared by generate_aes*_ctr_proof and prove_aes*_ctr_encrypt; same contract as chacha_prove_checked.
+static int aes_prove_checked(cb_ctx* ctx, int key_bytes, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
+                             uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len,
+                             std::vector<uint8_t>& proof, size_t& num_blocks, char** json_out, size_t* json_len) {
     // validation order and messages: wasm_api.rs:660-678 / 784-802
     if (key_len != (size_t)key_bytes)
         return ret_json(json_error("Key must be " + std::to_string(key_bytes) + " bytes, got " + std::to_string(key_len)), json_out, json_len);
@@ -545,14 +557,13 @@ static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const
     if (ct_len != pt_len)
         return ret_json(json_error("Ciphertext must be same length as plaintext, got " + std::to_string(ct_len) + " vs " +
                                    std::to_string(pt_len)), json_out, json_len);
-    size_t num_blocks = pt_len / 16;
+    num_blocks = pt_len / 16;
     if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
         return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
                                    " blocks would exceed u32::MAX"), json_out, json_len);
     std::string derr;
     if (!ctx) ctx = default_ctx(derr);
     if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
-    std::vector<uint8_t> proof;
     std::string e;
     try {
         CB_CUDA(cudaSetDevice(ctx->device));
@@ -563,6 +574,17 @@ static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const
         return 1;
     }
     if (!e.empty()) return ret_json(json_error(e), json_out, json_len);
+    return -1;
+}
+
+static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const uint8_t* key, size_t key_len, const uint8_t* nonce,
+                        size_t nonce_len, uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len,
+                        char** json_out, size_t* json_len) {
+    std::vector<uint8_t> proof;
+    size_t num_blocks = 0;
+    const int rc = aes_prove_checked(ctx, key_bytes, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks,
+                                     json_out, json_len);
+    if (rc != -1) return rc;
     std::string b64 = host::base64_encode(proof.data(), proof.size());
     std::string js = std::string("{\"algorithm\":\"") + algorithm + "\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
                      "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 136)) +
@@ -634,6 +656,123 @@ int s2c_get_circuits_info(char** json_out, size_t* json_len) {
                     "\"aes256_ctr\":{\"block_bytes\":16,\"cols\":34784,\"constraints\":49024,\"key_bytes\":32},"
                     "\"chacha20\":{\"block_bytes\":64,\"cols\":33280,\"constraints\":54784,\"key_bytes\":32}}",
                     json_out, json_len);
+}
+
+// ---------------------------------------------------------------------------------------------- verify / prove+verify
+// verify_chacha20_proof / verify_aes_ctr_proof (wasm_api.rs:609-648, :904-946) and prove_*_encrypt (wasm_api.rs:61-188,
+// :210-330, :343-463).  Verification is host work (verify.cu); these entry points need no CUDA context.
+static const size_t MAX_PROOF_B64_LEN = 8u * 1024 * 1024;  // wasm_api.rs:27
+
+static std::string verify_dispatch(bool aes, const uint8_t* proof, size_t len, const uint8_t* nonce, uint32_t counter, const uint8_t* pt,
+                                   size_t pt_len, const uint8_t* ct, size_t ct_len, std::string& algorithm) {
+    static const uint8_t none = 0;
+    if (!pt) pt = &none;
+    if (!ct) ct = &none;
+    if (!aes) {
+        algorithm = "chacha20";
+        return verify_chacha20(proof, len, nonce, counter, pt, pt_len, ct, ct_len);
+    }
+    int ks = 0;
+    std::string e = verify_aes_ctr(proof, len, nonce, counter, pt, pt_len, ct, ct_len, &ks);
+    algorithm = ks == 0 ? "aes128-ctr" : "aes256-ctr";
+    return e;
+}
+
+static int verify_json(bool aes, const char* proof_b64, size_t b64_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                       const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    if (b64_len > MAX_PROOF_B64_LEN) return ret_json(json_error("Proof payload too large"), json_out, json_len);
+    if (nonce_len != 12) return ret_json(json_error("Nonce must be 12 bytes, got " + std::to_string(nonce_len)), json_out, json_len);
+    std::vector<uint8_t> bytes;
+    std::string berr = host::base64_decode(proof_b64, b64_len, bytes);
+    if (!berr.empty()) return ret_json(json_error("Invalid base64: " + berr), json_out, json_len);
+    std::string algorithm, e;
+    try {
+        e = verify_dispatch(aes, bytes.data(), bytes.size(), nonce, counter, pt, pt_len, ct, ct_len, algorithm);
+    } catch (const VerifyFormatError& ex) {
+        return ret_json(json_error(std::string("Invalid proof format: ") + ex.what()), json_out, json_len);
+    } catch (const std::exception& ex) {
+        return ret_json("{\"error\":\"" + json_escape(ex.what()) + "\",\"valid\":false}", json_out, json_len);
+    }
+    if (e.empty()) return ret_json("{\"algorithm\":\"" + algorithm + "\",\"valid\":true}", json_out, json_len);
+    return ret_json("{\"error\":\"" + json_escape(e) + "\",\"valid\":false}", json_out, json_len);
+}
+
+int s2c_verify_chacha20_proof(const char* proof_b64, size_t proof_b64_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                              const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    return verify_json(false, proof_b64, proof_b64_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+
+int s2c_verify_aes_ctr_proof(const char* proof_b64, size_t proof_b64_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                             const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    return verify_json(true, proof_b64, proof_b64_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+
+// raw form: bincode bytes in, 0 = valid, 1 = rejected / malformed; *error_out (s2c_free) receives the reference's error rendering
+static int verify_raw(bool aes, const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                      size_t pt_len, const uint8_t* ct, size_t ct_len, char** error_out) {
+    std::string algorithm, e;
+    try {
+        e = verify_dispatch(aes, proof, len, nonce, counter, pt, pt_len, ct, ct_len, algorithm);
+    } catch (const VerifyFormatError& ex) {
+        e = std::string("Invalid proof format: ") + ex.what();
+    } catch (const std::exception& ex) {
+        e = ex.what();
+    }
+    if (error_out) {
+        *error_out = nullptr;
+        if (!e.empty()) ret_json(e, error_out, nullptr);
+    }
+    return e.empty() ? 0 : 1;
+}
+int s2c_verify_chacha20_raw(const uint8_t* proof, size_t proof_len, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                            size_t pt_len, const uint8_t* ct, size_t ct_len, char** error_out) {
+    return verify_raw(false, proof, proof_len, nonce, counter, pt, pt_len, ct, ct_len, error_out);
+}
+int s2c_verify_aes_ctr_raw(const uint8_t* proof, size_t proof_len, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
+                           size_t pt_len, const uint8_t* ct, size_t ct_len, char** error_out) {
+    return verify_raw(true, proof, proof_len, nonce, counter, pt, pt_len, ct, ct_len, error_out);
+}
+
+static int encrypt_finish(bool aes, const char* algorithm, const std::vector<uint8_t>& proof, size_t num_blocks, const uint8_t* nonce,
+                          uint32_t counter, const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out,
+                          size_t* json_len) {
+    std::string alg, e;
+    try {
+        e = verify_dispatch(aes, proof.data(), proof.size(), nonce, counter, pt, pt_len, ct, ct_len, alg);
+    } catch (const std::exception& ex) {
+        e = ex.what();
+    }
+    if (!e.empty()) return ret_json(json_error("Verification failed: " + e), json_out, json_len);
+    return ret_json(std::string("{\"algorithm\":\"") + algorithm + "\",\"blocks\":" + std::to_string(num_blocks) + ",\"success\":true}",
+                    json_out, json_len);
+}
+
+int s2c_prove_chacha20_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                               const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    std::vector<uint8_t> proof;
+    size_t num_blocks = 0;
+    const int rc = chacha_prove_checked(ctx, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks, json_out,
+                                        json_len);
+    if (rc != -1) return rc;
+    return encrypt_finish(false, "chacha20", proof, num_blocks, nonce, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+int s2c_prove_aes128_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                                 const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    std::vector<uint8_t> proof;
+    size_t num_blocks = 0;
+    const int rc = aes_prove_checked(ctx, 16, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks, json_out,
+                                     json_len);
+    if (rc != -1) return rc;
+    return encrypt_finish(true, "aes128-ctr", proof, num_blocks, nonce, counter, pt, pt_len, ct, ct_len, json_out, json_len);
+}
+int s2c_prove_aes256_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                                 const uint8_t* pt, size_t pt_len, const uint8_t* ct, size_t ct_len, char** json_out, size_t* json_len) {
+    std::vector<uint8_t> proof;
+    size_t num_blocks = 0;
+    const int rc = aes_prove_checked(ctx, 32, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks, json_out,
+                                     json_len);
+    if (rc != -1) return rc;
+    return encrypt_finish(true, "aes256-ctr", proof, num_blocks, nonce, counter, pt, pt_len, ct, ct_len, json_out, json_len);
 }
 
 void s2c_free(void* p) { free(p); }

@@ -280,4 +280,42 @@ inline std::string base64_encode(const uint8_t* d, size_t n) {
     return out;
 }
 
+// base64 (RFC 4648 alphabet, canonical padding required) with the error renderings of the reference's decoder
+// (base64 0.22 DecodeError Display, wasm_api.rs:628).  Returns "" on success.
+inline std::string base64_decode(const char* s, size_t n, std::vector<uint8_t>& out) {
+    static int8_t T[256];
+    static bool init = false;
+    if (!init) {
+        memset(T, -1, sizeof T);
+        const char* A = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        for (int i = 0; i < 64; i++) T[(uint8_t)A[i]] = (int8_t)i;
+        init = true;
+    }
+    out.clear();
+    out.reserve(n / 4 * 3 + 3);
+    size_t body = n;
+    while (body > 0 && s[body - 1] == '=' && n - body < 2) body--;
+    const size_t pad = n - body;
+    for (size_t i = 0; i < body; i++)
+        if (T[(uint8_t)s[i]] < 0) return "Invalid symbol " + std::to_string((unsigned)(uint8_t)s[i]) + ", offset " + std::to_string(i) + ".";
+    if (body % 4 == 1) return "Invalid input length: " + std::to_string(n);
+    if ((body + pad) % 4 != 0) return "Invalid padding";
+    size_t i = 0;
+    for (; i + 4 <= body; i += 4) {
+        uint32_t v = (T[(uint8_t)s[i]] << 18) | (T[(uint8_t)s[i + 1]] << 12) | (T[(uint8_t)s[i + 2]] << 6) | T[(uint8_t)s[i + 3]];
+        out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)v);
+    }
+    const size_t rem = body - i;
+    if (rem == 2) {
+        uint32_t v = (T[(uint8_t)s[i]] << 18) | (T[(uint8_t)s[i + 1]] << 12);
+        if (v & 0xffff) return "Invalid last symbol " + std::to_string((unsigned)(uint8_t)s[i + 1]) + ", offset " + std::to_string(i + 1) + ".";
+        out.push_back((uint8_t)(v >> 16));
+    } else if (rem == 3) {
+        uint32_t v = (T[(uint8_t)s[i]] << 18) | (T[(uint8_t)s[i + 1]] << 12) | (T[(uint8_t)s[i + 2]] << 6);
+        if (v & 0xff) return "Invalid last symbol " + std::to_string((unsigned)(uint8_t)s[i + 2]) + ", offset " + std::to_string(i + 2) + ".";
+        out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 8));
+    }
+    return "";
+}
+
 }  // namespace host

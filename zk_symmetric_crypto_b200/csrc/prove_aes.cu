@@ -67,13 +67,10 @@ std::vector<uint8_t> expand_key(const uint8_t* key, int key_len) {
 }
 
 // Column bookkeeping of the AIR (same traversal as the witness / constraint kernels): S-box (input, output) columns.
-struct Layout {
-    int n_cols = 0, n_constraints = 0;
-    std::vector<int> lk_in, lk_out;
-};
-Layout make_layout(int nr) {
+}  // namespace
+AesLayout aes_make_layout(int nr) {
     static const int SR[16] = {0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 1, 6, 11};
-    Layout L;
+    AesLayout L;
     int col = 16 + 16 * (nr + 1) + 32, k = 0;
     auto xor_byte = [&]() { col += 25; k += 35; return col - 1; };
     auto xtime = [&]() { col += 17; k += 26; return col - 1; };
@@ -105,6 +102,9 @@ Layout make_layout(int nr) {
     L.n_constraints = k + (int)L.lk_in.size() / 2;
     return L;
 }
+namespace {
+using Layout = AesLayout;
+Layout make_layout(int nr) { return aes_make_layout(nr); }
 
 struct PtQ {
     QM31 x, y;

@@ -88,6 +88,11 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
 
 }  // namespace
 
+// shared with the host verifier (verify.cu)
+QM31 chacha_constraints_at_mask(const std::vector<QM31>& mask, const std::vector<QM31>& alpha_powers_rev) {
+    return eval_constraints_at_mask(mask, alpha_powers_rev);
+}
+
 // ------------------------------------------------------------------------------------------------ streaming plan
 // Packed witness word indices (kernels_chacha.cu): 0..15 initial state | 80 quarter rounds x [sum,carry,xor]x4 |
 // 16 final adds x [sum,carry] | 16 plaintext | 16 ciphertext.  Sum words are "dependent" (combined from operand tiles,

@@ -53,3 +53,25 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 // AES-128/256-CTR (prove_aes.cu): key_len 16 or 32; len = multiple of 16 bytes.  Returns "" or the reference's error string.
 std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter,
                           const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof);
+
+// AES-CTR AIR column bookkeeping shared by the prover and the host verifier
+struct AesLayout {
+    int n_cols = 0, n_constraints = 0;
+    std::vector<int> lk_in, lk_out;  // S-box lookup (input, output) columns in relation order
+};
+AesLayout aes_make_layout(int n_rounds);
+
+// ChaCha20 stream AIR on QM31 mask values; alpha_powers_rev[k] = alpha^(K-1-k)
+m31::QM31 chacha_constraints_at_mask(const std::vector<m31::QM31>& mask, const std::vector<m31::QM31>& alpha_powers_rev);
+
+// ---- host verifier (verify.cu): air_stream.rs:343-421, air_ctr.rs:619-714 followed by upstream stwo::core::verifier::verify.
+// Both return "" when the proof verifies and otherwise the reference's `{:?}` rendering of its VerificationError.
+// A malformed byte string throws VerifyFormatError (the reference's "Invalid proof format: ..." branch).
+struct VerifyFormatError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                            size_t pt_len, const uint8_t* ciphertext, size_t ct_len);
+// *key_size_out: 0 = AES-128, 1 = AES-256 (read from the proof's statement before any check)
+std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out);

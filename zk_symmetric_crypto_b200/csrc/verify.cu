@@ -1,0 +1,693 @@
+// Host-side verifier for the ChaCha20 stream and AES-128/256-CTR proofs.
+//
+// Verification is a few thousand field operations and a few hundred Blake2s calls: it stays on the CPU (as SURVEY.md 8(f).2
+// asks) and shares the channel / field / layout code with the GPU prover.  Mirrors
+//   /root/reference/stwo/src/chacha/bitwise/air_stream.rs:284-421   (validate_pcs_config, verify_stream_with_public_inputs)
+//   /root/reference/stwo/src/aes/lookup/air_ctr.rs:619-714          (verify_aes_ctr_with_public_inputs)
+// followed by the upstream (stwo rev f117d487, un-vendored) core::verifier::verify, CommitmentSchemeVerifier::verify_values,
+// vcs_lifted MerkleVerifierLifted::verify, pcs::quotients::fri_answers and FriVerifier::{commit, decommit}, restated from the
+// prover side of this repo (which is pinned byte-for-byte against the reference).  Accept / reject decisions and error
+// renderings are checked against the reference's own verifier in tests/.
+#include <map>
+#include "prover.hpp"
+
+using namespace m31;
+using host::Channel;
+using host::Hash32;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ bincode reader
+struct Reader {
+    const uint8_t* p;
+    size_t len, pos = 0;
+    void need(size_t n) const {
+        if (n > len - pos) throw VerifyFormatError("io error: unexpected end of file");
+    }
+    uint8_t u8() { need(1); return p[pos++]; }
+    uint32_t u32() { need(4); uint32_t v = host::load_le32(p + pos); pos += 4; return v; }
+    uint64_t u64() { uint64_t lo = u32(); uint64_t hi = u32(); return lo | (hi << 32); }
+    // Vec length prefix; elem = serialised size of one element (guards allocations against forged lengths)
+    size_t vec_len(size_t elem) {
+        uint64_t n = u64();
+        // the reference's product build is wasm32: bincode rejects lengths beyond its usize before reading anything
+        if (n > 0xFFFFFFFFull)
+            throw VerifyFormatError("Invalid size " + std::to_string(n) + ": sizes must fit in a usize (0 to 4294967295)");
+        if (n > (len - pos) / (elem ? elem : 1)) throw VerifyFormatError("io error: unexpected end of file");
+        return (size_t)n;
+    }
+    Hash32 hash() { need(32); Hash32 h; memcpy(h.b, p + pos, 32); pos += 32; return h; }
+    // serde for M31 is a plain u32; values are reduced like M31::from on the way in would not be: keep them as sent and
+    // reject non-canonical words in the field checks below by comparing exactly
+    QM31 qm31() { QM31 q; for (int c = 0; c < 4; c++) q.v[c] = u32(); return q; }
+};
+
+struct FriLayerProof {
+    std::vector<QM31> witness;
+    std::vector<Hash32> decommitment;
+    Hash32 commitment;
+};
+
+struct StarkProofData {
+    PcsConfig cfg;
+    std::vector<Hash32> commitments;
+    std::vector<std::vector<std::vector<QM31>>> sampled;   // [tree][col][sample]
+    std::vector<std::vector<Hash32>> decommitments;         // [tree][witness hash]
+    std::vector<std::vector<std::vector<uint32_t>>> queried;  // [tree][col][query]
+    uint64_t pow_nonce = 0;
+    FriLayerProof first;
+    std::vector<FriLayerProof> inner;
+    std::vector<QM31> last_poly;
+    uint32_t last_log = 0;
+};
+
+FriLayerProof read_layer(Reader& r) {
+    FriLayerProof l;
+    size_t n = r.vec_len(16);
+    l.witness.resize(n);
+    for (auto& q : l.witness) q = r.qm31();
+    n = r.vec_len(32);
+    l.decommitment.resize(n);
+    for (auto& h : l.decommitment) h = r.hash();
+    l.commitment = r.hash();
+    return l;
+}
+
+StarkProofData read_stark(Reader& r) {
+    StarkProofData s;
+    s.cfg.pow_bits = r.u32();
+    s.cfg.log_blowup = r.u32();
+    s.cfg.log_last_layer_degree_bound = r.u32();
+    s.cfg.n_queries = r.u64();
+    s.cfg.fold_step = r.u32();
+    uint8_t tag = r.u8();
+    if (tag == 1) r.u32();
+    else if (tag != 0) throw VerifyFormatError("invalid tag encoding for Option");
+    size_t n = r.vec_len(32);
+    s.commitments.resize(n);
+    for (auto& h : s.commitments) h = r.hash();
+    n = r.vec_len(8);
+    s.sampled.resize(n);
+    for (auto& t : s.sampled) {
+        t.resize(r.vec_len(8));
+        for (auto& c : t) {
+            c.resize(r.vec_len(16));
+            for (auto& q : c) q = r.qm31();
+        }
+    }
+    n = r.vec_len(8);
+    s.decommitments.resize(n);
+    for (auto& t : s.decommitments) {
+        t.resize(r.vec_len(32));
+        for (auto& h : t) h = r.hash();
+    }
+    n = r.vec_len(8);
+    s.queried.resize(n);
+    for (auto& t : s.queried) {
+        t.resize(r.vec_len(8));
+        for (auto& c : t) {
+            c.resize(r.vec_len(4));
+            for (auto& v : c) v = r.u32();
+        }
+    }
+    s.pow_nonce = r.u64();
+    s.first = read_layer(r);
+    n = r.vec_len(80);
+    s.inner.reserve(n);
+    for (size_t i = 0; i < n; i++) s.inner.push_back(read_layer(r));
+    n = r.vec_len(16);
+    s.last_poly.resize(n);
+    for (auto& q : s.last_poly) q = r.qm31();
+    s.last_log = r.u32();
+    return s;
+}
+
+// air_stream.rs:284-322 (the same function is used for AES, air_ctr.rs:628)
+std::string validate_pcs_config(const PcsConfig& c) {
+    const PcsConfig min;
+    if (c.pow_bits < min.pow_bits)
+        return "InvalidStructure(\"Proof pow_bits (" + std::to_string(c.pow_bits) + ") below minimum (" + std::to_string(min.pow_bits) + ")\")";
+    if (c.log_blowup < min.log_blowup)
+        return "InvalidStructure(\"Proof log_blowup_factor (" + std::to_string(c.log_blowup) + ") below minimum (" +
+               std::to_string(min.log_blowup) + ")\")";
+    if (c.n_queries < min.n_queries)
+        return "InvalidStructure(\"Proof n_queries (" + std::to_string(c.n_queries) + ") below minimum (" + std::to_string(min.n_queries) +
+               ")\")";
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------ circle points over QM31
+struct PtQ {
+    QM31 x, y;
+};
+PtQ pt_add_m(const PtQ& p, host::Pt s) { return {qsub(qmul_m(p.x, s.x), qmul_m(p.y, s.y)), qadd(qmul_m(p.x, s.y), qmul_m(p.y, s.x))}; }
+PtQ pt_double(const PtQ& p) { return {qsub(qmul_m(qmul(p.x, p.x), 2), qone()), qmul_m(qmul(p.x, p.y), 2)}; }
+PtQ pt_repeated_double(PtQ p, int k) {
+    for (int i = 0; i < k; i++) p = pt_double(p);
+    return p;
+}
+std::array<uint32_t, 8> pt_key(const PtQ& p) { return {p.x.v[0], p.x.v[1], p.x.v[2], p.x.v[3], p.y.v[0], p.y.v[1], p.y.v[2], p.y.v[3]}; }
+
+QM31 vanishing_at(int trace_log, const PtQ& z) { return coset_vanishing_q(trace_log, host::CirclePointQ{z.x, z.y}); }
+
+QM31 from_coords(const QM31* c) {  // SecureField::from_partial_evals
+    const QM31 units[4] = {{{1, 0, 0, 0}}, {{0, 1, 0, 0}}, {{0, 0, 1, 0}}, {{0, 0, 0, 1}}};
+    QM31 r = qzero();
+    for (int k = 0; k < 4; k++) r = qadd(r, qmul(c[k], units[k]));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ AIR description
+struct ColumnSpec {
+    int log;        // trace log size (the committed evaluation has log + log_blowup)
+    int n_samples;  // 1: mask [0]; 2: mask [-1, 0]
+};
+struct AirSpec {
+    std::vector<std::vector<ColumnSpec>> trees;  // the trace trees (the composition tree is appended by the verifier)
+    int log_size = 0;                             // largest trace log size n; the composition polynomial has log n + 1
+};
+
+uint32_t lift_pos(uint32_t q, int from_log, int to_log) {  // vcs_lifted index map from the lifting domain to a smaller one
+    const int sh = from_log - to_log;
+    return sh ? (((q >> (sh + 1)) << 1) | (q & 1)) : q;
+}
+
+// ------------------------------------------------------------------------------------------------ lifted Merkle verifier
+// MerkleVerifierLifted::verify: leaf = Blake2s(values of all columns, smallest columns first), node = Blake2s(l || r);
+// witness hashes are consumed bottom-up in position order for every sibling that is not derivable (merkle_decommit's order).
+// Returns "" or the MerkleVerificationError variant name.
+std::string merkle_verify(const Hash32& root, const std::vector<int>& col_logs, int height,
+                          const std::vector<uint32_t>& positions /* sorted unique leaf positions */,
+                          const std::vector<std::vector<uint32_t>>& leaf_values /* [position][column in tree order] */,
+                          const std::vector<Hash32>& witness) {
+    std::vector<int> order(col_logs.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col_logs[a] < col_logs[b]; });
+    std::vector<std::pair<uint32_t, Hash32>> cur;
+    std::vector<uint8_t> buf(4 * col_logs.size());
+    for (size_t i = 0; i < positions.size(); i++) {
+        for (size_t j = 0; j < order.size(); j++) {
+            uint32_t v = leaf_values[i][order[j]];
+            for (int b = 0; b < 4; b++) buf[4 * j + b] = (uint8_t)(v >> (8 * b));
+        }
+        cur.push_back({positions[i], host::blake2s_bytes(buf.data(), buf.size())});
+    }
+    size_t w = 0;
+    for (int l = 0; l < height; l++) {
+        std::vector<std::pair<uint32_t, Hash32>> nxt;
+        for (size_t i = 0; i < cur.size();) {
+            const uint32_t p = cur[i].first;
+            Hash32 left, right;
+            if ((p & 1) == 0 && i + 1 < cur.size() && cur[i + 1].first == p + 1) {
+                left = cur[i].second;
+                right = cur[i + 1].second;
+                i += 2;
+            } else {
+                if (w >= witness.size()) return "WitnessTooShort";
+                if (p & 1) { left = witness[w++]; right = cur[i].second; }
+                else { left = cur[i].second; right = witness[w++]; }
+                i += 1;
+            }
+            uint8_t cat[64];
+            memcpy(cat, left.b, 32);
+            memcpy(cat + 32, right.b, 32);
+            nxt.push_back({p >> 1, host::blake2s_bytes(cat, 64)});
+        }
+        cur.swap(nxt);
+    }
+    if (w != witness.size()) return "WitnessTooLong";
+    if (cur.size() != 1 || memcmp(cur[0].second.b, root.b, 32) != 0) return "RootMismatch";
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------ the STARK verifier
+// stwo::core::verifier::verify after the AIR driver has committed the trace trees on `ch`.
+// composition(z, sampled, random_coeff) returns the expected composition value at z from the trace mask values.
+template <class CompositionFn>
+std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& sp, CompositionFn&& composition) {
+    const PcsConfig& cfg = sp.cfg;
+    const int n = air.log_size;
+    const size_t n_trees = air.trees.size() + 1;
+    if (cfg.log_blowup > 8 || cfg.n_queries > 4096 || cfg.log_last_layer_degree_bound > 16 || cfg.fold_step > 16 || cfg.fold_step == 0)
+        return "InvalidStructure(\"PCS configuration out of range\")";
+    const int blow = (int)cfg.log_blowup;
+    const int m = n + blow;  // lifting log: the largest committed column
+    if (sp.commitments.size() != n_trees) return "InvalidStructure(\"Unexpected number of commitments\")";
+
+    const QM31 random_coeff = ch.draw_secure_felt();
+    ch.mix_root(sp.commitments.back());
+    const host::CirclePointQ zq = host::get_random_point(ch);
+    const PtQ Z{zq.x, zq.y};
+
+    // ---- shape of the sampled values: the mask of every column, then 8 composition columns with one sample each
+    std::vector<std::vector<ColumnSpec>> trees = air.trees;
+    trees.push_back(std::vector<ColumnSpec>(8, ColumnSpec{n, 1}));
+    if (sp.sampled.size() != n_trees) return "InvalidStructure(\"Unexpected sampled_values structure\")";
+    for (size_t t = 0; t < n_trees; t++) {
+        if (sp.sampled[t].size() != trees[t].size()) return "InvalidStructure(\"Unexpected sampled_values structure\")";
+        for (size_t c = 0; c < trees[t].size(); c++)
+            if ((int)sp.sampled[t][c].size() != trees[t][c].n_samples) return "InvalidStructure(\"Unexpected sampled_values structure\")";
+    }
+
+    // ---- composition OODS check: left + pi^(n-1)(z.x) * right == sum of constraint quotients at z
+    {
+        QM31 lc[4], rc[4];
+        for (int k = 0; k < 4; k++) { lc[k] = sp.sampled.back()[k][0]; rc[k] = sp.sampled.back()[4 + k][0]; }
+        QM31 pix = Z.x;
+        for (int i = 0; i < n - 1; i++) pix = qsub(qmul_m(qmul(pix, pix), 2), qone());
+        const QM31 got = qadd(from_coords(lc), qmul(pix, from_coords(rc)));
+        const QM31 expect = composition(Z, sp.sampled, random_coeff);
+        if (!qeq(got, expect)) return "OodsNotMatching";
+    }
+
+    // ---- CommitmentSchemeVerifier::verify_values
+    {
+        std::vector<QM31> flat;
+        for (auto& t : sp.sampled)
+            for (auto& c : t)
+                for (auto& q : c) flat.push_back(q);
+        ch.mix_felts(flat.data(), flat.size());
+    }
+    const QM31 fri_coeff = ch.draw_secure_felt();
+
+    // FriVerifier::commit
+    ch.mix_root(sp.first.commitment);
+    std::vector<QM31> fold_alpha;
+    fold_alpha.push_back(ch.draw_secure_felt());
+    int layer_bound = m - blow - 1;  // CirclePolyDegreeBound(m - blow).fold_to_line()
+    for (size_t i = 0; i < sp.inner.size(); i++) {
+        ch.mix_root(sp.inner[i].commitment);
+        fold_alpha.push_back(ch.draw_secure_felt());
+        if (layer_bound < (int)cfg.fold_step) return "Fri(InvalidNumFriLayers)";
+        layer_bound -= (int)cfg.fold_step;
+    }
+    if (layer_bound != (int)cfg.log_last_layer_degree_bound) return "Fri(InvalidNumFriLayers)";
+    if (cfg.fold_step != 1) return "InvalidStructure(\"unsupported FRI fold_step\")";
+    if (sp.last_poly.size() > ((size_t)1 << cfg.log_last_layer_degree_bound)) return "Fri(LastLayerDegreeInvalid)";
+    if (cfg.log_last_layer_degree_bound != 0) return "InvalidStructure(\"unsupported log_last_layer_degree_bound\")";
+    ch.mix_felts(sp.last_poly.data(), sp.last_poly.size());
+
+    if (!ch.verify_pow_nonce(cfg.pow_bits, sp.pow_nonce)) return "ProofOfWork";
+    ch.mix_u64(sp.pow_nonce);
+    const std::vector<uint32_t> queries = host::queries_generate(ch, m, (int)cfg.n_queries);
+    const size_t nq = queries.size();
+
+    // ---- Merkle decommitments of the trace and composition trees
+    if (sp.decommitments.size() != n_trees || sp.queried.size() != n_trees) return "InvalidStructure(\"Unexpected proof structure\")";
+    for (size_t t = 0; t < n_trees; t++) {
+        const auto& cols = trees[t];
+        if (sp.queried[t].size() > cols.size()) return "Merkle(TooManyQueriedValues)";
+        if (sp.queried[t].size() < cols.size()) return "Merkle(TooFewQueriedValues)";
+        for (auto& c : sp.queried[t]) {
+            if (c.size() > nq) return "Merkle(TooManyQueriedValues)";
+            if (c.size() < nq) return "Merkle(TooFewQueriedValues)";
+        }
+        if (cols.empty()) {
+            const Hash32 e = host::blake2s_bytes(nullptr, 0);
+            if (!sp.decommitments[t].empty()) return "Merkle(WitnessTooLong)";
+            if (memcmp(e.b, sp.commitments[t].b, 32) != 0) return "Merkle(RootMismatch)";
+            continue;
+        }
+        int height = 0;
+        std::vector<int> logs;
+        for (auto& c : cols) { logs.push_back(c.log + blow); height = std::max(height, c.log + blow); }
+        // leaf positions on this tree and, per leaf, the values of all columns (a column of a smaller size repeats its value
+        // on all leaves that lift to the same index; the queried values must agree where queries collide)
+        std::map<uint32_t, std::vector<uint32_t>> leaves;
+        for (size_t qi = 0; qi < nq; qi++) {
+            const uint32_t pos = lift_pos(queries[qi], m, height);
+            std::vector<uint32_t> vals(cols.size());
+            for (size_t c = 0; c < cols.size(); c++) vals[c] = sp.queried[t][c][qi];
+            auto it = leaves.find(pos);
+            if (it == leaves.end()) leaves.emplace(pos, std::move(vals));
+            else if (it->second != vals) return "Merkle(RootMismatch)";
+        }
+        std::vector<uint32_t> positions;
+        std::vector<std::vector<uint32_t>> lv;
+        for (auto& kv : leaves) { positions.push_back(kv.first); lv.push_back(kv.second); }
+        const std::string e = merkle_verify(sp.commitments[t], logs, height, positions, lv, sp.decommitments[t]);
+        if (!e.empty()) return "Merkle(" + e + ")";
+    }
+
+    // ---- fri_answers: quotient value at every query from the queried values and the samples.  Every (column, sample) pair has
+    //      its own power of fri_coeff (alpha^0 first, tree / column / sample order); a column with two samples first gets a
+    //      periodicity copy of its offset-0 sample at z + h_k (k = its lift); samples are grouped by point, batches summed.
+    struct Entry { size_t tree, col; QM31 val, alpha; };
+    struct Batch { PtQ pt; std::vector<Entry> e; };
+    std::map<std::array<uint32_t, 8>, Batch> batches;
+    {
+        const PtQ Zp = pt_add_m(Z, host::index_to_point((0x80000000u - (1u << (31 - n))) & 0x7fffffffu));
+        QM31 alpha = qone();
+        for (size_t t = 0; t < n_trees; t++)
+            for (size_t c = 0; c < trees[t].size(); c++) {
+                std::vector<std::pair<PtQ, QM31>> ent;
+                if (trees[t][c].n_samples == 2) {
+                    const int k = n - trees[t][c].log;
+                    PtQ zp = Z;
+                    if (k > 0) zp = pt_add_m(Z, host::index_to_point(1u << (31 - k)));
+                    ent.push_back({zp, sp.sampled[t][c][1]});
+                    ent.push_back({Zp, sp.sampled[t][c][0]});
+                    ent.push_back({Z, sp.sampled[t][c][1]});
+                } else {
+                    ent.push_back({Z, sp.sampled[t][c][0]});
+                }
+                for (auto& pv : ent) {
+                    Batch& b = batches[pt_key(pv.first)];
+                    b.pt = pv.first;
+                    b.e.push_back({t, c, pv.second, alpha});
+                    alpha = qmul(alpha, fri_coeff);
+                }
+            }
+    }
+    std::vector<QM31> answers(nq);
+    for (size_t qi = 0; qi < nq; qi++) {
+        const host::Pt dp = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(queries[qi], m)));
+        QM31 total = qzero();
+        for (auto& kv : batches) {
+            const Batch& b = kv.second;
+            const QM31 py = b.pt.y, px = b.pt.x;
+            const QM31 c = qsub(qconj(py), py);
+            QM31 num = qzero();
+            for (auto& e : b.e) {
+                const QM31 a = qsub(qconj(e.val), e.val);
+                const QM31 bb = qsub(qmul(e.val, c), qmul(a, py));
+                // alpha * (c f - a y - b)
+                QM31 term = qsub(qsub(qmul_m(c, sp.queried[e.tree][e.col][qi]), qmul_m(a, dp.y)), bb);
+                num = qadd(num, qmul(e.alpha, term));
+            }
+            const CM31 prx{px.v[0], px.v[1]}, pix{px.v[2], px.v[3]}, pry{py.v[0], py.v[1]}, piy{py.v[2], py.v[3]};
+            const CM31 d = csub(cmul(csub(prx, CM31{dp.x, 0}), piy), cmul(csub(pry, CM31{dp.y, 0}), pix));
+            total = qadd(total, qmul_c(num, cinv(d)));
+        }
+        answers[qi] = total;
+    }
+
+    // ---- FriVerifier::decommit
+    auto fri_layer = [&](const FriLayerProof& lp, int log, const std::vector<uint32_t>& pos, const std::vector<QM31>& vals,
+                         std::vector<uint32_t>& pair_pos, std::vector<QM31>& pair_vals) -> std::string {
+        // returns "evals" / Merkle error / ""; fills the values at both positions of every queried pair
+        size_t w = 0;
+        for (size_t i = 0; i < pos.size();) {
+            const uint32_t start = (pos[i] >> 1) << 1;
+            QM31 v[2];
+            bool have[2] = {false, false};
+            while (i < pos.size() && ((pos[i] >> 1) << 1) == start) {
+                v[pos[i] & 1] = vals[i];
+                have[pos[i] & 1] = true;
+                i++;
+            }
+            for (int s = 0; s < 2; s++) {
+                if (!have[s]) {
+                    if (w >= lp.witness.size()) return "evals";
+                    v[s] = lp.witness[w++];
+                }
+                pair_pos.push_back(start + s);
+                pair_vals.push_back(v[s]);
+            }
+        }
+        if (w != lp.witness.size()) return "evals";
+        std::vector<std::vector<uint32_t>> lv;
+        for (auto& q : pair_vals) lv.push_back({q.v[0], q.v[1], q.v[2], q.v[3]});
+        return merkle_verify(lp.commitment, std::vector<int>(4, log), log, pair_pos, lv, lp.decommitment);
+    };
+    std::vector<uint32_t> pos = queries;
+    std::vector<QM31> vals = answers;
+    {
+        std::vector<uint32_t> pp;
+        std::vector<QM31> pv;
+        const std::string e = fri_layer(sp.first, m, pos, vals, pp, pv);
+        if (e == "evals") return "Fri(FirstLayerEvaluationsInvalid)";
+        if (!e.empty()) return "Fri(FirstLayerCommitmentInvalid { error: " + e + " })";
+        // fold_circle_into_line
+        pos.clear();
+        vals.clear();
+        for (size_t i = 0; i < pp.size(); i += 2) {
+            const host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(pp[i], m)));
+            const QM31 f0 = qadd(pv[i], pv[i + 1]), f1 = qmul_m(qsub(pv[i], pv[i + 1]), inv(p.y));
+            pos.push_back(pp[i] >> 1);
+            vals.push_back(qadd(f0, qmul(fold_alpha[0], f1)));
+        }
+    }
+    int L = m - 1;
+    for (size_t li = 0; li < sp.inner.size(); li++, L--) {
+        std::vector<uint32_t> pp;
+        std::vector<QM31> pv;
+        const std::string e = fri_layer(sp.inner[li], L, pos, vals, pp, pv);
+        if (e == "evals") return "Fri(InnerLayerEvaluationsInvalid { inner_layer: " + std::to_string(li) + " })";
+        if (!e.empty()) return "Fri(InnerLayerCommitmentInvalid { inner_layer: " + std::to_string(li) + ", error: " + e + " })";
+        const host::Coset cs = host::Coset::half_odds(L);
+        pos.clear();
+        vals.clear();
+        for (size_t i = 0; i < pp.size(); i += 2) {
+            const uint32_t x = cs.at(host::bit_reverse(pp[i], L)).x;
+            const QM31 f0 = qadd(pv[i], pv[i + 1]), f1 = qmul_m(qsub(pv[i], pv[i + 1]), inv(x));
+            pos.push_back(pp[i] >> 1);
+            vals.push_back(qadd(f0, qmul(fold_alpha[li + 1], f1)));
+        }
+    }
+    // last layer: a constant polynomial (log_last_layer_degree_bound = 0)
+    const QM31 last = sp.last_poly.empty() ? qzero() : sp.last_poly[0];
+    for (auto& v : vals)
+        if (!qeq(v, last)) return "Fri(LastLayerEvaluationsInvalid)";
+    return "";
+}
+
+bool canonical(const StarkProofData& sp) {
+    auto okq = [](const QM31& q) { return q.v[0] < P && q.v[1] < P && q.v[2] < P && q.v[3] < P; };
+    for (auto& t : sp.sampled) for (auto& c : t) for (auto& q : c) if (!okq(q)) return false;
+    for (auto& t : sp.queried) for (auto& c : t) for (auto v : c) if (v >= P) return false;
+    for (auto& q : sp.first.witness) if (!okq(q)) return false;
+    for (auto& l : sp.inner) for (auto& q : l.witness) if (!okq(q)) return false;
+    for (auto& q : sp.last_poly) if (!okq(q)) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ AES-CTR constraints at a point
+// Same traversal as kernels_aes.cu's constraints_kernel, on QM31 mask values, accumulating Horner-style
+// (acc = acc * random_coeff + constraint / vanishing) like the upstream PointEvaluator.
+struct AesPointEval {
+    const std::vector<std::vector<QM31>>& v;  // main-trace samples [col][0]
+    QM31 rc, den_inv, acc;
+    int col = 0;
+    const QM31& ld(int c) const { return v[c][0]; }
+    void emit(const QM31& c) { acc = qadd(qmul(acc, rc), qmul(c, den_inv)); }
+    QM31 bits8(QM31 (&b)[8]) {
+        QM31 s = qzero();
+        for (int i = 0; i < 8; i++) {
+            b[i] = ld(col++);
+            emit(qmul(b[i], qsub(qone(), b[i])));
+            s = qadd(s, qmul_m(b[i], 1u << i));
+        }
+        return s;
+    }
+    int xor_byte(int a, int b) {
+        QM31 ab[8], bb[8], cb[8];
+        const QM31 sa = bits8(ab), sb = bits8(bb), sc = bits8(cb);
+        emit(qsub(ld(a), sa));
+        emit(qsub(ld(b), sb));
+        for (int i = 0; i < 8; i++) {
+            const QM31 mm = qmul(ab[i], bb[i]);
+            emit(qadd(qsub(qsub(cb[i], ab[i]), bb[i]), qadd(mm, mm)));
+        }
+        const int r = col++;
+        emit(qsub(ld(r), sc));
+        return r;
+    }
+    int xtime(int a) {
+        QM31 ab[8], rb[8];
+        const QM31 sa = bits8(ab);
+        emit(qsub(ld(a), sa));
+        const QM31 sr = bits8(rb);
+        const QM31 h = ab[7];
+        auto x2 = [&](int i, int j) {
+            const QM31 mm = qmul(ab[j], h);
+            return qadd(qsub(qsub(rb[i], ab[j]), h), qadd(mm, mm));
+        };
+        emit(qsub(rb[0], h));
+        emit(x2(1, 0));
+        emit(qsub(rb[2], ab[1]));
+        emit(x2(3, 2));
+        emit(x2(4, 3));
+        emit(qsub(rb[5], ab[4]));
+        emit(qsub(rb[6], ab[5]));
+        emit(qsub(rb[7], ab[6]));
+        const int r = col++;
+        emit(qsub(ld(r), sr));
+        return r;
+    }
+    int mul3(int a) { return xor_byte(xtime(a), a); }
+};
+
+QM31 lookup_combine(const QM31& z, const QM31& alpha, const QM31& in, const QM31& out) { return qsub(qadd(in, qmul(alpha, out)), z); }
+
+}  // namespace
+
+// ================================================================================================ ChaCha20
+std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                            size_t pt_len, const uint8_t* ciphertext, size_t ct_len) {
+    constexpr int N_COLS = 33280, N_CONSTRAINTS = 54784;
+    Reader r{proof, len};
+    const uint32_t log_size = r.u32();
+    uint8_t p_nonce[12];
+    for (int i = 0; i < 12; i++) p_nonce[i] = r.u8();
+    const uint32_t p_counter = r.u32();
+    const Hash32 pth = r.hash(), cth = r.hash();
+    const StarkProofData sp = read_stark(r);
+
+    std::string e = validate_pcs_config(sp.cfg);
+    if (!e.empty()) return e;
+    {   // ChaChaPublicInputs::verify (air_stream.rs:56-64)
+        const Hash32 h1 = host::blake2s_bytes(plaintext, pt_len), h2 = host::blake2s_bytes(ciphertext, ct_len);
+        if (memcmp(p_nonce, nonce, 12) != 0 || p_counter != counter || memcmp(h1.b, pth.b, 32) != 0 || memcmp(h2.b, cth.b, 32) != 0)
+            return "OodsNotMatching";
+    }
+    if (sp.commitments.size() < 2) return "OodsNotMatching";
+    if (log_size < 1 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
+    if (!canonical(sp)) return "InvalidStructure(\"non-canonical field element\")";
+
+    Channel ch;
+    ch.mix_root(sp.commitments[0]);
+    ch.mix_u64(log_size);
+    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(p_nonce + 4 * i));
+    ch.mix_u64(p_counter);
+    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(pth.b + 4 * i));
+    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(cth.b + 4 * i));
+    ch.mix_root(sp.commitments[1]);
+
+    AirSpec air;
+    air.log_size = (int)log_size;
+    air.trees.resize(2);
+    air.trees[1].assign(N_COLS, ColumnSpec{(int)log_size, 1});
+    return verify_stark(air, ch, sp, [&](const PtQ& z, const std::vector<std::vector<std::vector<QM31>>>& sampled, const QM31& rc) {
+        std::vector<QM31> apr(N_CONSTRAINTS);
+        QM31 cur = qone();
+        for (int k = 0; k < N_CONSTRAINTS; k++) { apr[N_CONSTRAINTS - 1 - k] = cur; cur = qmul(cur, rc); }
+        std::vector<QM31> mask(N_COLS);
+        for (int j = 0; j < N_COLS; j++) mask[j] = sampled[1][j][0];
+        return qmul(chacha_constraints_at_mask(mask, apr), qinv(vanishing_at((int)log_size, z)));
+    });
+}
+
+// ================================================================================================ AES-CTR
+std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out) {
+    Reader r{proof, len};
+    const uint32_t log_size = r.u32();
+    const uint32_t key_size = r.u32();
+    if (key_size > 1) throw VerifyFormatError("invalid value: integer `" + std::to_string(key_size) + "`, expected variant index 0 <= i < 2");
+    if (key_size_out) *key_size_out = (int)key_size;
+    uint8_t p_nonce[12];
+    for (int i = 0; i < 12; i++) p_nonce[i] = r.u8();
+    const uint32_t p_counter = r.u32();
+    const Hash32 pth = r.hash(), cth = r.hash();
+    const QM31 csum = r.qm31(), tsum = r.qm31();
+    const uint64_t n_ctr_inter = r.u64(), n_sbox_inter = r.u64();
+    const StarkProofData sp = read_stark(r);
+
+    std::string e = validate_pcs_config(sp.cfg);
+    if (!e.empty()) return e;
+    {   // AESCtrPublicInputs::verify (air_ctr.rs:66-76)
+        const Hash32 h1 = host::blake2s_bytes(plaintext, pt_len), h2 = host::blake2s_bytes(ciphertext, ct_len);
+        if (memcmp(p_nonce, nonce, 12) != 0 || p_counter != counter || memcmp(h1.b, pth.b, 32) != 0 || memcmp(h2.b, cth.b, 32) != 0)
+            return "OodsNotMatching";
+    }
+    if (n_ctr_inter > (1u << 16) || n_sbox_inter > (1u << 16)) return "OodsNotMatching";
+    if (sp.commitments.size() < 3) return "OodsNotMatching";
+    if (log_size < 8 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
+    for (int c = 0; c < 4; c++)
+        if (csum.v[c] >= P || tsum.v[c] >= P) return "InvalidStructure(\"non-canonical field element\")";
+    if (!canonical(sp)) return "InvalidStructure(\"non-canonical field element\")";
+
+    const int n = (int)log_size, nr = key_size == 0 ? 10 : 14;
+    static const AesLayout L128 = aes_make_layout(10), L256 = aes_make_layout(14);
+    const AesLayout& lay = nr == 10 ? L128 : L256;
+    const int C = lay.n_cols, NL = (int)lay.lk_in.size(), NI = 4 * (NL / 2);
+    // the AIR fixes the interaction widths; a statement that claims others describes a different circuit
+    if (n_ctr_inter != (uint64_t)NI || n_sbox_inter != 4) return "InvalidStructure(\"Unexpected sampled_values structure\")";
+
+    Channel ch;
+    ch.mix_root(sp.commitments[0]);
+    ch.mix_u64(log_size);
+    ch.mix_u64(key_size);
+    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(p_nonce + 4 * i));
+    ch.mix_u64(p_counter);
+    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(pth.b + 4 * i));
+    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(cth.b + 4 * i));
+    ch.mix_root(sp.commitments[1]);
+    uint32_t zf[8];
+    ch.draw_base_felts(zf);
+    const QM31 lz{{zf[0], zf[1], zf[2], zf[3]}}, lalpha{{zf[4], zf[5], zf[6], zf[7]}};
+    {
+        QM31 sums[2] = {csum, tsum};
+        ch.mix_felts(sums, 2);
+    }
+    ch.mix_root(sp.commitments[2]);
+    if (!qeq(qadd(csum, tsum), qzero())) return "OodsNotMatching";
+
+    AirSpec air;
+    air.log_size = n;
+    air.trees.resize(3);
+    air.trees[0].assign(2, ColumnSpec{8, 1});
+    air.trees[1].assign(C, ColumnSpec{n, 1});
+    air.trees[1].push_back(ColumnSpec{8, 1});
+    air.trees[2].assign(NI - 4, ColumnSpec{n, 1});
+    for (int i = 0; i < 4; i++) air.trees[2].push_back(ColumnSpec{n, 2});
+    for (int i = 0; i < 4; i++) air.trees[2].push_back(ColumnSpec{8, 2});
+
+    return verify_stark(air, ch, sp, [&](const PtQ& z, const std::vector<std::vector<std::vector<QM31>>>& sampled, const QM31& rc) {
+        auto div_n = [&](const QM31& s, int lg) { return qmul_m(s, inv((uint32_t)(((uint64_t)1 << lg) % P))); };
+        AesPointEval ev{sampled[1], rc, qinv(vanishing_at(n, z)), qzero()};
+        int s[16], t[16];
+        static const int SR[16] = {0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 1, 6, 11};
+        const int rk0 = 16, pt0 = 16 + 16 * (nr + 1), ct0 = pt0 + 16;
+        ev.col = ct0 + 16;
+        for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(i, rk0 + i);
+        for (int rnd = 1; rnd <= nr; rnd++) {
+            for (int i = 0; i < 16; i++) s[i] = ev.col++;
+            for (int i = 0; i < 16; i++) t[i] = s[SR[i]];
+            if (rnd < nr) {
+                for (int c = 0; c < 4; c++) {
+                    const int s0 = t[4 * c], s1 = t[4 * c + 1], s2 = t[4 * c + 2], s3 = t[4 * c + 3];
+                    int t0, t1, t2, t3;
+                    t0 = ev.xtime(s0); t1 = ev.mul3(s1); t2 = ev.xor_byte(t0, t1); t3 = ev.xor_byte(t2, s2); s[4 * c] = ev.xor_byte(t3, s3);
+                    t0 = ev.xtime(s1); t1 = ev.mul3(s2); t2 = ev.xor_byte(s0, t0); t3 = ev.xor_byte(t2, t1); s[4 * c + 1] = ev.xor_byte(t3, s3);
+                    t0 = ev.xtime(s2); t1 = ev.mul3(s3); t2 = ev.xor_byte(s0, s1); t3 = ev.xor_byte(t2, t0); s[4 * c + 2] = ev.xor_byte(t3, t1);
+                    t0 = ev.mul3(s0); t1 = ev.xtime(s3); t2 = ev.xor_byte(t0, s1); t3 = ev.xor_byte(t2, s2); s[4 * c + 3] = ev.xor_byte(t3, t1);
+                }
+            } else {
+                for (int i = 0; i < 16; i++) s[i] = t[i];
+            }
+            for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(s[i], rk0 + 16 * rnd + i);
+        }
+        for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(s[i], pt0 + i);
+        for (int i = 0; i < 16; i++) ev.emit(qsub(ev.ld(s[i]), ev.ld(ct0 + i)));
+        // finalize_logup_in_pairs
+        const auto& inter = sampled[2];
+        QM31 prev_col = qzero();
+        const int nb = NL / 2;
+        for (int k = 0; k < nb; k++) {
+            const QM31 p0 = lookup_combine(lz, lalpha, ev.ld(lay.lk_in[2 * k]), ev.ld(lay.lk_out[2 * k]));
+            const QM31 p1 = lookup_combine(lz, lalpha, ev.ld(lay.lk_in[2 * k + 1]), ev.ld(lay.lk_out[2 * k + 1]));
+            QM31 cc[4], pc[4];
+            const int si = (k == nb - 1) ? 1 : 0;  // mask [-1, 0] on the last column: sample 0 = previous row
+            for (int c = 0; c < 4; c++) { cc[c] = inter[4 * k + c][si]; pc[c] = inter[4 * k + c][0]; }
+            const QM31 cur = from_coords(cc);
+            QM31 diff = qsub(cur, prev_col);
+            if (k == nb - 1) diff = qadd(qsub(diff, from_coords(pc)), div_n(csum, n));
+            prev_col = cur;
+            ev.emit(qsub(qmul(diff, qmul(p0, p1)), qadd(p0, p1)));
+        }
+        // S-box table component on its own (log 8) domain: the lifted columns were sampled at the doubled point
+        {
+            const PtQ z8 = pt_repeated_double(z, n - 8);
+            const QM31 den8 = qinv(vanishing_at(8, z8));
+            const QM31 p = lookup_combine(lz, lalpha, sampled[0][0][0], sampled[0][1][0]);
+            QM31 cc[4], pc[4];
+            for (int c = 0; c < 4; c++) { cc[c] = inter[NI + c][1]; pc[c] = inter[NI + c][0]; }
+            const QM31 diff = qadd(qsub(from_coords(cc), from_coords(pc)), div_n(tsum, 8));
+            const QM31 G = qadd(qmul(diff, p), sampled[1][C][0]);  // numerator -mult moved to the left-hand side
+            ev.acc = qadd(qmul(ev.acc, rc), qmul(G, den8));
+        }
+        return ev.acc;
+    });
+}
