@@ -204,7 +204,8 @@ def test_chacha_commit_constraints_pipeline(backend, nb, seed):
     want = sc.eval_at_point(coef[:ncheck], z[0], z[1])
     assert np.array_equal(got, want)
     rc = sc.QM31(5, 6, 7, 8)
-    batches = [((z[0], z[1]), [(j, sc.QM31(*[int(x) for x in want[j]])) for j in range(ncheck)])]
+    pw = op.secure_powers(rc, ncheck)  # every (column, sample) pair has its own power of the random coefficient, alpha^0 first
+    batches = [((z[0], z[1]), [(j, sc.QM31(*[int(x) for x in want[j]]), sc.QM31(*[int(x) for x in pw[j]])) for j in range(ncheck)])]
     quot = op.fri_quotients([lde[j] for j in range(ncheck)], batches, rc, log + 1)
     d_q = be.malloc(4 * m * 4)
     be._ck(be.L.cb_accumulate_quotients(be.ctx, d_l, ctypes.c_size_t(m), ncheck, log + 1, hp(u32(want)), pt8, q4(rc), d_q, ctypes.c_size_t(m)))
