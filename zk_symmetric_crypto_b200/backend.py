@@ -32,7 +32,9 @@ class BackendError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libs2c_b200.so")
+    """S2C_B200_LIB overrides the in-tree library (used to compare kernel build variants; same switch as the koffi stub in
+    INTEGRATION.md)."""
+    return os.environ.get("S2C_B200_LIB") or os.path.join(_HERE, "libs2c_b200.so")
 
 
 def lib():

@@ -486,7 +486,11 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
     const uint32_t* __restrict__ in = scratch + ((size_t)blockIdx.y << log_n) + q0 + q;
     uint32_t* __restrict__ out = jobs.out[job];
     const int lr = jobs.shard_log;
+    // rq < 2^12 <= shard rows: the shard / column part of a store offset is uniform over the block (kept off the per-thread
+    // integer pipe), only rq is per thread
     const size_t rq = (size_t)q0 + q;
+    const bool sharded = lr != m;  // unsharded tiles ([cols][2^m]) keep the compile-time store offsets
+    uint32_t* __restrict__ outu = out + ((size_t)col << m) + rq;
     uint32_t twr[1 << RA], v[1 << RA];
     if (RB == 0) {
         load_tw<RA>(twr, tw.IX, tw.IY, log_n, K1, 0, 0);
@@ -500,8 +504,13 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
             for (int k = 0; k < J; k++) u[k] = v[k];
             load_tw<RA>(twr, tw.X, tw.Y, m, K1, (uint32_t)h << JB, 0);
             fwd_block<RA>(u, twr, jobs.one, jobs.mone);
+            if (!sharded) {
 #pragma unroll
-            for (int k = 0; k < J; k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)k << K1) + rq)] = u[k];
+                for (int k = 0; k < J; k++) outu[((size_t)h << log_n) + ((size_t)k << K1)] = u[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < J; k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)k << K1)) + rq] = u[k];
+            }
         }
         return;
     }
@@ -548,8 +557,14 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
 #pragma unroll
         for (int k = 0; k < (1 << RA); k++) v[k] = sh[((j0 + k) << 5) | q];
         fwd_block<RA>(v, twr, jobs.one, jobs.mone);
+        if (!sharded) {  // immediate store offsets from one base pointer
+            uint32_t* __restrict__ o = outu + ((size_t)h << log_n) + ((size_t)j0 << K1);
 #pragma unroll
-        for (int k = 0; k < (1 << RA); k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)(j0 + k) << K1) + rq)] = v[k];
+            for (int k = 0; k < (1 << RA); k++) o[(size_t)k << K1] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < (1 << RA); k++) out[soff(lr, cols_per_job, col, ((size_t)h << log_n) + ((size_t)(j0 + k) << K1)) + rq] = v[k];
+        }
     }
 }
 

@@ -351,7 +351,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     static const int peak_trans_lag[3] = {plan_peak_transient(plan, 0), 0, plan_peak_transient(plan, 2)};
     const int peak_trans = peak_trans_lag[lag];
     cudaStream_t sf = overlap ? ctx->stream2 : st;
-    const size_t tile_words = 32 * Mr;
+    // placement knobs (KiB) for measuring how the power-of-two strides of the transform passes interact with the DRAM
+    // address map: extra pitch between tile slots, offset of the FFT scratch behind the slots
+    static const size_t tile_pad_words = getenv("S2C_TILE_PAD_KB") ? (size_t)atol(getenv("S2C_TILE_PAD_KB")) * 256 : 0;
+    static const size_t scratch_off_words = getenv("S2C_SCRATCH_OFF_KB") ? (size_t)atol(getenv("S2C_SCRATCH_OFF_KB")) * 256 : 0;
+    const size_t tile_words = 32 * Mr + tile_pad_words;
     // sharded mode: whole transformed tiles ([G][32][Mr]) wait here for the all-to-all; at most ceil(16/G) jobs per rank and group
     const int n_stage = G > 1 ? (16 + G - 1) / G : 0;
     const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, G > 1 ? n_stage : MAX_FFT_JOBS, n);
@@ -378,7 +382,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         n_cache = comm_min_int(cm, n_cache, st);  // every rank must take the same caching decisions
     }
     // tile slots + FFT scratch live in the context's persistent arena
-    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_words + stage_words;
+    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
     uint32_t* arena_p;
     if (ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30))
         arena_p = (uint32_t*)ctx->arena;
@@ -386,7 +390,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         ctx->release_arena();
         arena_p = (uint32_t*)ctx->ensure_arena(arena_words * 4);
     }
-    uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words;
+    uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words;
     uint32_t* stage_p = scratch_p + scratch_words;
     Tiles tiles;
     tiles.init(n_cache, peak_trans, tile_words, arena_p);
@@ -431,10 +435,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     if (owner == R) {
                         const uint32_t* stg = stage_p + (size_t)(k++) * 32 * M;
                         for (int r = 0; r < G; r++)
-                            if (r != R) comm_send_u32(cm, stg + (size_t)r * tile_words, tile_words, r, st);
-                        CB_CUDA(cudaMemcpyAsync(slot, stg + (size_t)R * tile_words, tile_words * 4, cudaMemcpyDeviceToDevice, st));
+                            if (r != R) comm_send_u32(cm, stg + (size_t)r * (32 * Mr), 32 * Mr, r, st);
+                        CB_CUDA(cudaMemcpyAsync(slot, stg + (size_t)R * (32 * Mr), (size_t)32 * Mr * 4, cudaMemcpyDeviceToDevice, st));
                     } else {
-                        comm_recv_u32(cm, slot, tile_words, owner, st);
+                        comm_recv_u32(cm, slot, 32 * Mr, owner, st);
                     }
                 }
                 comm_group_end();
