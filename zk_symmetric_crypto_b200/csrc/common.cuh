@@ -133,9 +133,12 @@ cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs
                                      const uint32_t* apr_hi, uint32_t* acc, int first);
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi);
 cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0 = 0);
+cudaError_t launch_gather_cached(cudaStream_t st, const uint32_t* arena, size_t tile_words, size_t M, const int* slot_dev, int n_words,
+                                 const uint32_t rows[4], int nq, uint32_t* out);
 cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
-                              uint32_t* out);
-cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g);
+                              uint32_t* out, const int* words_dev = nullptr);
+cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g,
+                               const int* words_dev = nullptr);
 cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t stride, int ncols, size_t N, const uint32_t* coefs,
                                uint32_t* g, int accumulate);
 cudaError_t launch_basis4(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const uint32_t init[4],

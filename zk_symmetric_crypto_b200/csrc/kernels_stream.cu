@@ -164,10 +164,13 @@ __global__ void scale_rows_kernel(uint32_t* __restrict__ acc, size_t M, int trac
 // out[(word*32 + bit)*4 + c] = scale * sum_r bit(W[word][r]) * wt[c][r]     (one block per witness word)
 // (masked adds with a one-instruction reduction each; a 64-bit IMAD.WIDE accumulation was measured 40 % slower here:
 // 121 registers and IMAD.WIDE issuing at half rate)
+// `words` (optional): the witness words to process, one block each (the adder-sum words are skipped by the callers: their
+// values follow from their operands' by linearity); output rows are indexed by the word number.
 __global__ void __launch_bounds__(256) bitcol_dot_kernel(const uint32_t* __restrict__ W, size_t N, const uint32_t* __restrict__ wt,
-                                                         uint32_t scale, uint32_t* __restrict__ out) {
+                                                         uint32_t scale, uint32_t* __restrict__ out, const int* __restrict__ words) {
     const int lane = threadIdx.x & 63, bg = threadIdx.x >> 6;
-    const uint32_t* __restrict__ wrow = W + (size_t)blockIdx.x * N;
+    const size_t word = words ? (size_t)words[blockIdx.x] : (size_t)blockIdx.x;
+    const uint32_t* __restrict__ wrow = W + word * N;
     uint32_t acc[8][4];
 #pragma unroll
     for (int b = 0; b < 8; b++)
@@ -199,19 +202,21 @@ __global__ void __launch_bounds__(256) bitcol_dot_kernel(const uint32_t* __restr
     if (threadIdx.x < 128) {
         const int g = threadIdx.x >> 5, x = threadIdx.x & 31;  // x = bit*4 + c
         uint32_t v = mulm(addm(red[2 * g][x], red[2 * g + 1][x]), scale);
-        out[((size_t)blockIdx.x * 32 + 8 * g) * 4 + x] = v;
+        out[(word * 32 + 8 * g) * 4 + x] = v;
     }
 }
 
 // g[c][r] = sum over words w, bits b of bit(W[w][r], b) * coefs[w*32+b][c]     block = 64 rows x PARTS word-slices
 // (64-bit IMAD.WIDE accumulation as above: at most 33,280 terms)
 __global__ void __launch_bounds__(1024) bitrow_comb_kernel(const uint32_t* __restrict__ W, size_t N, int n_words,
-                                                           const uint4* __restrict__ coefs, uint32_t* __restrict__ g) {
+                                                           const uint4* __restrict__ coefs, uint32_t* __restrict__ g,
+                                                           const int* __restrict__ words) {
     const int rl = threadIdx.x & 63, part = threadIdx.x >> 6, parts = blockDim.x >> 6;
     const size_t r = (size_t)blockIdx.x * 64 + rl;
     uint64_t acc[4] = {0, 0, 0, 0};
     if (r < N) {
-        for (int w = part; w < n_words; w += parts) {
+        for (int wi = part; wi < n_words; wi += parts) {
+            const int w = words ? words[wi] : wi;
             const uint32_t word = __ldg(W + (size_t)w * N + r);
             const uint4* __restrict__ cf = coefs + (size_t)w * 32;
 #pragma unroll 8
@@ -272,6 +277,18 @@ __global__ void __launch_bounds__(1024) rowcomb_m31_kernel(const uint32_t* __res
     }
 }
 
+// out[(w*32 + i)*4 + c] = tile(w)[i][rows[c]] for the words whose LDE tile ([32][M]) is still cached in the arena
+__global__ void gather_cached_kernel(const uint32_t* __restrict__ arena, size_t tile_words, size_t M, const int* __restrict__ slot,
+                                     int n_words, uint4 rows, int nq, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_words * 128) return;
+    const int c = idx & 3, i = (idx >> 2) & 31, w = idx >> 7;
+    const int sl = slot[w];
+    if (sl < 0 || c >= nq) return;
+    const uint32_t r = c == 0 ? rows.x : c == 1 ? rows.y : c == 2 ? rows.z : rows.w;
+    out[idx] = arena[(size_t)sl * tile_words + (size_t)i * M + r];
+}
+
 // component-wise basis doubling for up to 4 base-field points at once: b[c][half+k] = b[c][k] * f[c]
 __global__ void basis4_step_kernel(uint32_t* b, size_t stride, uint32_t half, uint4 f) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,15 +327,25 @@ cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trac
     return cudaGetLastError();
 }
 
-cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
-                              uint32_t* out) {
-    strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out);
+cudaError_t launch_gather_cached(cudaStream_t st, const uint32_t* arena, size_t tile_words, size_t M, const int* slot_dev, int n_words,
+                                 const uint32_t rows[4], int nq, uint32_t* out) {
+    if (n_words <= 0) return cudaSuccess;
+    strm::gather_cached_kernel<<<(n_words * 128 + 255) / 256, 256, 0, st>>>(arena, tile_words, M, slot_dev, n_words,
+                                                                            make_uint4(rows[0], rows[1], rows[2], rows[3]), nq, out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g) {
+cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
+                              uint32_t* out, const int* words_dev) {
+    if (n_words <= 0) return cudaSuccess;
+    strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g,
+                               const int* words_dev) {
     int parts = N >= 8192 ? 4 : 16;
-    strm::bitrow_comb_kernel<<<(unsigned)((N + 63) / 64), 64 * parts, 0, st>>>(W, N, n_words, (const uint4*)coefs, g);
+    strm::bitrow_comb_kernel<<<(unsigned)((N + 63) / 64), 64 * parts, 0, st>>>(W, N, n_words, (const uint4*)coefs, g, words_dev);
     return cudaGetLastError();
 }
 

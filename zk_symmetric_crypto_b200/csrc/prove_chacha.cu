@@ -643,6 +643,14 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     std::vector<QM31> sampled((size_t)N_COLS + 8);
     const FftTables tw_t{ctx->tw.IX, ctx->tw.IY, ctx->tw.X, ctx->tw.Y, ctx->tw.max_log};  // transposed inverse transform
     DBuf<uint32_t> basis(ctx, 4 * N), wt(ctx, 4 * N);
+    // the 336 adder-sum words are skipped in every pass over the packed witness: s_i = a_i + b_i + c_(i-1) - 2 c_i is an
+    // identity of polynomials (kernels_stream.cu fact 1), so sampled values follow from the operands' and the sum columns'
+    // quotient coefficients are folded into the operands' coefficients
+    std::vector<int> indep_words;
+    for (auto& g : plan)
+        for (int w : g.fft) indep_words.push_back(w);
+    DBuf<int> d_indep(ctx, indep_words.size());
+    CB_CUDA(cudaMemcpyAsync(d_indep.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     {
         std::vector<QM31> maps(n);
         maps[0] = z.y;
@@ -652,12 +660,22 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         CB_CUDA(launch_basis(st, basis.p, N, n, maps.data()));
         ColSrc bs{SRC_M31, basis.p, N, 0};
         CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
-        CB_CUDA(launch_bitcol_dot(st, W.p, N, N_WORDS, wt.p, inv_n, d_sampled.p));
+        CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)indep_words.size(), wt.p, inv_n, d_sampled.p, d_indep.p));
         for (int half = 0; half < 2; half++)
             CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
         ctx->launches += n + 6;
         CB_CUDA(cudaMemcpyAsync(sampled.data(), d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
+        for (auto& g : plan)
+            for (auto& cb : g.comb) {
+                QM31 cin = qzero();
+                for (int i = 0; i < 32; i++) {
+                    const QM31 cv = sampled[(size_t)cb.c * 32 + i];
+                    sampled[(size_t)cb.res * 32 + i] =
+                        qsub(qadd(qadd(sampled[(size_t)cb.a * 32 + i], sampled[(size_t)cb.b * 32 + i]), cin), qadd(cv, cv));
+                    cin = cv;
+                }
+            }
     }
     ctx->stage_end();
     ch.mix_felts(sampled.data(), sampled.size());
@@ -682,9 +700,29 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             for (int k = 0; k < 4; k++) coefs[j * 4 + k] = ac.v[k];
             alpha = qmul(alpha, rc);
         }
-        DBuf<uint32_t> d_coefs(ctx, nc * 4), g(ctx, 4 * N), g_lde(ctx, 4 * M), d_bc(ctx, 12 * 4);
-        CB_CUDA(cudaMemcpyAsync(d_coefs.p, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_bitrow_comb(st, W.p, N, N_WORDS, d_coefs.p, g.p));
+        // fold the sum columns' coefficients into their operands' (reverse dependency order: a sum may feed a later sum)
+        std::vector<uint32_t> fc(coefs.begin(), coefs.begin() + (size_t)N_COLS * 4);
+        for (size_t gi = plan.size(); gi-- > 0;)
+            for (size_t ci = plan[gi].comb.size(); ci-- > 0;) {
+                const Comb& cb = plan[gi].comb[ci];
+                for (int i = 0; i < 32; i++)
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t kap = fc[((size_t)cb.res * 32 + i) * 4 + k];
+                        uint32_t& fa = fc[((size_t)cb.a * 32 + i) * 4 + k];
+                        fa = add(fa, kap);
+                        uint32_t& fb = fc[((size_t)cb.b * 32 + i) * 4 + k];
+                        fb = add(fb, kap);
+                        uint32_t& fcy = fc[((size_t)cb.c * 32 + i) * 4 + k];
+                        fcy = sub(fcy, add(kap, kap));
+                        if (i > 0) {
+                            uint32_t& fcp = fc[((size_t)cb.c * 32 + i - 1) * 4 + k];
+                            fcp = add(fcp, kap);
+                        }
+                    }
+            }
+        DBuf<uint32_t> d_coefs(ctx, (size_t)N_COLS * 4), g(ctx, 4 * N), g_lde(ctx, 4 * M), d_bc(ctx, 12 * 4);
+        CB_CUDA(cudaMemcpyAsync(d_coefs.p, fc.data(), fc.size() * 4, cudaMemcpyHostToDevice, st));
+        CB_CUDA(launch_bitrow_comb(st, W.p, N, (int)indep_words.size(), d_coefs.p, g.p, d_indep.p));
         ColSrc gs{SRC_M31, g.p, N, 0};
         CB_CUDA(launch_fft(st, gs, 4, n, cfg.log_blowup, 1 | 4, nullptr, 0, g_lde.p, M, ctx->tw, g.p, N));
         uint32_t bc[12 * 4] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -716,36 +754,76 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ch.mix_u64(pow_nonce);
     std::vector<uint32_t> queries = host::queries_generate(ch, m, cfg.n_queries);
 
-    // ---- decommit: queried LDE values of the trace columns are evaluated from the packed witness like the OODS samples
+    // ---- decommit: queried LDE values of the trace columns.  Tiles that stayed cached since the commitment pass are read
+    //      directly; adder-sum words follow from their operands (kernels_stream.cu fact 1, which holds row by row on the
+    //      extended domain); only the words from the first uncached tile on are evaluated from the packed witness like the
+    //      OODS samples (all words when the tiles are row-sharded over several ranks).
     ctx->stage_begin("decommit");
     std::vector<uint8_t> fri_bytes = fri_decommit(ctx, fri, cfg, queries);
     std::vector<Hash32> dec1 = merkle_decommit(ctx, tree1, queries), dec2 = merkle_decommit(ctx, tree2, queries);
     const int nq = (int)queries.size();
     std::vector<uint32_t> qv1((size_t)N_COLS * nq), qv2((size_t)8 * nq);
     {
+        std::vector<int> slot(N_WORDS, -1);
+        std::vector<char> indep(N_WORDS, 0);
+        for (auto& g : plan)
+            for (int w : g.fft) indep[w] = 1;
+        int w0 = 0;  // words >= w0 come from the packed witness
+        if (G == 1) {
+            w0 = N_WORDS;
+            for (int w = N_WORDS - 1; w >= 0; w--)
+                if (indep[w] && tiles.cache_slot[w] < 0) w0 = w;
+            for (int w = 0; w < w0; w++)
+                if (indep[w]) slot[w] = tiles.cache_slot[w];
+        }
+        DBuf<int> d_slot(ctx, N_WORDS);
+        CB_CUDA(cudaMemcpyAsync(d_slot.p, slot.data(), N_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
         DBuf<uint32_t> d_rows(ctx, nq), d_q2(ctx, qv2.size()), d_q1(ctx, (size_t)N_COLS * 4);
         std::vector<uint32_t> q4((size_t)N_COLS * 4);
         for (int q0 = 0; q0 < nq; q0 += 4) {
-            uint32_t init[4] = {0, 0, 0, 0};
-            std::vector<std::array<uint32_t, 4>> maps(n);
-            for (int c = 0; c < 4 && q0 + c < nq; c++) {
-                host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(queries[q0 + c], m)));
-                init[c] = 1;
-                maps[0][c] = p.y;
-                uint32_t x = p.x;
-                for (int j = 1; j < n; j++) { maps[j][c] = x; x = sub(mul(2, mul(x, x)), 1); }
+            const int nqc = nq - q0 < 4 ? nq - q0 : 4;
+            if (w0 < N_WORDS) {
+                uint32_t init[4] = {0, 0, 0, 0};
+                std::vector<std::array<uint32_t, 4>> maps(n);
+                for (int c = 0; c < nqc; c++) {
+                    host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(queries[q0 + c], m)));
+                    init[c] = 1;
+                    maps[0][c] = p.y;
+                    uint32_t x = p.x;
+                    for (int j = 1; j < n; j++) { maps[j][c] = x; x = sub(mul(2, mul(x, x)), 1); }
+                }
+                for (int c = nqc; c < 4; c++)
+                    for (int j = 0; j < n; j++) maps[j][c] = 0;
+                CB_CUDA(launch_basis4(st, basis.p, N, n, init, (const uint32_t(*)[4])maps.data()));
+                ColSrc bs{SRC_M31, basis.p, N, 0};
+                CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
+                CB_CUDA(launch_bitcol_dot(st, W.p + (size_t)w0 * N, N, N_WORDS - w0, wt.p, inv_n, d_q1.p + (size_t)w0 * 128));
+                ctx->launches += n + 3;
             }
-            for (int c = nq - q0; c < 4; c++)
-                for (int j = 0; j < n; j++) maps[j][c] = 0;
-            CB_CUDA(launch_basis4(st, basis.p, N, n, init, (const uint32_t(*)[4])maps.data()));
-            ColSrc bs{SRC_M31, basis.p, N, 0};
-            CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
-            CB_CUDA(launch_bitcol_dot(st, W.p, N, N_WORDS, wt.p, inv_n, d_q1.p));
-            ctx->launches += n + 3;
+            if (w0 > 0) {
+                uint32_t rows4[4] = {0, 0, 0, 0};
+                for (int c = 0; c < nqc; c++) rows4[c] = queries[q0 + c];
+                CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, M, d_slot.p, w0, rows4, nqc, d_q1.p));
+                ctx->launches++;
+            }
             CB_CUDA(cudaMemcpyAsync(q4.data(), d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
+            if (w0 > 0)
+                for (auto& g : plan)
+                    for (auto& cb : g.comb) {
+                        if (cb.res >= w0) continue;
+                        for (int c = 0; c < nqc; c++) {
+                            uint32_t cin = 0;
+                            for (int i = 0; i < 32; i++) {
+                                const uint32_t av = q4[((size_t)cb.a * 32 + i) * 4 + c], bv = q4[((size_t)cb.b * 32 + i) * 4 + c],
+                                               cv = q4[((size_t)cb.c * 32 + i) * 4 + c];
+                                q4[((size_t)cb.res * 32 + i) * 4 + c] = sub(add(add(av, bv), cin), add(cv, cv));
+                                cin = cv;
+                            }
+                        }
+                    }
             for (int j = 0; j < N_COLS; j++)
-                for (int c = 0; c < 4 && q0 + c < nq; c++) qv1[(size_t)j * nq + q0 + c] = q4[(size_t)j * 4 + c];
+                for (int c = 0; c < nqc; c++) qv1[(size_t)j * nq + q0 + c] = q4[(size_t)j * 4 + c];
         }
         CB_CUDA(cudaMemcpyAsync(d_rows.p, queries.data(), nq * 4, cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_gather_rows(st, comp_lde.p, M, 8, d_rows.p, nq, d_q2.p));
