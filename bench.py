@@ -443,6 +443,19 @@ def main():
                                            "columns_transformed": cols_t},
                         "all_kernels_gbs": {k: alg[k] / (stages[k] / 1000.0) / 1e9 for k in stages if k in alg and stages[k] > 0},
                         "counters": cnt}
+        if roofline:
+            # measured DRAM traffic / pipe utilisation of the same kernel from the committed ncu capture (one launch)
+            try:
+                nk = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels_r01.json"))).get(top)
+            except Exception:
+                nk = None
+            if nk and L == 20:
+                roofline["traffic"] = nk["dram_bytes"]
+                roofline["traffic_unit"] = "DRAM bytes read+written by ONE launch (ncu --set full); that launch's algorithmic bytes: %s" % (
+                    nk.get("launch_algorithmic_bytes"))
+                roofline["int_pipe"] = {k: nk[k] for k in ("kernel", "launch_ms", "issue_active_pct", "alu_pipe_pct", "fma_pipe_pct",
+                                                           "dram_pct", "registers") if k in nk}
+                roofline["int_pipe"]["source"] = "profiles/ncu_kernels_r01.json"
         per_step = 1 if sharded else world
         value = per_step * args.steps / (ms / 1000.0)
         e2e_value = per_step * args.steps / (ms_e2e / 1000.0)

@@ -159,36 +159,58 @@ struct Eval {
     int col, k;
     __device__ __forceinline__ uint32_t ld(int c) const { return lde[(size_t)c * stride]; }
     __device__ __forceinline__ void emit(uint32_t C) { acc.mac(tlo, thi, k++, C); }
-    // loads 8 bit columns, emits their boolean constraints, returns sum 2^i b_i (< 2^8 * p as u32 lazily: kept canonical)
-    __device__ __forceinline__ uint32_t bits8(uint32_t (&b)[8]) {
+    // boolean constraints of 8 bit values (already loaded), returns sum 2^i b_i
+    __device__ __forceinline__ uint32_t bits8(const uint32_t (&b)[8]) {
         uint32_t s = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            b[i] = ld(col++);
             emit(bool_c(b[i], b[i] + b[i]));
             s = m31d::addm(s, m31d::mulm(b[i], 1u << i));
         }
         return s;
     }
+    // Every operation first issues ALL of its column loads (27 for a byte xor, 18 for xtime) and only then evaluates its
+    // constraints, in the reference's order: with ~150 registers only 12 warps are resident per SM, so the loads in flight
+    // per thread are what hides the HBM latency.
     // returns the column index of the result byte
     __device__ __forceinline__ int xor_byte(int a, int b) {
         uint32_t ab[8], bb[8], cb[8];
+        const uint32_t* p = lde + (size_t)col * stride;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ab[i] = p[(size_t)i * stride];
+            bb[i] = p[(size_t)(8 + i) * stride];
+            cb[i] = p[(size_t)(16 + i) * stride];
+        }
+        const uint32_t vr = p[(size_t)24 * stride], va = ld(a), vb = ld(b);
+        asm volatile("" ::: "memory");  // keep the loads together: the scheduler otherwise sinks each next to its use
+        const int r = col + 24;
+        col += 25;
         const uint32_t sa = bits8(ab), sb = bits8(bb), sc = bits8(cb);
-        emit(m31d::subm(ld(a), sa));
-        emit(m31d::subm(ld(b), sb));
+        emit(m31d::subm(va, sa));
+        emit(m31d::subm(vb, sb));
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t m = m31d::mulm(ab[i], bb[i]);
             emit(m31d::addm(m31d::subm(m31d::subm(cb[i], ab[i]), bb[i]), m31d::dbl(m)));
         }
-        const int r = col++;
-        emit(m31d::subm(ld(r), sc));
+        emit(m31d::subm(vr, sc));
         return r;
     }
     __device__ __forceinline__ int xtime(int a) {
         uint32_t ab[8], rb[8];
+        const uint32_t* p = lde + (size_t)col * stride;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ab[i] = p[(size_t)i * stride];
+            rb[i] = p[(size_t)(8 + i) * stride];
+        }
+        const uint32_t vr = p[(size_t)16 * stride], va = ld(a);
+        asm volatile("" ::: "memory");
+        const int r = col + 16;
+        col += 17;
         const uint32_t sa = bits8(ab);
-        emit(m31d::subm(ld(a), sa));
+        emit(m31d::subm(va, sa));
         const uint32_t sr = bits8(rb);
         const uint32_t h = ab[7];
         auto x2 = [&](int i, int j) {
@@ -203,8 +225,7 @@ struct Eval {
         emit(m31d::subm(rb[5], ab[4]));
         emit(m31d::subm(rb[6], ab[5]));
         emit(m31d::subm(rb[7], ab[6]));
-        const int r = col++;
-        emit(m31d::subm(ld(r), sr));
+        emit(m31d::subm(vr, sr));
         return r;
     }
     __device__ __forceinline__ int mul3(int a) { return xor_byte(xtime(a), a); }
