@@ -198,13 +198,15 @@ struct Tiles {
     size_t tile_words = 0;
     uint32_t* arena = nullptr;
     std::vector<int> slot_of, cache_slot, free_trans;
+    std::vector<char> want;  // independent words that get a cache slot in pass 1 (chosen up front, cache_choice())
     // slots released while group g is processed become reusable `lag` groups later (lag 2 when tiles are produced on a second
     // stream: the producer of group g only waits for the consumer of group g-2)
     std::vector<std::vector<int>> pending;
     int lag = 0, group = 0;
     int in_use = 0, peak = 0;
-    void init(int cache, int trans, size_t tw_, uint32_t* mem) {
+    void init(int cache, int trans, size_t tw_, uint32_t* mem, const std::vector<char>& want_) {
         n_cache = cache; n_trans = trans; tile_words = tw_; arena = mem; cache_used = 0;
+        want = want_;
         slot_of.assign(N_WORDS, -1);
         cache_slot.assign(N_WORDS, -1);
         free_trans.clear();
@@ -235,7 +237,7 @@ struct Tiles {
     // returns true when the tile must be (re)computed
     bool acquire(int w, bool indep, int pass) {
         if (indep && pass == 2 && cache_slot[w] >= 0) { slot_of[w] = cache_slot[w]; return false; }
-        if (indep && pass == 1 && cache_used < n_cache) { cache_slot[w] = cache_used++; slot_of[w] = cache_slot[w]; return true; }
+        if (indep && pass == 1 && want[w] && cache_used < n_cache) { cache_slot[w] = cache_used++; slot_of[w] = cache_slot[w]; return true; }
         if (free_trans.empty()) throw CbError("internal: transient tile slots exhausted");
         slot_of[w] = n_cache + free_trans.back();
         free_trans.pop_back();
@@ -252,9 +254,28 @@ struct Tiles {
     }
 };
 
-int plan_peak_transient(const std::vector<Group>& plan, int lag) {
+// Which independent words keep their LDE tile between the passes when only n_cache fit: the words of the last groups
+// (final additions, plaintext, ciphertext) and of the first group come first, then the quarter-round groups in order.
+// Those tail groups hold up to 48 tiles live at once; left uncached they alone would set the transient-slot peak
+// (48 instead of 28 slots, i.e. 20 fewer cached tiles).
+std::vector<char> cache_choice(const std::vector<Group>& plan, int n_cache) {
+    std::vector<int> order;
+    for (size_t g = plan.size() - 4; g < plan.size(); g++)
+        for (int w : plan[g].fft) order.push_back(w);
+    for (int w : plan[0].fft) order.push_back(w);
+    for (size_t g = 1; g + 4 < plan.size(); g++)
+        for (int w : plan[g].fft) order.push_back(w);
+    std::vector<char> want(N_WORDS, 0);
+    for (int i = 0; i < n_cache && i < (int)order.size(); i++) want[order[i]] = 1;
+    return want;
+}
+
+// transient slots a pass needs when the words in `want` are cached (both passes have the same live sets)
+int plan_peak_transient(const std::vector<Group>& plan, int lag, const std::vector<char>& want) {
     Tiles t;
-    t.init(0, N_WORDS, 0, nullptr);
+    int n_want = 0;
+    for (char c : want) n_want += c;
+    t.init(n_want, N_WORDS, 0, nullptr, want);
     t.lag = lag;
     int gi = 0;
     for (auto& g : plan) {
@@ -348,8 +369,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
     const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr && G == 1;
     const int lag = overlap ? 2 : 0;
-    static const int peak_trans_lag[3] = {plan_peak_transient(plan, 0), 0, plan_peak_transient(plan, 2)};
-    const int peak_trans = peak_trans_lag[lag];
+    static const int peak_trans_none = plan_peak_transient(plan, 2, std::vector<char>(N_WORDS, 0));  // nothing cached
     cudaStream_t sf = overlap ? ctx->stream2 : st;
     // placement knobs (KiB) for measuring how the power-of-two strides of the transform passes interact with the DRAM
     // address map: extra pitch between tile slots, offset of the FFT scratch behind the slots
@@ -375,12 +395,29 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         const size_t other = (scratch_words + stage_words + 96 * M) * 4 + ((size_t)3 << 30);
         const size_t tile_bytes = tile_words * 4;
         const size_t can = avail > other ? (avail - other) / tile_bytes : 0;
-        if (can < (size_t)peak_trans) throw CbError("not enough device memory for the tile arena at log_size " + std::to_string(n));
+        if (can < (size_t)peak_trans_none) throw CbError("not enough device memory for the tile arena at log_size " + std::to_string(n));
         const int cap = opt.max_cached_tiles >= 0 ? opt.max_cached_tiles : ctx->max_cached_tiles;
         if (cap >= 0 && n_cache > cap) n_cache = cap;
-        if ((size_t)n_cache > can - peak_trans) n_cache = (int)(can - peak_trans);
+        // the largest cache whose tiles plus the transient slots the plan then needs fit
+        // (n_cache + peak(n_cache) never decreases with n_cache: binary search; the answer is remembered per thread)
+        static thread_local size_t memo_can = 0;
+        static thread_local int memo_in = -1, memo_lag = -1, memo_out = 0;
+        if (memo_can == can && memo_in == n_cache && memo_lag == lag) {
+            n_cache = memo_out;
+        } else {
+            auto fits = [&](int c) { return (size_t)(c + plan_peak_transient(plan, lag, cache_choice(plan, c))) <= can; };
+            int lo = 0, hi = n_cache;  // fits(0) holds (checked above)
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) / 2;
+                if (fits(mid)) lo = mid; else hi = mid - 1;
+            }
+            memo_can = can; memo_in = n_cache; memo_lag = lag; memo_out = lo;
+            n_cache = lo;
+        }
         n_cache = comm_min_int(cm, n_cache, st);  // every rank must take the same caching decisions
     }
+    const std::vector<char> want = cache_choice(plan, n_cache);
+    const int peak_trans = plan_peak_transient(plan, lag, want);
     // tile slots + FFT scratch live in the context's persistent arena
     const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
     uint32_t* arena_p;
@@ -393,7 +430,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words;
     uint32_t* stage_p = scratch_p + scratch_words;
     Tiles tiles;
-    tiles.init(n_cache, peak_trans, tile_words, arena_p);
+    tiles.init(n_cache, peak_trans, tile_words, arena_p, want);
     tiles.lag = lag;
     ctx->fft_words = 0;
     ctx->cached_tiles = n_cache;
@@ -756,8 +793,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- decommit: queried LDE values of the trace columns.  Tiles that stayed cached since the commitment pass are read
     //      directly; adder-sum words follow from their operands (kernels_stream.cu fact 1, which holds row by row on the
-    //      extended domain); only the words from the first uncached tile on are evaluated from the packed witness like the
-    //      OODS samples (all words when the tiles are row-sharded over several ranks).
+    //      extended domain); only the independent words without a cached tile are evaluated from the packed witness like the
+    //      OODS samples (all independent words when the tiles are row-sharded over several ranks).
     ctx->stage_begin("decommit");
     std::vector<uint8_t> fri_bytes = fri_decommit(ctx, fri, cfg, queries);
     std::vector<Hash32> dec1 = merkle_decommit(ctx, tree1, queries), dec2 = merkle_decommit(ctx, tree2, queries);
@@ -768,21 +805,20 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         std::vector<char> indep(N_WORDS, 0);
         for (auto& g : plan)
             for (int w : g.fft) indep[w] = 1;
-        int w0 = 0;  // words >= w0 come from the packed witness
-        if (G == 1) {
-            w0 = N_WORDS;
-            for (int w = N_WORDS - 1; w >= 0; w--)
-                if (indep[w] && tiles.cache_slot[w] < 0) w0 = w;
-            for (int w = 0; w < w0; w++)
-                if (indep[w]) slot[w] = tiles.cache_slot[w];
+        std::vector<int> need;  // independent words whose tile is not cached (all of them when the tiles are row-sharded)
+        for (int w = 0; w < N_WORDS; w++) {
+            if (!indep[w]) continue;
+            if (G == 1 && tiles.cache_slot[w] >= 0) slot[w] = tiles.cache_slot[w];
+            else need.push_back(w);
         }
-        DBuf<int> d_slot(ctx, N_WORDS);
+        DBuf<int> d_slot(ctx, N_WORDS), d_need(ctx, need.size() + 1);
         CB_CUDA(cudaMemcpyAsync(d_slot.p, slot.data(), N_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(d_need.p, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         DBuf<uint32_t> d_rows(ctx, nq), d_q2(ctx, qv2.size()), d_q1(ctx, (size_t)N_COLS * 4);
         std::vector<uint32_t> q4((size_t)N_COLS * 4);
         for (int q0 = 0; q0 < nq; q0 += 4) {
             const int nqc = nq - q0 < 4 ? nq - q0 : 4;
-            if (w0 < N_WORDS) {
+            if (!need.empty()) {
                 uint32_t init[4] = {0, 0, 0, 0};
                 std::vector<std::array<uint32_t, 4>> maps(n);
                 for (int c = 0; c < nqc; c++) {
@@ -797,29 +833,26 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 CB_CUDA(launch_basis4(st, basis.p, N, n, init, (const uint32_t(*)[4])maps.data()));
                 ColSrc bs{SRC_M31, basis.p, N, 0};
                 CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
-                CB_CUDA(launch_bitcol_dot(st, W.p + (size_t)w0 * N, N, N_WORDS - w0, wt.p, inv_n, d_q1.p + (size_t)w0 * 128));
+                CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)need.size(), wt.p, inv_n, d_q1.p, d_need.p));
                 ctx->launches += n + 3;
             }
-            if (w0 > 0) {
+            if (need.size() < (size_t)N_INDEP_WORDS) {
                 uint32_t rows4[4] = {0, 0, 0, 0};
                 for (int c = 0; c < nqc; c++) rows4[c] = queries[q0 + c];
-                CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, M, d_slot.p, w0, rows4, nqc, d_q1.p));
+                CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, M, d_slot.p, N_WORDS, rows4, nqc, d_q1.p));
                 ctx->launches++;
             }
             CB_CUDA(cudaMemcpyAsync(q4.data(), d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
-            if (w0 > 0)
-                for (auto& g : plan)
-                    for (auto& cb : g.comb) {
-                        if (cb.res >= w0) continue;
-                        for (int c = 0; c < nqc; c++) {
-                            uint32_t cin = 0;
-                            for (int i = 0; i < 32; i++) {
-                                const uint32_t av = q4[((size_t)cb.a * 32 + i) * 4 + c], bv = q4[((size_t)cb.b * 32 + i) * 4 + c],
-                                               cv = q4[((size_t)cb.c * 32 + i) * 4 + c];
-                                q4[((size_t)cb.res * 32 + i) * 4 + c] = sub(add(add(av, bv), cin), add(cv, cv));
-                                cin = cv;
-                            }
+            for (auto& g : plan)
+                for (auto& cb : g.comb)
+                    for (int c = 0; c < nqc; c++) {
+                        uint32_t cin = 0;
+                        for (int i = 0; i < 32; i++) {
+                            const uint32_t av = q4[((size_t)cb.a * 32 + i) * 4 + c], bv = q4[((size_t)cb.b * 32 + i) * 4 + c],
+                                           cv = q4[((size_t)cb.c * 32 + i) * 4 + c];
+                            q4[((size_t)cb.res * 32 + i) * 4 + c] = sub(add(add(av, bv), cin), add(cv, cv));
+                            cin = cv;
                         }
                     }
             for (int j = 0; j < N_COLS; j++)
