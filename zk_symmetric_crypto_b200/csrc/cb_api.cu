@@ -54,6 +54,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
+    if (ctx->tw_shift_dev) cudaFree(ctx->tw_shift_dev);
     ctx->release_arena();
     try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);

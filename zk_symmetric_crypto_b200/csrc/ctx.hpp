@@ -40,6 +40,8 @@ struct cb_ctx {
     // twiddles (device) for canonic domains up to tw.max_log
     FftTables tw{nullptr, nullptr, nullptr, nullptr, 0};
     uint32_t* tw_dev = nullptr;
+    FftTables tw_shift{nullptr, nullptr, nullptr, nullptr, 0};  // host::make_twiddles(.., shifted = true)
+    uint32_t* tw_shift_dev = nullptr;
     // per-stage device timing of the last proof (CUDA events on `stream`)
     bool profile = false;
     std::vector<StageTime> stages;
@@ -57,6 +59,7 @@ struct cb_ctx {
     void* ensure_arena(size_t bytes);
     void release_arena();
     void ensure_twiddles(int max_log);
+    void ensure_twiddles_shifted(int max_log);
     void* dmalloc(size_t bytes);
     void dfree(void* p);
     void sync() { CB_CUDA(cudaStreamSynchronize(stream)); }

@@ -94,14 +94,17 @@ inline void batch_inverse(std::vector<uint32_t>& v) {
     }
 }
 
-inline TwiddleTables make_twiddles(int max_log) {
+// shifted = false: the tower of canonic half cosets half_odds(k) (initial g_(k+2), step g_k).
+// shifted = true:  the tower with initial g_(k+3): its log-k circle domain is the first half (storage rows [0, 2^k)) of the
+// canonic domain of log size k+1, i.e. the sub-domain on which the trace coset's vanishing polynomial is constant.
+inline TwiddleTables make_twiddles(int max_log, bool shifted = false) {
     TwiddleTables t;
     t.max_log = max_log;
     size_t ny = (size_t)1 << max_log;  // Y[k], k=0..max_log-1 at offset 2^k
     t.Y.assign(ny, 0);
     t.X.assign(ny / 2 + 1, 0);         // X[k], k=1..max_log-1 at offset 2^(k-1)
     for (int k = 0; k < max_log; k++) {
-        std::vector<Pt> p = Coset::half_odds(k).points();
+        std::vector<Pt> p = (shifted ? Coset{subgroup_gen(k + 3), subgroup_gen(k), k} : Coset::half_odds(k)).points();
         size_t n = (size_t)1 << k;
         for (size_t j = 0; j < n; j++) t.Y[n + j] = p[bit_reverse((uint32_t)j, k)].y;
         if (k >= 1)

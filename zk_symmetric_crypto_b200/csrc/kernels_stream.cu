@@ -95,11 +95,12 @@ __device__ __forceinline__ void addx_job(const ConstraintJob& J, size_t row, siz
     }
 }
 
+// rows: the first `rows` rows of the tiles are evaluated (M = row count of a tile = column stride)
 __global__ void __launch_bounds__(128, CONS_MIN_BLOCKS) constraints_tiles_kernel(ConstraintJobs jobs, size_t M, const uint4* __restrict__ tlo,
                                                                 const uint4* __restrict__ thi, uint32_t* __restrict__ acc,
-                                                                int first) {
+                                                                int first, size_t rows) {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= M) return;
+    if (row >= rows) return;
     AccSplit A;
     A.init();
     for (int j = 0; j < jobs.n; j++) {
@@ -310,10 +311,11 @@ cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t 
 
 // apr_lo / apr_hi: the reversed alpha-power table split by launch_split16
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
-                                     const uint32_t* apr_hi, uint32_t* acc, int first) {
-    int threads = M >= 128 * 148 ? 128 : 32;
-    strm::constraints_tiles_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(
-        jobs, M, (const uint4*)apr_lo, (const uint4*)apr_hi, acc, first);
+                                     const uint32_t* apr_hi, uint32_t* acc, int first, size_t rows) {
+    if (rows == 0 || rows > M) rows = M;
+    int threads = rows >= 128 * 148 ? 128 : 32;
+    strm::constraints_tiles_kernel<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(
+        jobs, M, (const uint4*)apr_lo, (const uint4*)apr_hi, acc, first, rows);
     return cudaGetLastError();
 }
 

@@ -608,16 +608,23 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
     CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
     ctx->launches += 2;
-    {
-        std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);
-        for (uint32_t i = 0; i < den.size(); i++) {
-            uint32_t row = i << n;
-            host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(row, m)));
-            den[i] = inv(host::coset_vanishing_m31(n, p));
-        }
-        CB_CUDA(cudaMemcpyAsync(d_den.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, st));
-        ctx->sync();
+    std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);  // 1 / Z_H on the two halves of the (bit-reversed) evaluation domain
+    for (uint32_t i = 0; i < den.size(); i++) {
+        uint32_t row = i << n;
+        host::Pt p = host::index_to_point(host::canonic_index_at(m, host::bit_reverse(row, m)));
+        den[i] = inv(host::coset_vanishing_m31(n, p));
     }
+    CB_CUDA(cudaMemcpyAsync(d_den.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, st));
+    ctx->sync();
+    // Half-domain evaluation.  The constraints have degree 2, so the quotient q = C / Z_H lies in the (N+1)-dimensional space
+    // {p_left + c * Z_H}: N coefficients of the log-n circle basis plus ONE constant c in front of Z_H = pi^(n-1)(x) (the
+    // reference's "right half" of the composition polynomial is that constant).  Storage rows [0, N) of the evaluation domain
+    // form a circle domain of log size n on which Z_H is constant (= v): q restricted to it is p_left + v c, interpolated with
+    // the shifted twiddle tower (host::make_twiddles(.., true)); one more row (row N, where Z_H = -v) separates c.
+    // So only N + 1 of the 2N rows are evaluated; coefficients - and therefore the proof bytes - are unchanged.
+    // (Row-sharded mode keeps the full-domain evaluation: the first-half rows live on half of the ranks only.)
+    const bool half_mode = G == 1;
+    const size_t cons_rows = half_mode ? std::min(M, N + 128) : 0;
     run_pass(2, [&](size_t gi, const Group& g) {
         ConstraintJobs cj{};
         for (auto& c : g.cons)
@@ -627,7 +634,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                             c.kx, c.kb0, c.kb1, c.kb2, c.kbc, c.arg, c.type};
         if (cj.n == 0) return;
         ctx->stage_begin("constraints");
-        CB_CUDA(launch_constraints_tiles(st, cj, Mr, apr_lo.p, apr_hi.p, accp, gi == 0));
+        CB_CUDA(launch_constraints_tiles(st, cj, Mr, apr_lo.p, apr_hi.p, accp, gi == 0, cons_rows));
         ctx->stage_end();
         ctx->launches++;
     });
@@ -659,7 +666,38 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     {
         DBuf<uint32_t> scratch4(ctx, 4 * M);
         ColSrc src{SRC_M31, acc.p, M, 0};
-        CB_CUDA(launch_fft(st, src, 4, m, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw, scratch4.p, M));
+        if (half_mode) {
+            ctx->ensure_twiddles_shifted(n);
+            CB_CUDA(cudaMemsetAsync(comp_coef.p, 0, 4 * M * 4, st));
+            CB_CUDA(launch_fft(st, src, 4, n, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw_shift, scratch4.p, N));  // E = p_left + v c
+            // E at the point of storage row N, and q there
+            const host::Pt ps = host::index_to_point(host::canonic_index_at(m, host::bit_reverse((uint32_t)N, m)));
+            std::vector<QM31> maps(n);
+            maps[0] = qfrom(ps.y);
+            uint32_t x = ps.x;
+            for (int j = 1; j < n; j++) { maps[j] = qfrom(x); x = sub(mul(2, mul(x, x)), 1); }
+            DBuf<uint32_t> bas(ctx, 4 * N), d_e(ctx, 16);
+            CB_CUDA(launch_basis(st, bas.p, N, n, maps.data()));
+            CB_CUDA(launch_oods_dot(st, comp_coef.p, M, 4, n, bas.p, N, d_e.p));
+            uint32_t e16[16], qn[4], c0[4];
+            CB_CUDA(cudaMemcpyAsync(e16, d_e.p, sizeof e16, cudaMemcpyDeviceToHost, st));
+            for (int c = 0; c < 4; c++) {
+                CB_CUDA(cudaMemcpyAsync(&qn[c], acc.p + (size_t)c * M + N, 4, cudaMemcpyDeviceToHost, st));
+                CB_CUDA(cudaMemcpyAsync(&c0[c], comp_coef.p + (size_t)c * M, 4, cudaMemcpyDeviceToHost, st));
+            }
+            ctx->sync();
+            const uint32_t v = inv(den[0]), inv2v = inv(add(v, v));
+            for (int c = 0; c < 4; c++) {
+                const uint32_t cc = mul(sub(e16[4 * c], qn[c]), inv2v);  // E(p*) - q(p*) = 2 v c
+                const uint32_t left0 = sub(c0[c], mul(v, cc));
+                CB_CUDA(cudaMemcpyAsync(comp_coef.p + (size_t)c * M, &left0, 4, cudaMemcpyHostToDevice, st));
+                CB_CUDA(cudaMemcpyAsync(comp_coef.p + (size_t)c * M + N, &cc, 4, cudaMemcpyHostToDevice, st));
+            }
+            ctx->sync();
+            ctx->launches += n + 4;
+        } else {
+            CB_CUDA(launch_fft(st, src, 4, m, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw, scratch4.p, M));
+        }
         for (int half = 0; half < 2; half++) {
             ColSrc cs{SRC_M31, comp_coef.p + half * N, M, 0};
             CB_CUDA(launch_fft(st, cs, 4, n, cfg.log_blowup, 4, nullptr, 0, comp_lde.p + (size_t)half * 4 * M, M, ctx->tw, nullptr, 0));

@@ -17,6 +17,22 @@ void cb_ctx::ensure_twiddles(int max_log) {
     sync();
 }
 
+void cb_ctx::ensure_twiddles_shifted(int max_log) {
+    if (tw_shift.max_log >= max_log) return;
+    if (max_log < 6) max_log = 6;
+    host::TwiddleTables t = host::make_twiddles(max_log, true);
+    if (tw_shift_dev) { sync(); CB_CUDA(cudaFree(tw_shift_dev)); tw_shift_dev = nullptr; }
+    size_t nx = t.X.size(), ny = t.Y.size();
+    CB_CUDA(cudaMalloc(&tw_shift_dev, (2 * nx + 2 * ny) * sizeof(uint32_t)));
+    uint32_t* p = tw_shift_dev;
+    CB_CUDA(cudaMemcpyAsync(p, t.X.data(), nx * 4, cudaMemcpyHostToDevice, stream)); tw_shift.X = p; p += nx;
+    CB_CUDA(cudaMemcpyAsync(p, t.Y.data(), ny * 4, cudaMemcpyHostToDevice, stream)); tw_shift.Y = p; p += ny;
+    CB_CUDA(cudaMemcpyAsync(p, t.IX.data(), nx * 4, cudaMemcpyHostToDevice, stream)); tw_shift.IX = p; p += nx;
+    CB_CUDA(cudaMemcpyAsync(p, t.IY.data(), ny * 4, cudaMemcpyHostToDevice, stream)); tw_shift.IY = p;
+    tw_shift.max_log = max_log;
+    sync();
+}
+
 cudaEvent_t cb_ctx::event(size_t i) {
     while (ev_pool.size() <= i) {
         cudaEvent_t e;
