@@ -127,12 +127,18 @@ void fft_init_attrs();
 void fft2_init_attrs();
 size_t fft_packed_scratch_words(int kind, int njobs, int log_n);
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
-                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0);
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0, int first_half_only = 0);
 cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t M);
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
                                      const uint32_t* apr_hi, uint32_t* acc, int first, size_t rows = 0);
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi);
 cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0 = 0);
+struct TileRowJobs {
+    int n;
+    int word[MAX_LEAF_GROUPS];
+    const uint32_t* tile[MAX_LEAF_GROUPS];
+};
+cudaError_t launch_gather_tile_row(cudaStream_t st, const TileRowJobs& jobs, size_t M, size_t row, uint32_t* out);
 cudaError_t launch_gather_cached(cudaStream_t st, const uint32_t* arena, size_t tile_words, size_t M, const int* slot_dev, int n_words,
                                  const uint32_t rows[4], int nq, uint32_t* out);
 cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,

@@ -137,6 +137,7 @@ __device__ __forceinline__ void apply_layers(uint32_t* s, int ncol, int colstrid
 struct Jobs {
     int n;                    // jobs in this launch (<= MAX_FFT_JOBS)
     uint32_t one, mone;       // run-time 1 and -1: x*one+y compiles to IMAD, moving butterfly additions to the FMA pipe
+    int halves;               // 2: the whole extended column; 1: only storage rows [0, 2^n) (all the constraint pass reads)
     int shard_log;            // log2 of the rows per row-shard of the output tile (= log_n+1 when the tile is not sharded):
                               // tile layout [shards][cols][2^shard_log], so that a rank's row range of all columns is contiguous
     const uint32_t* src[MAX_FFT_JOBS];  // packed witness word row (2^n words)
@@ -497,8 +498,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
 #pragma unroll
         for (int k = 0; k < J; k++) v[k] = in[(size_t)k << K1];
         inv_block<RA>(v, twr, jobs.one, jobs.mone);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < jobs.halves; h++) {
             uint32_t u[1 << RA];
 #pragma unroll
             for (int k = 0; k < J; k++) u[k] = v[k];
@@ -535,8 +535,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
 #pragma unroll
         for (int k = 0; k < (1 << RBs); k++) c[k] = s0[((pb + (k << RA)) << 5) | q];
         inv_block<RBs>(c, twb, jobs.one, jobs.mone);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < jobs.halves; h++) {
             uint32_t u[1 << RBs];
 #pragma unroll
             for (int k = 0; k < (1 << RBs); k++) u[k] = c[k];
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__(256) mid12_kernel(Jobs jobs, int cols_per_job,
     }
     __syncthreads();
     // forward step A: local bits [0,RA), to global
-    for (int pa = wid; pa < 2 * (J >> RA); pa += nw) {
+    for (int pa = wid; pa < jobs.halves * (J >> RA); pa += nw) {
         const int h = pa >= (J >> RA);
         const int j0 = (pa - h * (J >> RA)) << RA;
         const uint32_t* sh = h ? s1 : s0;
@@ -615,7 +614,7 @@ size_t fft_packed_scratch_words(int kind, int njobs, int log_n) {
 // apart, src[j] -> the first of them).  src[j]: packed word row of job j (2^log_n words);
 // out[j]: tile [cols][2^(log_n+1)].  Returns the number of kernels launched through *launches.
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
-                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log) {
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log, int first_half_only) {
     using namespace fft2;
 #define HOOK(name, b) do { if (hook) hook->fn(hook->user, name, b); } while (0)
     const int cpj = kind == SRC_BITS ? 32 : 4;
@@ -626,6 +625,7 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         jobs.one = 1u;
         jobs.shard_log = (shard_log > 0 && shard_log < log_n + 1) ? shard_log : log_n + 1;
         jobs.mone = 0xffffffffu;
+        jobs.halves = (first_half_only && log_n > 12 && log_n <= 20 && !g_force_generic_fft && jobs.shard_log == log_n + 1) ? 1 : 2;
         for (int j = 0; j < jobs.n; j++) { jobs.src[j] = src[j0 + j]; jobs.out[j] = out[j0 + j]; }
         if (log_n <= 12) {
             const int big = 2 << log_n;
@@ -665,7 +665,7 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
                 default: launch_mid12<8>(st, jobs, cpj, scr2, tw); break;
             }
             HOOK("fft_mid", 0);
-            dim3 gC((2u << log_n) / T2, jobs.n * gpj2);
+            dim3 gC(((unsigned)jobs.halves << log_n) / T2, jobs.n * gpj2);
             HOOK("fft_low", 1);
             fft_low12_kernel<NC><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
             HOOK("fft_low", 0);

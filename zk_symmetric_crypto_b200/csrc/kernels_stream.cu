@@ -290,6 +290,14 @@ __global__ void gather_cached_kernel(const uint32_t* __restrict__ arena, size_t 
     out[idx] = arena[(size_t)sl * tile_words + (size_t)i * M + r];
 }
 
+// out[word[t] * 32 + i] = tile_t[i][row] for up to MAX_LEAF_GROUPS tiles ([32][M] each)
+__global__ void gather_tile_row_kernel(TileRowJobs jobs, size_t M, size_t row, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= jobs.n * 32) return;
+    const int t = idx >> 5, i = idx & 31;
+    out[(size_t)jobs.word[t] * 32 + i] = jobs.tile[t][(size_t)i * M + row];
+}
+
 // component-wise basis doubling for up to 4 base-field points at once: b[c][half+k] = b[c][k] * f[c]
 __global__ void basis4_step_kernel(uint32_t* b, size_t stride, uint32_t half, uint4 f) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,6 +334,12 @@ cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32
 
 cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0) {
     strm::scale_rows_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(acc, M, trace_log, den_inv, row0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_tile_row(cudaStream_t st, const TileRowJobs& jobs, size_t M, size_t row, uint32_t* out) {
+    if (jobs.n <= 0) return cudaSuccess;
+    strm::gather_tile_row_kernel<<<(jobs.n * 32 + 127) / 128, 128, 0, st>>>(jobs, M, row, out);
     return cudaGetLastError();
 }
 

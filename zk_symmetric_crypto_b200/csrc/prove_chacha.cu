@@ -436,6 +436,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ctx->cached_tiles = n_cache;
     ctx->transient_tiles = peak_trans;
 
+    // single-GPU mode evaluates the constraints on storage rows [0, N] only (see "half-domain evaluation" below): tiles
+    // recomputed for the constraint pass need only their first half
+    const bool half_mode = G == 1;
     auto run_pass = [&](int pass, auto&& consume) {
         const size_t NG = plan.size();
         tiles.flush();
@@ -492,7 +495,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 // producer: may overwrite slots released two groups ago -> wait for that group's consumer
                 if (overlap && gi >= 2) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(NG + gi - 2), 0));
                 int nl = 0;
-                CB_CUDA(launch_fft_packed(sf, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl));
+                CB_CUDA(launch_fft_packed(sf, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl, 0,
+                                          pass == 2 && half_mode));
                 ctx->launches += nl;
                 ctx->fft_words += src.size();
                 if (overlap) {
@@ -511,6 +515,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree.  Sharded mode: every rank builds
     //      the subtree over its Mr leaves; rank 0 collects the layers, adds the top log2(G) layers and broadcasts the root.
+    DBuf<uint32_t> d_rowN(ctx, half_mode ? (size_t)N_COLS : 1);
     DevMerkle tree1;
     tree1.log_leaves = m;
     if (R == 0) tree1.nodes = DBuf<uint32_t>(ctx, (((size_t)2 << m) - 1) * 8);
@@ -535,6 +540,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             ctx->stage_end();
             ctx->launches++;
             bytes_before += 128ull * g.hash.size();
+            if (half_mode) {  // every column's value at storage row N (the one row of the second half the composition needs)
+                TileRowJobs tj{};
+                for (int w : g.hash) { tj.word[tj.n] = w; tj.tile[tj.n] = tiles.ptr(w); tj.n++; }
+                CB_CUDA(launch_gather_tile_row(st, tj, M, N, d_rowN.p));
+                ctx->launches++;
+            }
         });
         ctx->stage_begin("merkle_nodes");
         for (int l = 0; l < lr; l++) {
@@ -594,6 +605,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ch.mix_u64(counter);
     for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
 
+    std::vector<uint32_t> rowN(half_mode ? N_COLS : 0);
+    if (half_mode) CB_CUDA(cudaMemcpyAsync(rowN.data(), d_rowN.p, (size_t)N_COLS * 4, cudaMemcpyDeviceToHost, st));
     ctx->sync();
     roots.push_back(tree1.root);
     ch.mix_root(tree1.root);
@@ -623,8 +636,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // the shifted twiddle tower (host::make_twiddles(.., true)); one more row (row N, where Z_H = -v) separates c.
     // So only N + 1 of the 2N rows are evaluated; coefficients - and therefore the proof bytes - are unchanged.
     // (Row-sharded mode keeps the full-domain evaluation: the first-half rows live on half of the ranks only.)
-    const bool half_mode = G == 1;
-    const size_t cons_rows = half_mode ? std::min(M, N + 128) : 0;
+    const size_t cons_rows = half_mode ? N : 0;
     run_pass(2, [&](size_t gi, const Group& g) {
         ConstraintJobs cj{};
         for (auto& c : g.cons)
@@ -640,6 +652,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     });
     CB_CUDA(launch_scale_rows(st, accp, Mr, n, d_den.p, (size_t)R * Mr));
     ctx->launches++;
+    // reversed powers of the random coefficient on the host: the one-row evaluation below and prove()'s closing check
+    std::vector<QM31> aprh(N_CONSTRAINTS);
+    QM31 q_rowN = qzero();
+    if (R == 0) {
+        QM31 cur = qone();
+        for (int e = 0; e < N_CONSTRAINTS; e++) { aprh[N_CONSTRAINTS - 1 - e] = cur; cur = qmul(cur, random_coeff); }
+    }
+    if (half_mode) {  // the constraint sum at storage row N, on the host while the GPU works through the constraint pass
+        std::vector<QM31> mask(N_COLS);
+        for (int j = 0; j < N_COLS; j++) mask[j] = qfrom(rowN[j]);
+        q_rowN = eval_constraints_at_mask(mask, aprh);
+    }
     if (G > 1) {
         // the row shards of the accumulator go to rank 0, which finishes the proof alone (4-8 columns from here on)
         comm_group_start();
@@ -681,11 +705,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             CB_CUDA(launch_oods_dot(st, comp_coef.p, M, 4, n, bas.p, N, d_e.p));
             uint32_t e16[16], qn[4], c0[4];
             CB_CUDA(cudaMemcpyAsync(e16, d_e.p, sizeof e16, cudaMemcpyDeviceToHost, st));
-            for (int c = 0; c < 4; c++) {
-                CB_CUDA(cudaMemcpyAsync(&qn[c], acc.p + (size_t)c * M + N, 4, cudaMemcpyDeviceToHost, st));
-                CB_CUDA(cudaMemcpyAsync(&c0[c], comp_coef.p + (size_t)c * M, 4, cudaMemcpyDeviceToHost, st));
-            }
+            for (int c = 0; c < 4; c++) CB_CUDA(cudaMemcpyAsync(&c0[c], comp_coef.p + (size_t)c * M, 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
+            for (int c = 0; c < 4; c++) qn[c] = mul(q_rowN.v[c], den[1]);
             const uint32_t v = inv(den[0]), inv2v = inv(add(v, v));
             for (int c = 0; c < 4; c++) {
                 const uint32_t cc = mul(sub(e16[4 * c], qn[c]), inv2v);  // E(p*) - q(p*) = 2 v c
@@ -906,9 +928,6 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- prove()'s closing check: composition OODS value == constraints on the sampled mask / Z_H(z)
     {
-        std::vector<QM31> aprh(N_CONSTRAINTS);
-        QM31 cur = qone();
-        for (int e = 0; e < N_CONSTRAINTS; e++) { aprh[N_CONSTRAINTS - 1 - e] = cur; cur = qmul(cur, random_coeff); }
         std::vector<QM31> mask(sampled.begin(), sampled.begin() + N_COLS);
         QM31 num = eval_constraints_at_mask(mask, aprh);
         QM31 zh = coset_vanishing_q(n, z);
