@@ -129,3 +129,33 @@ def test_oracle_matches_reference_live():
     assert ref_wasm.verify_chacha20_proof(mine["proof"], nonce, counter + 1, pt, ct)["valid"] is False
     assert ref_wasm.get_circuits_info()["chacha20"] == {"cols": ca.N_COLS, "constraints": ca.N_CONSTRAINTS,
                                                         "block_bytes": 64, "key_bytes": 32}
+
+
+def test_half_domain_facts_behind_the_constraint_pass():
+    """The CUDA prover evaluates the constraints on storage rows [0, N) only.  Pinned here on the oracle:
+    (i) those rows are the circle domain with half coset g_(n+2) + <g_(n-1)>, in its own bit-reversed order;
+    (ii) the trace coset's vanishing polynomial is constant on them and takes the opposite value on rows [N, 2N);
+    (iii) the composition polynomial of a real trace is p_left + c * Z_H: its right half is one constant per coordinate."""
+    import prover as op
+    for n in (4, 5, 7):
+        N = 1 << n
+        xs, ys = sc.canonic_domain(n + 1).points_bitrev()
+        sub = sc.CircleDomain(sc.Coset(sc.subgroup_gen(n + 2), n - 1))   # initial g_(n+2), step g_(n-1)
+        sx, sy = sub.points_bitrev()
+        assert np.array_equal(xs[:N], sx) and np.array_equal(ys[:N], sy)
+        z = op.coset_vanishing_on_domain(n, n + 1)
+        assert len(set(int(v) for v in z[:N])) == 1 and len(set(int(v) for v in z[N:])) == 1
+        assert (int(z[0]) + int(z[N])) % sc.P == 0
+    key, nonce, counter, pt, ct = case_inputs(3, 7)
+    log, K, NO, C, PT, CT, mrows = oracle_api.build_chacha_inputs(key, nonce, counter, pt, ct)
+    trace, valid = ca.generate_stream_trace(log, K, NO, C, PT, CT, mrows)
+    assert valid
+    lde = sc.circle_fft(sc.circle_ifft(trace), log + 1)
+    alpha = sc.QM31(123456789, 987654321, 55555, 2147483000)
+    apr = op.secure_powers(alpha, ca.N_CONSTRAINTS)[::-1].copy()
+    acc = ca.evaluate_constraints(lde, apr)
+    acc = sc.q_mul_m31(acc, sc.m_inv(op.coset_vanishing_on_domain(log, log + 1)))
+    halves = op.finalize_composition(acc, log + 1)        # [left c0..c3, right c0..c3], 2^log coefficients each
+    for right in halves[4:]:
+        assert not np.any(right[1:])                      # only the constant term survives
+    assert any(int(r[0]) for r in halves[4:])
