@@ -28,14 +28,17 @@ __global__ void basis_step_kernel(uint32_t* b, size_t n_stride, uint32_t half, Q
     for (int c = 0; c < 4; c++) b[c * n_stride + half + k] = r.v[c];
 }
 
-// out[col] = sum_k coeffs[col][k] * basis[k]   (M31 x QM31 dot product), one block per column
+// out[col] = sum_k coeffs[col][k] * basis[k]   (M31 x QM31 dot product).  One block per (column, slice): with only a handful
+// of columns (the 4 + 4 composition coefficient columns) one block per column left 144 SMs idle (2.2 ms per launch at n = 20).
 __global__ void __launch_bounds__(256) oods_dot_kernel(const uint32_t* __restrict__ coeffs, size_t stride, uint32_t n,
                                                        const uint32_t* __restrict__ basis, size_t b_stride,
-                                                       uint32_t* __restrict__ out) {
-    const uint32_t* c = coeffs + (size_t)blockIdx.x * stride;
+                                                       uint32_t* __restrict__ out, int slices) {
+    const uint32_t col = blockIdx.x / slices, sl = blockIdx.x % slices;
+    const uint32_t len = n / slices, k0 = sl * len;
+    const uint32_t* c = coeffs + (size_t)col * stride;
     uint64_t a[4] = {0, 0, 0, 0};
     int pend = 0;
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    for (uint32_t k = k0 + threadIdx.x; k < k0 + len; k += blockDim.x) {
         uint32_t v = __ldg(c + k);
 #pragma unroll
         for (int q = 0; q < 4; q++) a[q] += (uint64_t)v * __ldg(basis + q * b_stride + k);
@@ -50,6 +53,16 @@ __global__ void __launch_bounds__(256) oods_dot_kernel(const uint32_t* __restric
         for (int t = 0; t < 256; t++) s += red[threadIdx.x][t];
         out[(size_t)blockIdx.x * 4 + threadIdx.x] = reduce64_full(s);
     }
+}
+
+// out[col][q] = sum over slices of partial[col][slice][q]
+__global__ void oods_reduce_kernel(const uint32_t* __restrict__ partial, int n_cols, int slices, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_cols * 4) return;
+    const int col = idx >> 2, q = idx & 3;
+    uint64_t s = 0;
+    for (int t = 0; t < slices; t++) s += partial[((size_t)col * slices + t) * 4 + q];
+    out[idx] = reduce64_full(s);
 }
 
 // canonic circle-domain point of storage row r (domain log m >= 2) from the twiddle tables
@@ -209,8 +222,21 @@ cudaError_t launch_basis(cudaStream_t st, uint32_t* basis, size_t stride, int lo
 cudaError_t launch_oods_dot(cudaStream_t st, const uint32_t* coeffs, size_t stride, int n_cols, int log_n, const uint32_t* basis,
                             size_t b_stride, uint32_t* out) {
     if (n_cols == 0) return cudaSuccess;
-    pcs::oods_dot_kernel<<<n_cols, 256, 0, st>>>(coeffs, stride, 1u << log_n, basis, b_stride, out);
-    return cudaGetLastError();
+    const uint32_t n = 1u << log_n;
+    int slices = 1;
+    while (n_cols * slices < 592 && (n / (2 * slices)) >= 4096) slices *= 2;
+    if (slices == 1) {
+        pcs::oods_dot_kernel<<<n_cols, 256, 0, st>>>(coeffs, stride, n, basis, b_stride, out, 1);
+        return cudaGetLastError();
+    }
+    uint32_t* partial = nullptr;
+    cudaError_t e = cudaMallocAsync(&partial, (size_t)n_cols * slices * 16, st);
+    if (e != cudaSuccess) return e;
+    pcs::oods_dot_kernel<<<n_cols * slices, 256, 0, st>>>(coeffs, stride, n, basis, b_stride, partial, slices);
+    pcs::oods_reduce_kernel<<<(n_cols * 4 + 127) / 128, 128, 0, st>>>(partial, n_cols, slices, out);
+    e = cudaGetLastError();
+    cudaFreeAsync(partial, st);
+    return e;
 }
 
 cudaError_t launch_quotients(cudaStream_t st, const uint32_t* cols, size_t stride, int n_main, const uint32_t* extra,

@@ -167,17 +167,23 @@ __global__ void scale_rows_kernel(uint32_t* __restrict__ acc, size_t M, int trac
 // 121 registers and IMAD.WIDE issuing at half rate)
 // `words` (optional): the witness words to process, one block each (the adder-sum words are skipped by the callers: their
 // values follow from their operands' by linearity); output rows are indexed by the word number.
+// blockIdx.y = row slice: a block covers rows [slice * rows_per_slice, +rows_per_slice) and, when there are several slices,
+// writes an unscaled partial sum to out[slice][1040 * 128] (summed and scaled by bitcol_reduce_kernel).  Slicing keeps all
+// SMs busy when few words are visited (62 words for the query values) and trims the last partial wave.
 __global__ void __launch_bounds__(256) bitcol_dot_kernel(const uint32_t* __restrict__ W, size_t N, const uint32_t* __restrict__ wt,
-                                                         uint32_t scale, uint32_t* __restrict__ out, const int* __restrict__ words) {
+                                                         uint32_t scale, uint32_t* __restrict__ out, const int* __restrict__ words,
+                                                         size_t rows_per_slice, size_t slice_stride) {
     const int lane = threadIdx.x & 63, bg = threadIdx.x >> 6;
     const size_t word = words ? (size_t)words[blockIdx.x] : (size_t)blockIdx.x;
     const uint32_t* __restrict__ wrow = W + word * N;
+    const size_t r_begin = (size_t)blockIdx.y * rows_per_slice;
+    const size_t r_end = r_begin + rows_per_slice < N ? r_begin + rows_per_slice : N;
     uint32_t acc[8][4];
 #pragma unroll
     for (int b = 0; b < 8; b++)
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[b][c] = 0;
-    for (size_t r = lane; r < N; r += 64) {
+    for (size_t r = r_begin + lane; r < r_end; r += 64) {
         const uint32_t w = __ldg(wrow + r) >> (8 * bg);
         uint32_t t[4];
 #pragma unroll
@@ -202,9 +208,22 @@ __global__ void __launch_bounds__(256) bitcol_dot_kernel(const uint32_t* __restr
     __syncthreads();
     if (threadIdx.x < 128) {
         const int g = threadIdx.x >> 5, x = threadIdx.x & 31;  // x = bit*4 + c
-        uint32_t v = mulm(addm(red[2 * g][x], red[2 * g + 1][x]), scale);
-        out[(word * 32 + 8 * g) * 4 + x] = v;
+        uint32_t v = addm(red[2 * g][x], red[2 * g + 1][x]);
+        if (gridDim.y == 1) v = mulm(v, scale);
+        out[(size_t)blockIdx.y * slice_stride + (word * 32 + 8 * g) * 4 + x] = v;
     }
+}
+
+// out[word][..] = scale * sum over slices of partial[slice][word][..] for the listed words
+__global__ void bitcol_reduce_kernel(const uint32_t* __restrict__ partial, size_t slice_stride, int slices, uint32_t scale,
+                                     const int* __restrict__ words, int n_words, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_words * 128) return;
+    const size_t word = words ? (size_t)words[idx >> 7] : (size_t)(idx >> 7);
+    const size_t o = word * 128 + (idx & 127);
+    uint32_t v = 0;
+    for (int s = 0; s < slices; s++) v = addm(v, partial[(size_t)s * slice_stride + o]);
+    out[o] = mulm(v, scale);
 }
 
 // g[c][r] = sum over words w, bits b of bit(W[w][r], b) * coefs[w*32+b][c]     block = 64 rows x PARTS word-slices
@@ -354,8 +373,21 @@ cudaError_t launch_gather_cached(cudaStream_t st, const uint32_t* arena, size_t 
 cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* wt, uint32_t scale,
                               uint32_t* out, const int* words_dev) {
     if (n_words <= 0) return cudaSuccess;
-    strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev);
-    return cudaGetLastError();
+    int slices = 1;
+    while (n_words * slices < 2368 && (N / (2 * slices)) >= 8192) slices *= 2;  // >= 4 waves of 592 resident blocks
+    if (slices == 1) {
+        strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        return cudaGetLastError();
+    }
+    const size_t slice_stride = (size_t)1040 * 128;  // outputs are indexed by word number (< 1040 witness words)
+    uint32_t* partial = nullptr;
+    cudaError_t e = cudaMallocAsync(&partial, slice_stride * slices * 4, st);
+    if (e != cudaSuccess) return e;
+    strm::bitcol_dot_kernel<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    strm::bitcol_reduce_kernel<<<(n_words * 128 + 255) / 256, 256, 0, st>>>(partial, slice_stride, slices, scale, words_dev, n_words, out);
+    e = cudaGetLastError();
+    cudaFreeAsync(partial, st);
+    return e;
 }
 
 cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g,
