@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -237,11 +237,11 @@ def aes_main(args, rank, local_rank, world):
 
     def step():
         return be.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
-    for _ in range(max(args.warmup, 3)):
-        proof = step()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)   # started before the warm-up: see the ChaCha path
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        proof = step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -384,11 +384,13 @@ def main():
         ms, wall_ms = sharding.max_over_ranks([ms, wall * 1000.0], device="cuda")  # multi-GPU numbers: max over ranks
         return ms, wall_ms / 1000.0, proof
 
-    for _ in range(max(args.warmup, 3)):
-        proof = step_dev()
+    # the clock sampler (nvidia-smi polling) is started before the warm-up so that its start-up (NVML initialisation takes
+    # driver locks for a few hundred ms) does not land inside the timed region; it keeps sampling through the timed steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        proof = step_dev()
     l0 = be.launch_count()
     ms, wall, proof = timed(step_dev, args.steps)
     launches = be.launch_count() - l0

@@ -1,7 +1,9 @@
-# round artefacts: default bench (both arms), launch list of one proof under ncu (978 launches per proof; 3 warm-up proofs skipped)
+# round artefacts: default bench (both arms), launch list of one proof under ncu (the 3 warm-up proofs are skipped)
 python bench.py > gpurun_out/BENCH_local_cuda.json 2> gpurun_out/BENCH_local_cuda.err; tail -c 300 gpurun_out/BENCH_local_cuda.err
+PER=$(python -c "import json; d=json.loads(open('gpurun_out/BENCH_local_cuda.json').read().strip().split(chr(10))[-1]); print(d['gpu_launches'] // d['steps'])")
+echo "launches per proof: $PER"
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/BENCH_local_ref.json 2> gpurun_out/BENCH_local_ref.err; tail -c 600 gpurun_out/BENCH_local_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 2934 -c 978 --csv --log-file gpurun_out/launches_r01_L20.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * PER)) -c $PER --csv --log-file gpurun_out/launches_r01_L20.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
 python - <<'PY'
 import csv, collections, re

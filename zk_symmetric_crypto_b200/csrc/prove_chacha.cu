@@ -394,7 +394,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         // quotient / FRI columns (~48 M words), plus slack for the allocator
         const size_t other = (scratch_words + stage_words + 96 * M) * 4 + ((size_t)3 << 30);
         const size_t tile_bytes = tile_words * 4;
-        const size_t can = avail > other ? (avail - other) / tile_bytes : 0;
+        size_t can = avail > other ? (avail - other) / tile_bytes : 0;
+        // hysteresis: free memory moves by a few MB between proofs; do not re-make a 170 GB arena to gain or lose a few tiles
+        if (ctx->arena) {
+            const size_t fixed = (scratch_off_words + scratch_words + stage_words) * 4;
+            const size_t have = ctx->arena_bytes > fixed ? (ctx->arena_bytes - fixed) / tile_bytes : 0;
+            if (have + 8 >= can && have <= can + 8) can = have;
+        }
         if (can < (size_t)peak_trans_none) throw CbError("not enough device memory for the tile arena at log_size " + std::to_string(n));
         const int cap = opt.max_cached_tiles >= 0 ? opt.max_cached_tiles : ctx->max_cached_tiles;
         if (cap >= 0 && n_cache > cap) n_cache = cap;
