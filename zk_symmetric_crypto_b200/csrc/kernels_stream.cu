@@ -297,11 +297,21 @@ __global__ void __launch_bounds__(256) bitrow_lookup_kernel(const uint32_t* __re
     for (int j = 0; j < BR_ROWS; j++)
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[j][c] = 0;
+    // the next word's table (16 KB from L2) is fetched into registers while the current word's rows are processed
+    uint4 nxt[4];
+    if (w_begin < w_end) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) nxt[e] = __ldg(T + (size_t)w_begin * 1024 + e * 256 + threadIdx.x);
+    }
     for (int wi = w_begin; wi < w_end; wi++) {
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 4; e++) tab[e * 256 + threadIdx.x] = __ldg(T + (size_t)wi * 1024 + e * 256 + threadIdx.x);
+        for (int e = 0; e < 4; e++) tab[e * 256 + threadIdx.x] = nxt[e];
         __syncthreads();
+        if (wi + 1 < w_end) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) nxt[e] = __ldg(T + (size_t)(wi + 1) * 1024 + e * 256 + threadIdx.x);
+        }
         const uint32_t* __restrict__ wrow = W + (size_t)(words ? words[wi] : wi) * N;
 #pragma unroll
         for (int j = 0; j < BR_ROWS; j++) {
