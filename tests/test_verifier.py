@@ -181,6 +181,22 @@ def test_chacha_verdicts_match_reference(chacha_ref_proof):
 
 
 @needs_ref
+@pytest.mark.parametrize("nb,seed", [(17, 2), (64, 4)])
+def test_chacha_larger_reference_proofs(nb, seed):
+    """log_size 5 and 6 (more FRI layers, deeper trees): accept, and reject like the reference on a sample of mutations."""
+    key, nonce, counter, pt, ct = case_inputs(nb, seed)
+    raw = base64.b64decode(ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof"])
+    assert z.verify_chacha20_raw(raw, nonce, counter, pt, ct) == (True, None)
+    L = Layout(raw, 84)
+    muts = [flip(raw, L.sampled[(1, 31000)][0] + 9), flip(raw, L.queried[(1, 12345)][0] + 4), flip(raw, L.decommit[1][0] + 70),
+            flip(raw, L.inner[-1][2]), flip(raw, L.inner[1][0][0]) if L.inner[1][0][1] else flip(raw, L.inner[1][1][0]),
+            flip(raw, L.last_poly[0] + 5), resize_vec(raw, L.fri_first_decommit[0], L.fri_first_decommit[1], L.fri_first_decommit[1] - 1, 32)]
+    for i, mutated in enumerate(muts):
+        mine, ref = both(z.verify_chacha20_proof, ref_wasm.verify_chacha20_proof, mutated, nonce, counter, pt, ct)
+        assert mine == ref and mine.get("valid") is not True, i
+
+
+@needs_ref
 def test_verify_input_validation_matches_reference(chacha_ref_proof):
     raw, nonce, counter, pt, ct = chacha_ref_proof
     b64 = base64.b64encode(raw).decode()

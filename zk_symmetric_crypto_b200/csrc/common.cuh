@@ -54,15 +54,6 @@ struct QuotBatch {
 
 // ---- streaming prover job lists (passed to kernels by value) ----
 #define MAX_FFT_JOBS 16
-struct CombineJob {
-    const uint32_t *a, *b, *c;  // operand tiles and carry tile, [32][M] each
-    uint32_t* res;              // sum tile (may alias a)
-};
-#define MAX_COMBINE_JOBS 16
-struct CombineJobs {
-    CombineJob j[MAX_COMBINE_JOBS];
-    int n;
-};
 enum { CJ_BOOL = 0, CJ_XOR = 1, CJ_XORN = 2, CJ_ADDX = 3 };
 struct ConstraintJob {
     const uint32_t *t0, *t1, *t2;  // tiles [32][M]: CJ_BOOL t0; CJ_XOR* r = t0, a = t1, d = t2; CJ_ADDX x = t0 (or null), a = t1, d = t2
@@ -128,7 +119,6 @@ void fft2_init_attrs();
 size_t fft_packed_scratch_words(int kind, int njobs, int log_n);
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
                               const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0, int first_half_only = 0);
-cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t M);
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
                                      const uint32_t* apr_hi, uint32_t* acc, int first, size_t rows = 0);
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi);

@@ -6,7 +6,7 @@
 // about the reference's arithmetic are used (all exact in M31/QM31, so results are bit-identical to the reference's):
 //   (1) interpolation and extension are linear.  The sum word of every 32-bit adder satisfies, bit by bit,
 //       s_i = a_i + b_i + c_{i-1} - 2 c_i on the trace domain, both sides have degree < N, hence the identity holds on the
-//       extended domain too: sum tiles are combined from operand tiles (combine_add_kernel) instead of transformed,
+//       extended domain too: sum tiles are combined from operand tiles (inside the leaf-hash and constraint kernels) instead of transformed,
 //       and the adder constraints (constraints_stream.rs:117-129) vanish identically on the evaluation domain.
 //   (2) f(z) for a column given by its trace-domain values is <values, w(z)> with w(z) = (iFFT)^T basis(z): out-of-domain
 //       samples and queried LDE values of all bit columns are masked sums over the packed witness (bitcol_dot_kernel).
@@ -21,27 +21,6 @@
 #endif
 namespace strm {
 using namespace m31d;
-
-// res_i = a_i + b_i + c_{i-1} - 2 c_i for the 32 bit-columns of a word tile [32][M]; jobs run in order inside one thread
-// (a later job may read an earlier job's result of the same row).
-__global__ void __launch_bounds__(256) combine_add_kernel(CombineJobs jobs, size_t M) {
-    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= M) return;
-    for (int j = 0; j < jobs.n; j++) {
-        const uint32_t* __restrict__ a = jobs.j[j].a + row;
-        const uint32_t* __restrict__ b = jobs.j[j].b + row;
-        const uint32_t* __restrict__ c = jobs.j[j].c + row;
-        uint32_t* __restrict__ r = jobs.j[j].res + row;
-        uint32_t cin = 0;
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            uint32_t av = a[(size_t)i * M], bv = b[(size_t)i * M], cv = c[(size_t)i * M];
-            uint32_t t = addm(addm(av, bv), cin);
-            r[(size_t)i * M] = subm(t, dbl(cv));
-            cin = cv;
-        }
-    }
-}
 
 // acc[row] += sum over jobs of sum_i apr[k] * C(row)   (apr[k] = alpha^(K-1-k), 4 coordinates, split in 16-bit halves)
 //   CJ_BOOL: C = b(1-b), b = t0[i], k = kb0 + i*step          (constraints_stream.rs:85-101)
@@ -410,13 +389,6 @@ __global__ void basis4_step_kernel(uint32_t* b, size_t stride, uint32_t half, ui
 }
 
 }  // namespace strm
-
-cudaError_t launch_combine_add(cudaStream_t st, const CombineJobs& jobs, size_t M) {
-    if (jobs.n == 0) return cudaSuccess;
-    int threads = M >= 256 ? 256 : 32;
-    strm::combine_add_kernel<<<(unsigned)((M + threads - 1) / threads), threads, 0, st>>>(jobs, M);
-    return cudaGetLastError();
-}
 
 // apr_lo / apr_hi: the reversed alpha-power table split by launch_split16
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
