@@ -159,3 +159,69 @@ def test_half_domain_facts_behind_the_constraint_pass():
     for right in halves[4:]:
         assert not np.any(right[1:])                      # only the constant term survives
     assert any(int(r[0]) for r in halves[4:])
+
+
+def _plan_combs():
+    """(sum word, operand a, operand b, carry word) of every 32-bit adder of the AIR, in trace order -- the same bookkeeping
+    as build_plan() in csrc/prove_chacha.cu (words of 32 columns: 16 initial, 80 x [S C X]x4, 16 x [S C], 16 pt, 16 ct)."""
+    combs, state = [], list(range(16))
+    for q in range(80):
+        qi, a0 = q & 7, q & 3
+        a = a0
+        if qi < 4:
+            b, c, d = 4 + a0, 8 + a0, 12 + a0
+        else:
+            b, c, d = 4 + ((a0 + 1) & 3), 8 + ((a0 + 2) & 3), 12 + ((a0 + 3) & 3)
+        base = 16 + 12 * q
+        S1, C1, X1, S2, C2, X2, S3, C3, X3, S4, C4, X4 = range(base, base + 12)
+        combs += [(S1, state[a], state[b], C1), (S2, state[c], X1, C2), (S3, S1, X2, C3), (S4, S2, X3, C4)]
+        state[a], state[b], state[c], state[d] = S3, X4, S4, X3
+    for i in range(16):
+        combs.append((976 + 2 * i, state[i], i, 977 + 2 * i))
+    return combs
+
+
+def test_adder_sum_words_follow_from_their_operands():
+    """Facts behind the CUDA prover's skipping of the 336 adder-sum words, on the oracle's trace:
+    s_i = a_i + b_i + c_(i-1) - 2 c_i (i) on the extended domain, (ii) at an out-of-domain QM31 point, and (iii) a random
+    combination of all columns equals the combination with the sum columns' coefficients folded into their operands'."""
+    key, nonce, counter, pt, ct = case_inputs(5, 11)
+    log, K, NO, C, PT, CT, mrows = oracle_api.build_chacha_inputs(key, nonce, counter, pt, ct)
+    trace, valid = ca.generate_stream_trace(log, K, NO, C, PT, CT, mrows)
+    coef = sc.circle_ifft(trace)
+    lde = sc.circle_fft(coef, log + 1).astype(np.int64)
+    combs = _plan_combs()
+    assert len(combs) == 336
+    P = int(sc.P)
+    z = sc.get_random_point(sc.Blake2sChannel())
+    rng = np.random.default_rng(3)
+    kappa = rng.integers(0, P, size=ca.N_COLS, dtype=np.int64)
+    folded = kappa.copy()
+    for (S, A, B, Cy) in reversed(combs):
+        for i in range(32):
+            k = folded[S * 32 + i]
+            folded[A * 32 + i] = (folded[A * 32 + i] + k) % P
+            folded[B * 32 + i] = (folded[B * 32 + i] + k) % P
+            folded[Cy * 32 + i] = (folded[Cy * 32 + i] - 2 * k) % P
+            if i > 0:
+                folded[Cy * 32 + i - 1] = (folded[Cy * 32 + i - 1] + k) % P
+            folded[S * 32 + i] = 0
+    full = np.zeros(trace.shape[1], dtype=object)
+    part = np.zeros(trace.shape[1], dtype=object)
+    for j in range(ca.N_COLS):
+        col = trace[j].astype(object)
+        full = full + int(kappa[j]) * col
+        if folded[j]:
+            part = part + int(folded[j]) * col
+    assert all(int(x) % P == int(y) % P for x, y in zip(full, part))
+    for (S, A, B, Cy) in combs[:8] + combs[-4:]:
+        cols = lambda w: lde[32 * w:32 * w + 32]
+        cprev = np.vstack([np.zeros((1, lde.shape[1]), dtype=np.int64), cols(Cy)[:-1]])
+        assert np.array_equal(cols(S) % P, (cols(A) + cols(B) + cprev - 2 * cols(Cy)) % P)
+        ev = lambda w: [sc.QM31(*[int(v) for v in r]) for r in sc.eval_at_point(coef[32 * w:32 * w + 32], z[0], z[1])]
+        s, a, b, c = ev(S), ev(A), ev(B), ev(Cy)
+        for i in range(32):
+            want = a[i] + b[i] - c[i] - c[i]
+            if i > 0:
+                want = want + c[i - 1]
+            assert s[i].v == want.v
