@@ -3,6 +3,7 @@
 // /root/reference/stwo/src/wasm_api.rs:24): leaf = Blake2s(LE u32 column values of the row), node = Blake2s(l || r);
 // byte layouts were confirmed by tracing the reference binary (oracle/trace_blake.py).
 #pragma once
+#include <string.h>
 #include <stdint.h>
 #ifdef __CUDACC__
 #define B2_HD __host__ __device__ __forceinline__
@@ -105,10 +106,7 @@ inline void hash(const uint8_t* data, size_t len, uint8_t out[32]) {
     uint32_t m[16];
     size_t off = 0;
     while (len - off > 64) {
-        for (int i = 0; i < 16; i++) {
-            const uint8_t* p = data + off + 4 * i;
-            m[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-        }
+        memcpy(m, data + off, 64);  // little-endian host (see above)
         off += 64;
         compress(h, m, off, false);
     }

@@ -9,6 +9,7 @@
 // prover side of this repo (which is pinned byte-for-byte against the reference).  Accept / reject decisions and error
 // renderings are checked against the reference's own verifier in tests/.
 #include <map>
+#include <thread>
 #include "prover.hpp"
 
 using namespace m31;
@@ -120,6 +121,24 @@ StarkProofData read_stark(Reader& r) {
     for (auto& q : s.last_poly) q = r.qm31();
     s.last_log = r.u32();
     return s;
+}
+
+// ChaChaPublicInputs::verify / AESCtrPublicInputs::verify (air_stream.rs:56-64, air_ctr.rs:66-76): nonce, counter and the
+// Blake2s hashes of the verifier's plaintext / ciphertext must equal the statement's.  For large inputs (this is where
+// verification time goes: 2 x 64 MiB at log_n_rows = 20) the two hashes run on two threads.
+bool public_inputs_match(const uint8_t p_nonce[12], uint32_t p_counter, const Hash32& pth, const Hash32& cth, const uint8_t nonce[12],
+                         uint32_t counter, const uint8_t* plaintext, size_t pt_len, const uint8_t* ciphertext, size_t ct_len) {
+    if (memcmp(p_nonce, nonce, 12) != 0 || p_counter != counter) return false;
+    Hash32 h1, h2;
+    if (pt_len + ct_len >= ((size_t)1 << 20)) {
+        std::thread t([&] { h1 = host::blake2s_bytes(plaintext, pt_len); });
+        h2 = host::blake2s_bytes(ciphertext, ct_len);
+        t.join();
+    } else {
+        h1 = host::blake2s_bytes(plaintext, pt_len);
+        h2 = host::blake2s_bytes(ciphertext, ct_len);
+    }
+    return memcmp(h1.b, pth.b, 32) == 0 && memcmp(h2.b, cth.b, 32) == 0;
 }
 
 // air_stream.rs:284-322 (the same function is used for AES, air_ctr.rs:628)
@@ -536,11 +555,7 @@ std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonc
 
     std::string e = validate_pcs_config(sp.cfg);
     if (!e.empty()) return e;
-    {   // ChaChaPublicInputs::verify (air_stream.rs:56-64)
-        const Hash32 h1 = host::blake2s_bytes(plaintext, pt_len), h2 = host::blake2s_bytes(ciphertext, ct_len);
-        if (memcmp(p_nonce, nonce, 12) != 0 || p_counter != counter || memcmp(h1.b, pth.b, 32) != 0 || memcmp(h2.b, cth.b, 32) != 0)
-            return "OodsNotMatching";
-    }
+    if (!public_inputs_match(p_nonce, p_counter, pth, cth, nonce, counter, plaintext, pt_len, ciphertext, ct_len)) return "OodsNotMatching";
     if (sp.commitments.size() < 2) return "OodsNotMatching";
     if (log_size < 1 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
     if (!canonical(sp)) return "InvalidStructure(\"non-canonical field element\")";
@@ -586,11 +601,7 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
 
     std::string e = validate_pcs_config(sp.cfg);
     if (!e.empty()) return e;
-    {   // AESCtrPublicInputs::verify (air_ctr.rs:66-76)
-        const Hash32 h1 = host::blake2s_bytes(plaintext, pt_len), h2 = host::blake2s_bytes(ciphertext, ct_len);
-        if (memcmp(p_nonce, nonce, 12) != 0 || p_counter != counter || memcmp(h1.b, pth.b, 32) != 0 || memcmp(h2.b, cth.b, 32) != 0)
-            return "OodsNotMatching";
-    }
+    if (!public_inputs_match(p_nonce, p_counter, pth, cth, nonce, counter, plaintext, pt_len, ciphertext, ct_len)) return "OodsNotMatching";
     if (n_ctr_inter > (1u << 16) || n_sbox_inter > (1u << 16)) return "OodsNotMatching";
     if (sp.commitments.size() < 3) return "OodsNotMatching";
     if (log_size < 8 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
