@@ -376,3 +376,51 @@ def test_operator_round_trip_on_gpu():
         assert op.groth16_verify(sig, proof) is True
         assert op.groth16_verify(dict(sig, out=bytes(len(pt))), proof) is False
         op.release()
+
+
+@needs_ref
+def test_fuzzed_proofs_get_the_reference_answer(chacha_ref_proof, aes_ref_proofs):
+    """Seeded random damage (bit flips, truncation, forged length fields, non-canonical field words, deleted / inserted
+    bytes): never an accept, never a crash, and the same JSON as the reference verifier wherever the reference itself does
+    not panic."""
+    import random
+    rnd = random.Random(20260117)
+
+    def mutate(raw):
+        r = bytearray(raw)
+        kind = rnd.randrange(6)
+        if kind == 0:
+            for _ in range(rnd.randrange(1, 4)):
+                r[rnd.randrange(len(r))] ^= 1 << rnd.randrange(8)
+        elif kind == 1:
+            r = r[:rnd.randrange(len(r))]
+        elif kind == 2:
+            p = rnd.randrange(80, 400)
+            r[p:p + 8] = struct.pack("<Q", rnd.choice([0, 1, 2, 3, 5, 1 << 20, 1 << 40, (1 << 64) - 1]))
+        elif kind == 3:
+            p = rnd.randrange(len(r))
+            r[p:p + 4] = struct.pack("<I", rnd.choice([0x7FFFFFFF, 0x80000000, 0xFFFFFFFF]))
+        elif kind == 4:
+            p = rnd.randrange(len(r))
+            del r[p:p + rnd.randrange(1, 64)]
+        else:
+            p = rnd.randrange(len(r))
+            r[p:p] = bytes(rnd.randrange(1, 64))
+        return bytes(r)
+
+    raw, nonce, counter, pt, ct = chacha_ref_proof
+    _, araw, anonce, acounter, apt, act = aes_ref_proofs[0]
+    for R, args, mine_fn, ref_fn in ((raw, (nonce, counter, pt, ct), z.verify_chacha20_proof, ref_wasm.verify_chacha20_proof),
+                                     (araw, (anonce, acounter, apt, act), z.verify_aes_ctr_proof, ref_wasm.verify_aes_ctr_proof)):
+        for i in range(60):
+            m = mutate(R)
+            if m == R:
+                continue
+            b64 = base64.b64encode(m).decode()
+            mine = mine_fn(b64, *args)
+            assert mine.get("valid") is not True, i
+            try:
+                ref = ref_fn(b64, *args)
+            except RuntimeError:        # the reference trapped (panic inside the wasm module)
+                continue
+            assert mine == ref, (i, mine, ref)

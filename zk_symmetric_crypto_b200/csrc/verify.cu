@@ -28,18 +28,26 @@ struct Reader {
     uint8_t u8() { need(1); return p[pos++]; }
     uint32_t u32() { need(4); uint32_t v = host::load_le32(p + pos); pos += 4; return v; }
     uint64_t u64() { uint64_t lo = u32(); uint64_t hi = u32(); return lo | (hi << 32); }
-    // Vec length prefix; elem = serialised size of one element (guards allocations against forged lengths)
-    size_t vec_len(size_t elem) {
+    // `usize` fields travel as u64; the reference's product build is wasm32 and rejects anything beyond 32 bits
+    uint64_t usize() {
+        uint64_t n = u64();
+        if (n > 0xFFFFFFFFull) throw VerifyFormatError("invalid value: integer `" + std::to_string(n) + "`, expected usize");
+        return n;
+    }
+    // Vec length prefix.  Elements are then read one by one (push_back), so a forged length costs no memory: reading stops
+    // with "unexpected end of file" where the input runs out, exactly where bincode stops
+    size_t vec_len() {
         uint64_t n = u64();
         // the reference's product build is wasm32: bincode rejects lengths beyond its usize before reading anything
         if (n > 0xFFFFFFFFull)
             throw VerifyFormatError("Invalid size " + std::to_string(n) + ": sizes must fit in a usize (0 to 4294967295)");
-        if (n > (len - pos) / (elem ? elem : 1)) throw VerifyFormatError("io error: unexpected end of file");
         return (size_t)n;
     }
+    size_t cap(size_t n, size_t elem) const { return std::min(n, (len - pos) / elem + 1); }  // reserve() hint
     Hash32 hash() { need(32); Hash32 h; memcpy(h.b, p + pos, 32); pos += 32; return h; }
-    // serde for M31 is a plain u32; values are reduced like M31::from on the way in would not be: keep them as sent and
-    // reject non-canonical words in the field checks below by comparing exactly
+    // serde for M31 is a plain u32: words >= p are kept as sent, like the reference does.  They cannot survive: every value is
+    // hashed into the transcript or a Merkle leaf in its raw form, so the proof fails at the check that covers that value
+    // (which is also where the reference rejects it)
     QM31 qm31() { QM31 q; for (int c = 0; c < 4; c++) q.v[c] = u32(); return q; }
 };
 
@@ -64,12 +72,12 @@ struct StarkProofData {
 
 FriLayerProof read_layer(Reader& r) {
     FriLayerProof l;
-    size_t n = r.vec_len(16);
-    l.witness.resize(n);
-    for (auto& q : l.witness) q = r.qm31();
-    n = r.vec_len(32);
-    l.decommitment.resize(n);
-    for (auto& h : l.decommitment) h = r.hash();
+    size_t n = r.vec_len();
+    l.witness.reserve(r.cap(n, 16));
+    for (size_t i = 0; i < n; i++) l.witness.push_back(r.qm31());
+    n = r.vec_len();
+    l.decommitment.reserve(r.cap(n, 32));
+    for (size_t i = 0; i < n; i++) l.decommitment.push_back(r.hash());
     l.commitment = r.hash();
     return l;
 }
@@ -79,46 +87,50 @@ StarkProofData read_stark(Reader& r) {
     s.cfg.pow_bits = r.u32();
     s.cfg.log_blowup = r.u32();
     s.cfg.log_last_layer_degree_bound = r.u32();
-    s.cfg.n_queries = r.u64();
+    s.cfg.n_queries = r.usize();
     s.cfg.fold_step = r.u32();
     uint8_t tag = r.u8();
     if (tag == 1) r.u32();
     else if (tag != 0) throw VerifyFormatError("invalid tag encoding for Option");
-    size_t n = r.vec_len(32);
-    s.commitments.resize(n);
-    for (auto& h : s.commitments) h = r.hash();
-    n = r.vec_len(8);
-    s.sampled.resize(n);
-    for (auto& t : s.sampled) {
-        t.resize(r.vec_len(8));
-        for (auto& c : t) {
-            c.resize(r.vec_len(16));
-            for (auto& q : c) q = r.qm31();
+    size_t n = r.vec_len();
+    s.commitments.reserve(r.cap(n, 32));
+    for (size_t i = 0; i < n; i++) s.commitments.push_back(r.hash());
+    n = r.vec_len();
+    for (size_t t = 0; t < n; t++) {
+        s.sampled.emplace_back();
+        const size_t nc = r.vec_len();
+        s.sampled.back().reserve(r.cap(nc, 8));
+        for (size_t c = 0; c < nc; c++) {
+            s.sampled.back().emplace_back();
+            const size_t k = r.vec_len();
+            for (size_t i = 0; i < k; i++) s.sampled.back().back().push_back(r.qm31());
         }
     }
-    n = r.vec_len(8);
-    s.decommitments.resize(n);
-    for (auto& t : s.decommitments) {
-        t.resize(r.vec_len(32));
-        for (auto& h : t) h = r.hash();
+    n = r.vec_len();
+    for (size_t t = 0; t < n; t++) {
+        s.decommitments.emplace_back();
+        const size_t k = r.vec_len();
+        s.decommitments.back().reserve(r.cap(k, 32));
+        for (size_t i = 0; i < k; i++) s.decommitments.back().push_back(r.hash());
     }
-    n = r.vec_len(8);
-    s.queried.resize(n);
-    for (auto& t : s.queried) {
-        t.resize(r.vec_len(8));
-        for (auto& c : t) {
-            c.resize(r.vec_len(4));
-            for (auto& v : c) v = r.u32();
+    n = r.vec_len();
+    for (size_t t = 0; t < n; t++) {
+        s.queried.emplace_back();
+        const size_t nc = r.vec_len();
+        s.queried.back().reserve(r.cap(nc, 8));
+        for (size_t c = 0; c < nc; c++) {
+            s.queried.back().emplace_back();
+            const size_t k = r.vec_len();
+            for (size_t i = 0; i < k; i++) s.queried.back().back().push_back(r.u32());
         }
     }
     s.pow_nonce = r.u64();
     s.first = read_layer(r);
-    n = r.vec_len(80);
-    s.inner.reserve(n);
+    n = r.vec_len();
     for (size_t i = 0; i < n; i++) s.inner.push_back(read_layer(r));
-    n = r.vec_len(16);
-    s.last_poly.resize(n);
-    for (auto& q : s.last_poly) q = r.qm31();
+    n = r.vec_len();
+    s.last_poly.reserve(r.cap(n, 16));
+    for (size_t i = 0; i < n; i++) s.last_poly.push_back(r.qm31());
     s.last_log = r.u32();
     return s;
 }
@@ -247,11 +259,12 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
     const PcsConfig& cfg = sp.cfg;
     const int n = air.log_size;
     const size_t n_trees = air.trees.size() + 1;
-    if (cfg.log_blowup > 8 || cfg.n_queries > 4096 || cfg.log_last_layer_degree_bound > 16 || cfg.fold_step > 16 || cfg.fold_step == 0)
-        return "InvalidStructure(\"PCS configuration out of range\")";
-    const int blow = (int)cfg.log_blowup;
+    // (fields far outside anything a prover emits are only rejected after the checks the reference reaches first)
+    const bool cfg_sane = cfg.log_blowup <= 8 && cfg.n_queries <= 4096 && cfg.log_last_layer_degree_bound <= 16 && cfg.fold_step <= 16;
+    const int blow = cfg_sane ? (int)cfg.log_blowup : 1;
     const int m = n + blow;  // lifting log: the largest committed column
-    if (sp.commitments.size() != n_trees) return "InvalidStructure(\"Unexpected number of commitments\")";
+    // like the reference, the composition root is the LAST commitment of the proof (callers checked there are enough)
+    auto tree_root = [&](size_t t) -> const Hash32& { return t + 1 < n_trees ? sp.commitments[t] : sp.commitments.back(); };
 
     const QM31 random_coeff = ch.draw_secure_felt();
     ch.mix_root(sp.commitments.back());
@@ -293,14 +306,15 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
     ch.mix_root(sp.first.commitment);
     std::vector<QM31> fold_alpha;
     fold_alpha.push_back(ch.draw_secure_felt());
-    int layer_bound = m - blow - 1;  // CirclePolyDegreeBound(m - blow).fold_to_line()
+    int64_t layer_bound = n - 1;  // CirclePolyDegreeBound(m - blow).fold_to_line()
     for (size_t i = 0; i < sp.inner.size(); i++) {
         ch.mix_root(sp.inner[i].commitment);
         fold_alpha.push_back(ch.draw_secure_felt());
-        if (layer_bound < (int)cfg.fold_step) return "Fri(InvalidNumFriLayers)";
-        layer_bound -= (int)cfg.fold_step;
+        if (layer_bound < (int64_t)cfg.fold_step) return "Fri(InvalidNumFriLayers)";
+        layer_bound -= (int64_t)cfg.fold_step;
     }
-    if (layer_bound != (int)cfg.log_last_layer_degree_bound) return "Fri(InvalidNumFriLayers)";
+    if (layer_bound != (int64_t)cfg.log_last_layer_degree_bound) return "Fri(InvalidNumFriLayers)";
+    if (!cfg_sane) return "InvalidStructure(\"PCS configuration out of range\")";
     if (cfg.fold_step != 1) return "InvalidStructure(\"unsupported FRI fold_step\")";
     if (sp.last_poly.size() > ((size_t)1 << cfg.log_last_layer_degree_bound)) return "Fri(LastLayerDegreeInvalid)";
     if (cfg.log_last_layer_degree_bound != 0) return "InvalidStructure(\"unsupported log_last_layer_degree_bound\")";
@@ -324,7 +338,7 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
         if (cols.empty()) {
             const Hash32 e = host::blake2s_bytes(nullptr, 0);
             if (!sp.decommitments[t].empty()) return "Merkle(WitnessTooLong)";
-            if (memcmp(e.b, sp.commitments[t].b, 32) != 0) return "Merkle(RootMismatch)";
+            if (memcmp(e.b, tree_root(t).b, 32) != 0) return "Merkle(RootMismatch)";
             continue;
         }
         int height = 0;
@@ -344,7 +358,7 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
         std::vector<uint32_t> positions;
         std::vector<std::vector<uint32_t>> lv;
         for (auto& kv : leaves) { positions.push_back(kv.first); lv.push_back(kv.second); }
-        const std::string e = merkle_verify(sp.commitments[t], logs, height, positions, lv, sp.decommitments[t]);
+        const std::string e = merkle_verify(tree_root(t), logs, height, positions, lv, sp.decommitments[t]);
         if (!e.empty()) return "Merkle(" + e + ")";
     }
 
@@ -471,16 +485,6 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
     return "";
 }
 
-bool canonical(const StarkProofData& sp) {
-    auto okq = [](const QM31& q) { return q.v[0] < P && q.v[1] < P && q.v[2] < P && q.v[3] < P; };
-    for (auto& t : sp.sampled) for (auto& c : t) for (auto& q : c) if (!okq(q)) return false;
-    for (auto& t : sp.queried) for (auto& c : t) for (auto v : c) if (v >= P) return false;
-    for (auto& q : sp.first.witness) if (!okq(q)) return false;
-    for (auto& l : sp.inner) for (auto& q : l.witness) if (!okq(q)) return false;
-    for (auto& q : sp.last_poly) if (!okq(q)) return false;
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------------ AES-CTR constraints at a point
 // Same traversal as kernels_aes.cu's constraints_kernel, on QM31 mask values, accumulating Horner-style
 // (acc = acc * random_coeff + constraint / vanishing) like the upstream PointEvaluator.
@@ -558,7 +562,6 @@ std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonc
     if (!public_inputs_match(p_nonce, p_counter, pth, cth, nonce, counter, plaintext, pt_len, ciphertext, ct_len)) return "OodsNotMatching";
     if (sp.commitments.size() < 2) return "OodsNotMatching";
     if (log_size < 1 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
-    if (!canonical(sp)) return "InvalidStructure(\"non-canonical field element\")";
 
     Channel ch;
     ch.mix_root(sp.commitments[0]);
@@ -596,7 +599,7 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
     const uint32_t p_counter = r.u32();
     const Hash32 pth = r.hash(), cth = r.hash();
     const QM31 csum = r.qm31(), tsum = r.qm31();
-    const uint64_t n_ctr_inter = r.u64(), n_sbox_inter = r.u64();
+    const uint64_t n_ctr_inter = r.usize(), n_sbox_inter = r.usize();
     const StarkProofData sp = read_stark(r);
 
     std::string e = validate_pcs_config(sp.cfg);
@@ -605,16 +608,11 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
     if (n_ctr_inter > (1u << 16) || n_sbox_inter > (1u << 16)) return "OodsNotMatching";
     if (sp.commitments.size() < 3) return "OodsNotMatching";
     if (log_size < 8 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
-    for (int c = 0; c < 4; c++)
-        if (csum.v[c] >= P || tsum.v[c] >= P) return "InvalidStructure(\"non-canonical field element\")";
-    if (!canonical(sp)) return "InvalidStructure(\"non-canonical field element\")";
 
     const int n = (int)log_size, nr = key_size == 0 ? 10 : 14;
     static const AesLayout L128 = aes_make_layout(10), L256 = aes_make_layout(14);
     const AesLayout& lay = nr == 10 ? L128 : L256;
     const int C = lay.n_cols, NL = (int)lay.lk_in.size(), NI = 4 * (NL / 2);
-    // the AIR fixes the interaction widths; a statement that claims others describes a different circuit
-    if (n_ctr_inter != (uint64_t)NI || n_sbox_inter != 4) return "InvalidStructure(\"Unexpected sampled_values structure\")";
 
     Channel ch;
     ch.mix_root(sp.commitments[0]);
@@ -634,6 +632,9 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
     }
     ch.mix_root(sp.commitments[2]);
     if (!qeq(qadd(csum, tsum), qzero())) return "OodsNotMatching";
+    // the AIR fixes the interaction widths; a statement that claims others describes a different circuit (the reference
+    // reaches this only inside verify(), after the balance check above, and panics on some values)
+    if (n_ctr_inter != (uint64_t)NI || n_sbox_inter != 4) return "InvalidStructure(\"Unexpected sampled_values structure\")";
 
     AirSpec air;
     air.log_size = n;
