@@ -48,3 +48,20 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import ref_wasm" not in txt and "stwo_core" not in txt and "oracle/" not in txt.replace("oracle/trace_blake.py", "").replace("oracle/prover.py", ""), f
+
+
+def test_raw_entry_points_validate_lengths_before_reaching_c():
+    """s2c_*_raw take key[32] / nonce[12] and one length for both buffers: the Python binding rejects anything that would make the
+    C side read past a Python object, with the reference's messages (wasm_api.rs:475-493, 660-678)."""
+    ck = z.Backend._check_raw
+    ck(bytes(32), (32,), bytes(12), 0, 64, 64, 64)
+    for args, msg in (((bytes(31), (32,), bytes(12), 0, 64, 64, 64), "Key must be 32 bytes, got 31"),
+                      ((bytes(24), (16, 32), bytes(12), 0, 16, 16, 16), "Key must be 16 or 32 bytes, got 24"),
+                      ((bytes(32), (32,), bytes(11), 0, 64, 64, 64), "Nonce must be 12 bytes, got 11"),
+                      ((bytes(32), (32,), bytes(12), 0, 0, 0, 64), "Plaintext must be non-empty multiple of 64 bytes, got 0"),
+                      ((bytes(32), (32,), bytes(12), 0, 100, 100, 64), "Plaintext must be non-empty multiple of 64 bytes, got 100"),
+                      ((bytes(32), (32,), bytes(12), 0, 128, 64, 64), "Ciphertext must be same length as plaintext, got 64 vs 128"),
+                      ((bytes(32), (32,), bytes(12), 0xFFFFFFFF, 128, 128, 64), "Counter overflow: counter 4294967295 + 2 blocks would exceed u32::MAX")):
+        with pytest.raises(z.BackendError, match=msg.replace("+", r"\+")):
+            ck(*args)
+    ck(bytes(32), (32,), bytes(12), 0xFFFFFFFF, 64, 64, 64)   # a single block at the last counter value is fine

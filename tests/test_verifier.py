@@ -98,6 +98,19 @@ def put(raw, off, val):
     return bytes(r)
 
 
+def set_lifting(raw, config_off, v):
+    """PcsConfig.lifting_log_size (the Option<u32> closing the config) := Some(v)."""
+    off = config_off + 24
+    assert raw[off] == 0
+    return raw[:off] + b"\x01" + struct.pack("<I", v) + raw[off + 1:]
+
+
+def set_last_poly(raw, n_coef, log_size):
+    """Rewrites the trailing LinePoly {coeffs: Vec<QM31>, log_size: u32} (one coefficient in every proof of the default config)."""
+    assert struct.unpack_from("<Q", raw, len(raw) - 28)[0] == 1
+    return raw[:-28] + struct.pack("<Q", n_coef) + raw[-20:-4] * n_coef + struct.pack("<I", log_size)
+
+
 def resize_vec(raw, data_off, old_n, new_n, elem):
     """Rewrites a Vec's length prefix, dropping or zero-padding elements."""
     r = bytes(raw)
@@ -152,6 +165,12 @@ def chacha_mutations(raw):
             yield "fri inner %d decommitment" % i, flip(raw, d[0] + 2)
         yield "fri inner %d commitment" % i, flip(raw, c + 2)
     yield "fri last-layer coefficient", flip(raw, L.last_poly[0])
+    log = raw[0]
+    yield "lifting_log_size = the lifting log (empty preprocessed tree has no path of that height)", set_lifting(raw, L.config, log + 1)
+    yield "lifting_log_size above the lifting log", set_lifting(raw, L.config, log + 2)
+    yield "lifting_log_size far above", set_lifting(raw, L.config, log + 4)
+    for nc, lg in ((1, 1), (1, 3), (2, 0), (2, 1), (0, 0), (0, 1), (1, 31), (1, 32), (1, 40), (4, 2)):
+        yield "last layer poly with %d coefficients, log_size %d" % (nc, lg), set_last_poly(raw, nc, lg)
     yield "truncated", raw[:-10]
     yield "truncated statement", raw[:50]
     yield "trailing bytes", raw + b"abc"
@@ -175,7 +194,7 @@ def test_chacha_verdicts_match_reference(chacha_ref_proof):
         seen.add(mine.get("error", "valid"))
     # the mutations reach every stage of the verifier
     for expected in ("OodsNotMatching", "ProofOfWork", "Merkle(RootMismatch)", "Merkle(WitnessTooShort)", "Merkle(WitnessTooLong)",
-                     "Fri(InvalidNumFriLayers)", "Fri(FirstLayerCommitmentInvalid { error: RootMismatch })",
+                     "Fri(InvalidNumFriLayers)", "Fri(FirstLayerCommitmentInvalid { error: RootMismatch })", "Fri(LastLayerDegreeInvalid)",
                      "Invalid proof format: io error: unexpected end of file", "valid"):
         assert expected in seen, (expected, sorted(seen))
 
@@ -258,6 +277,11 @@ def aes_mutations(raw, key_len):
     yield "proof of work nonce", flip(raw, L.pow)
     yield "fri first-layer witness", flip(raw, L.fri_first_witness[0])
     yield "fri last-layer coefficient", flip(raw, L.last_poly[0])
+    log = raw[0]
+    yield "lifting_log_size = the lifting log", set_lifting(raw, L.config, log + 1)   # valid at log 8, WitnessTooShort above
+    yield "lifting_log_size above the lifting log", set_lifting(raw, L.config, log + 2)
+    for nc, lg in ((1, 1), (2, 0), (0, 1), (1, 32)):
+        yield "last layer poly with %d coefficients, log_size %d" % (nc, lg), set_last_poly(raw, nc, lg)
     yield "truncated", raw[:-10]
     yield "truncated statement", raw[:100]
     yield "key size variant out of range", put(raw, 4, 2)
@@ -277,7 +301,7 @@ def test_aes_verdicts_match_reference(aes_ref_proofs):
             mine, ref = both(z.verify_aes_ctr_proof, ref_wasm.verify_aes_ctr_proof, mutated, nonce, counter, pt, ct)
             assert mine == ref, (key_len, name)
             seen.add(mine.get("error"))
-        for expected in ("OodsNotMatching", "ProofOfWork", "Merkle(RootMismatch)"):
+        for expected in ("OodsNotMatching", "ProofOfWork", "Merkle(RootMismatch)", "Fri(LastLayerDegreeInvalid)"):
             assert expected in seen, (expected, sorted(seen, key=str))
 
 
@@ -289,6 +313,22 @@ def test_aes_statement_the_reference_cannot_parse_is_rejected(aes_ref_proofs):
     for off, val in ((4, 1), (120, raw[120] ^ 1), (128, 5)):
         ok, err = z.verify_aes_ctr_raw(put(raw, off, val), nonce, counter, pt, ct)
         assert not ok and err.startswith("InvalidStructure(")
+
+
+@needs_ref
+def test_lifting_log_size_the_reference_panics_on_is_rejected(chacha_ref_proof, aes_ref_proofs):
+    """lifting_log_size below the largest committed column (or beyond the circle group) is a panic in the reference (wasm trap);
+    here it is a structured rejection, never an accept."""
+    raw, nonce, counter, pt, ct = chacha_ref_proof
+    for v in (0, raw[0], 40):
+        bad = set_lifting(raw, 84, v)
+        with pytest.raises(RuntimeError):
+            ref_wasm.verify_chacha20_proof(base64.b64encode(bad).decode(), nonce, counter, pt, ct)
+        ok, err = z.verify_chacha20_raw(bad, nonce, counter, pt, ct)
+        assert not ok and err.startswith("InvalidStructure(")
+    key_len, raw, nonce, counter, pt, ct = aes_ref_proofs[2]
+    ok, err = z.verify_aes_ctr_raw(set_lifting(raw, 136, raw[0]), nonce, counter, pt, ct)
+    assert not ok and err.startswith("InvalidStructure(")
 
 
 @needs_ref

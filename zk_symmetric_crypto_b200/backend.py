@@ -153,11 +153,28 @@ class Backend:
         return {k: int(v) for k, v in (item.split("=") for item in s.split(";") if "=" in item)}
 
     # ---- product level
+    @staticmethod
+    def _check_raw(key, key_lens, nonce, counter, pt_len, ct_len, block):
+        """The *_raw C entry points take fixed-size key / nonce arrays and ONE length for both buffers: validate here, with
+        the reference's messages (wasm_api.rs:475-493, 660-678), so that the C side never reads past a Python object."""
+        if len(key) not in key_lens:
+            raise BackendError("Key must be %s bytes, got %d" % (" or ".join(str(k) for k in key_lens), len(key)))
+        if len(nonce) != 12:
+            raise BackendError("Nonce must be 12 bytes, got %d" % len(nonce))
+        if pt_len == 0 or pt_len % block:
+            raise BackendError("Plaintext must be non-empty multiple of %d bytes, got %d" % (block, pt_len))
+        if ct_len is not None and ct_len != pt_len:
+            raise BackendError("Ciphertext must be same length as plaintext, got %d vs %d" % (ct_len, pt_len))
+        nblk = pt_len // block
+        if nblk > 1 and (counter & 0xFFFFFFFF) + nblk - 1 > 0xFFFFFFFF:
+            raise BackendError("Counter overflow: counter %d + %d blocks would exceed u32::MAX" % (counter & 0xFFFFFFFF, nblk))
+
     def prove_chacha20_raw(self, key, nonce, counter, plaintext, ciphertext):
-        kb, _ = _bytes(key)
-        nb, _ = _bytes(nonce)
         pb = bytes(plaintext)
         cbuf = bytes(ciphertext)
+        self._check_raw(bytes(key), (32,), bytes(nonce), counter, len(pb), len(cbuf), 64)
+        kb, _ = _bytes(key)
+        nb, _ = _bytes(nonce)
         out = ctypes.POINTER(ctypes.c_uint8)()
         n = ctypes.c_size_t()
         rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,
@@ -173,7 +190,10 @@ class Backend:
 
     def prove_chacha20_ptr(self, key, nonce, counter, pt_ptr, ct_ptr, nbytes, on_device=False, pt_hash=None, ct_hash=None):
         """Raw-pointer form: host pointers (e.g. pinned memory) or, with on_device=True, device pointers plus the two
-        public-input hashes.  Returns the proof bytes."""
+        public-input hashes.  Returns the proof bytes.  Both buffers must hold `nbytes` bytes (the caller owns them)."""
+        self._check_raw(bytes(key), (32,), bytes(nonce), counter, nbytes, None, 64)
+        if on_device and (pt_hash is None or ct_hash is None or len(bytes(pt_hash)) != 32 or len(bytes(ct_hash)) != 32):
+            raise BackendError("device-input proving needs the two 32-byte public-input hashes")
         kb, _ = _bytes(key)
         nb, _ = _bytes(nonce)
         out = ctypes.POINTER(ctypes.c_uint8)()
@@ -234,6 +254,7 @@ class Backend:
 
     def prove_aes_ctr_raw(self, key, nonce, counter, plaintext, ciphertext):
         key, nonce, pb, cbuf = bytes(key), bytes(nonce), bytes(plaintext), bytes(ciphertext)
+        self._check_raw(key, (16, 32), nonce, counter, len(pb), len(cbuf), 16)
         out = ctypes.POINTER(ctypes.c_uint8)()
         n = ctypes.c_size_t()
         self._ck(self.L.s2c_prove_aes_ctr_raw(self.ctx, len(key), key, nonce, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,

@@ -423,18 +423,42 @@ const char* cb_counters(cb_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------- product level
-static cb_ctx* default_ctx(std::string& err) {
-    static std::mutex mu;
-    static cb_ctx* g = nullptr;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!g) {
-        int rc = cb_init(0, &g);
-        if (rc) {
-            err = "no usable CUDA device (cb_init=" + std::to_string(rc) + "); this backend has no CPU fallback";
-            g = nullptr;
+// Calls made with ctx == NULL share ONE process-wide context (stream, arena, error string, counters): they are serialised by
+// holding its mutex for the whole call.  Callers that want concurrency create their own contexts (one per thread).
+struct CtxUse {
+    cb_ctx* ctx = nullptr;
+    std::unique_lock<std::mutex> lk;
+    std::string err;
+    explicit CtxUse(cb_ctx* given) : ctx(given) {
+        if (ctx) return;
+        static std::mutex mu;
+        static cb_ctx* g = nullptr;
+        lk = std::unique_lock<std::mutex>(mu);
+        if (!g) {
+            int rc = cb_init(0, &g);
+            if (rc) {
+                err = "no usable CUDA device (cb_init=" + std::to_string(rc) + "); this backend has no CPU fallback";
+                g = nullptr;
+            }
         }
+        ctx = g;
     }
-    return g;
+};
+
+// copies the proof into a malloc'd buffer owned by the caller (s2c_free)
+static void give_proof(const std::vector<uint8_t>& proof, uint8_t** proof_out, size_t* proof_len) {
+    uint8_t* p = (uint8_t*)malloc(proof.size() ? proof.size() : 1);
+    if (!p) throw CbError("out of host memory for the proof buffer");
+    memcpy(p, proof.data(), proof.size());
+    *proof_out = p;
+    *proof_len = proof.size();
+}
+
+// wasm_api.rs:83-86 / :675-678: the last block's counter must fit a u32
+static void check_counter(uint32_t counter, size_t num_blocks) {
+    if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
+        throw CbError("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
+                      " blocks would exceed u32::MAX");
 }
 
 static int ret_json(const std::string& s, char** out, size_t* len) {
@@ -459,19 +483,17 @@ static std::string json_error(const std::string& m) { return "{\"error\":\"" + j
 
 int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
                            const uint8_t* ct, size_t len, uint8_t** proof_out, size_t* proof_len) {
-    std::string derr;
-    if (!ctx) ctx = default_ctx(derr);
+    CtxUse use(ctx);
+    ctx = use.ctx;
     if (!ctx) return 2;
     CB_TRY(ctx)
     CB_CUDA(cudaSetDevice(ctx->device));
     if (len == 0 || len % 64) throw CbError("Plaintext must be non-empty multiple of 64 bytes, got " + std::to_string(len));
+    check_counter(counter, len / 64);
     std::vector<uint8_t> proof;
     std::string e = prove_chacha20(ctx, key, nonce, counter, pt, ct, len, proof);
     if (!e.empty()) throw CbError(e);
-    uint8_t* p = (uint8_t*)malloc(proof.size());
-    memcpy(p, proof.data(), proof.size());
-    *proof_out = p;
-    *proof_len = proof.size();
+    give_proof(proof, proof_out, proof_len);
     CB_CATCH(ctx)
 }
 
@@ -488,12 +510,10 @@ int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     opt.pt_hash = pt_hash;
     opt.ct_hash = ct_hash;
     std::vector<uint8_t> proof;
+    check_counter(counter, len / 64);
     std::string e = prove_chacha20(ctx, key, nonce, counter, nullptr, nullptr, len, proof, opt);
     if (!e.empty()) throw CbError(e);
-    uint8_t* p = (uint8_t*)malloc(proof.size());
-    memcpy(p, proof.data(), proof.size());
-    *proof_out = p;
-    *proof_len = proof.size();
+    give_proof(proof, proof_out, proof_len);
     CB_CATCH(ctx)
 }
 
@@ -513,9 +533,9 @@ static int chacha_prove_checked(cb_ctx* ctx, const uint8_t* key, size_t key_len,
     if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
         return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
                                    " blocks would exceed u32::MAX"), json_out, json_len);
-    std::string derr;
-    if (!ctx) ctx = default_ctx(derr);
-    if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
+    CtxUse use(ctx);
+    ctx = use.ctx;
+    if (!ctx) return ret_json(json_error(use.err), json_out, json_len) ? 1 : 2;
     std::string e;
     try {
         CB_CUDA(cudaSetDevice(ctx->device));
@@ -538,11 +558,15 @@ int s2c_generate_chacha20_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len,
     const int rc = chacha_prove_checked(ctx, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks, json_out,
                                         json_len);
     if (rc != -1) return rc;
-    std::string b64 = host::base64_encode(proof.data(), proof.size());
-    std::string js = "{\"algorithm\":\"chacha20\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
-                     "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 84)) +
-                     ",\"success\":true}";
-    return ret_json(js, json_out, json_len);
+    try {  // nothing may unwind across the C ABI
+        std::string b64 = host::base64_encode(proof.data(), proof.size());
+        std::string js = "{\"algorithm\":\"chacha20\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
+                         "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 84)) +
+                         ",\"success\":true}";
+        return ret_json(js, json_out, json_len);
+    } catch (const std::exception& ex) {
+        return ret_json(json_error(std::string("backend failure: ") + ex.what()), json_out, json_len) ? 1 : 1;
+    }
 }
 
 // Validation + proving shared by generate_aes*_ctr_proof and prove_aes*_ctr_encrypt; same contract as chacha_prove_checked.
@@ -562,9 +586,9 @@ static int aes_prove_checked(cb_ctx* ctx, int key_bytes, const uint8_t* key, siz
     if (num_blocks > 1 && (uint64_t)counter + num_blocks - 1 > 0xFFFFFFFFull)
         return ret_json(json_error("Counter overflow: counter " + std::to_string(counter) + " + " + std::to_string(num_blocks) +
                                    " blocks would exceed u32::MAX"), json_out, json_len);
-    std::string derr;
-    if (!ctx) ctx = default_ctx(derr);
-    if (!ctx) return ret_json(json_error(derr), json_out, json_len) ? 1 : 2;
+    CtxUse use(ctx);
+    ctx = use.ctx;
+    if (!ctx) return ret_json(json_error(use.err), json_out, json_len) ? 1 : 2;
     std::string e;
     try {
         CB_CUDA(cudaSetDevice(ctx->device));
@@ -586,11 +610,15 @@ static int aes_generate(cb_ctx* ctx, int key_bytes, const char* algorithm, const
     const int rc = aes_prove_checked(ctx, key_bytes, key, key_len, nonce, nonce_len, counter, pt, pt_len, ct, ct_len, proof, num_blocks,
                                      json_out, json_len);
     if (rc != -1) return rc;
-    std::string b64 = host::base64_encode(proof.data(), proof.size());
-    std::string js = std::string("{\"algorithm\":\"") + algorithm + "\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" + b64 +
-                     "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 136)) +
-                     ",\"success\":true}";
-    return ret_json(js, json_out, json_len);
+    try {
+        std::string b64 = host::base64_encode(proof.data(), proof.size());
+        std::string js = std::string("{\"algorithm\":\"") + algorithm + "\",\"blocks\":" + std::to_string(num_blocks) + ",\"proof\":\"" +
+                         b64 + "\",\"proof_size_bytes\":" + std::to_string(stark_proof_size_estimate(proof.data(), proof.size(), 136)) +
+                         ",\"success\":true}";
+        return ret_json(js, json_out, json_len);
+    } catch (const std::exception& ex) {
+        return ret_json(json_error(std::string("backend failure: ") + ex.what()), json_out, json_len) ? 1 : 1;
+    }
 }
 
 int s2c_generate_aes128_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
@@ -606,20 +634,18 @@ int s2c_generate_aes256_ctr_proof(cb_ctx* ctx, const uint8_t* key, size_t key_le
 
 int s2c_prove_aes_ctr_raw(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt,
                           const uint8_t* ct, size_t len, uint8_t** proof_out, size_t* proof_len) {
-    std::string derr;
-    if (!ctx) ctx = default_ctx(derr);
+    CtxUse use(ctx);
+    ctx = use.ctx;
     if (!ctx) return 2;
     CB_TRY(ctx)
     CB_CUDA(cudaSetDevice(ctx->device));
     if (key_len != 16 && key_len != 32) throw CbError("key_len must be 16 or 32");
     if (len == 0 || len % 16) throw CbError("Plaintext must be non-empty multiple of 16 bytes, got " + std::to_string(len));
+    check_counter(counter, len / 16);
     std::vector<uint8_t> proof;
     std::string e = prove_aes_ctr(ctx, key_len, key, nonce, counter, pt, ct, len, proof);
     if (!e.empty()) throw CbError(e);
-    uint8_t* p = (uint8_t*)malloc(proof.size());
-    memcpy(p, proof.data(), proof.size());
-    *proof_out = p;
-    *proof_len = proof.size();
+    give_proof(proof, proof_out, proof_len);
     CB_CATCH(ctx)
 }
 

@@ -1,9 +1,14 @@
 // NCCL through dlopen (see comm.hpp).
 #include <dlfcn.h>
 #include <string.h>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include "comm.hpp"
+#if __has_include(<nccl.h>)
+#include <nccl.h>  // enum values only; every NCCL function is resolved with dlsym below
+#define S2C_HAVE_NCCL_H 1
+#endif
 
 namespace {
 struct UniqueId { char internal[128]; };
@@ -27,8 +32,8 @@ struct Api {
 
 Api& api() {
     static Api a;
-    static bool loaded = false;
-    if (!loaded) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -44,8 +49,7 @@ Api& api() {
         a.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
         if (!a.get_id || !a.init_rank || !a.destroy || !a.group_start || !a.group_end || !a.send || !a.recv || !a.allreduce)
             throw std::runtime_error("NCCL symbols missing");
-        loaded = true;
-    }
+    });
     return a;
 }
 
@@ -55,7 +59,11 @@ void ck(int rc, const char* what) {
         throw std::runtime_error(std::string(what) + ": NCCL error " + std::to_string(rc) + " (" + s + ")");
     }
 }
-constexpr int kUint32 = 3, kInt32 = 2, kMin = 3;  // ncclUint32, ncclInt32, ncclMin (nccl.h)
+#ifdef S2C_HAVE_NCCL_H
+constexpr int kUint32 = (int)ncclUint32, kInt32 = (int)ncclInt32, kMin = (int)ncclMin;
+#else
+constexpr int kUint32 = 3, kInt32 = 2, kMin = 3;  // ncclUint32, ncclInt32, ncclMin (nccl.h of NCCL 2.x)
+#endif
 }  // namespace
 
 void comm_unique_id(uint8_t out[128]) {
@@ -86,12 +94,14 @@ void comm_recv_u32(const Comm& c, uint32_t* p, size_t words, int peer, cudaStrea
 }
 int comm_min_int(const Comm& c, int v, cudaStream_t st) {
     if (!c.active()) return v;
-    int* d = nullptr;
-    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
-    cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, st);
-    ck(api().allreduce(d, d, 1, kInt32, kMin, c.comm, st), "ncclAllReduce");
-    cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+    struct DevInt {  // freed on every path, including a throwing ck()
+        int* p = nullptr;
+        DevInt() { if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) throw std::runtime_error("cudaMalloc"); }
+        ~DevInt() { cudaFree(p); }
+    } d;
+    cudaMemcpyAsync(d.p, &v, sizeof(int), cudaMemcpyHostToDevice, st);
+    ck(api().allreduce(d.p, d.p, 1, kInt32, kMin, c.comm, st), "ncclAllReduce");
+    cudaMemcpyAsync(&v, d.p, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
-    cudaFree(d);
     return v;
 }

@@ -68,6 +68,8 @@ struct StarkProofData {
     std::vector<FriLayerProof> inner;
     std::vector<QM31> last_poly;
     uint32_t last_log = 0;
+    bool has_lifting = false;      // PcsConfig.lifting_log_size: Option<u32>
+    uint32_t lifting_log = 0;
 };
 
 FriLayerProof read_layer(Reader& r) {
@@ -90,7 +92,7 @@ StarkProofData read_stark(Reader& r) {
     s.cfg.n_queries = r.usize();
     s.cfg.fold_step = r.u32();
     uint8_t tag = r.u8();
-    if (tag == 1) r.u32();
+    if (tag == 1) { s.has_lifting = true; s.lifting_log = r.u32(); }
     else if (tag != 0) throw VerifyFormatError("invalid tag encoding for Option");
     size_t n = r.vec_len();
     s.commitments.reserve(r.cap(n, 32));
@@ -260,9 +262,20 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
     const int n = air.log_size;
     const size_t n_trees = air.trees.size() + 1;
     // (fields far outside anything a prover emits are only rejected after the checks the reference reaches first)
-    const bool cfg_sane = cfg.log_blowup <= 8 && cfg.n_queries <= 4096 && cfg.log_last_layer_degree_bound <= 16 && cfg.fold_step <= 16;
+    // n + log_blowup is bounded by 30: the circle group has order 2^31, and every shift below (queries, canonic indices, subgroup
+    // generators) is taken with an exponent derived from m
+    const bool cfg_sane = cfg.log_blowup <= 8 && (uint64_t)n + cfg.log_blowup <= 30 && cfg.n_queries <= 4096 &&
+                          cfg.log_last_layer_degree_bound <= 16 && cfg.fold_step <= 16;
     const int blow = cfg_sane ? (int)cfg.log_blowup : 1;
     const int m = n + blow;  // lifting log: the largest committed column
+    // PcsConfig.lifting_log_size = Some(v) makes v the height of EVERY tree (None: each tree's own largest column) and the log
+    // every component is lifted to.  Behaviour of the reference verifier, pinned in tests/test_verifier.py: v below the largest
+    // committed column is a panic (wasm trap; reported as InvalidStructure here, like the other inputs that trap there);
+    // v above it moves every mask point, so the composition check fails (OodsNotMatching); v equal to it keeps the points, and
+    // a tree whose own columns are smaller (ChaCha's empty preprocessed tree, the AES S-box table tree above log 8) then has
+    // too few witness hashes for a tree of height v (Merkle(WitnessTooShort)).
+    const bool lift_all = sp.has_lifting;
+    if (lift_all && (sp.lifting_log < (uint32_t)m || sp.lifting_log > 30)) return "InvalidStructure(\"lifting_log_size out of range\")";
     // like the reference, the composition root is the LAST commitment of the proof (callers checked there are enough)
     auto tree_root = [&](size_t t) -> const Hash32& { return t + 1 < n_trees ? sp.commitments[t] : sp.commitments.back(); };
 
@@ -290,6 +303,7 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
         const QM31 got = qadd(from_coords(lc), qmul(pix, from_coords(rc)));
         const QM31 expect = composition(Z, sp.sampled, random_coeff);
         if (!qeq(got, expect)) return "OodsNotMatching";
+        if (lift_all && sp.lifting_log != (uint32_t)m) return "OodsNotMatching";  // components lifted past their own domain
     }
 
     // ---- CommitmentSchemeVerifier::verify_values
@@ -316,7 +330,9 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
     if (layer_bound != (int64_t)cfg.log_last_layer_degree_bound) return "Fri(InvalidNumFriLayers)";
     if (!cfg_sane) return "InvalidStructure(\"PCS configuration out of range\")";
     if (cfg.fold_step != 1) return "InvalidStructure(\"unsupported FRI fold_step\")";
-    if (sp.last_poly.size() > ((size_t)1 << cfg.log_last_layer_degree_bound)) return "Fri(LastLayerDegreeInvalid)";
+    // LinePoly::len() is 1 << log_size on the reference's 32-bit usize (the shift count wraps), whatever the number of
+    // coefficients sent; the coefficients are mixed as sent
+    if (((uint64_t)1 << (sp.last_log & 31)) > ((uint64_t)1 << cfg.log_last_layer_degree_bound)) return "Fri(LastLayerDegreeInvalid)";
     if (cfg.log_last_layer_degree_bound != 0) return "InvalidStructure(\"unsupported log_last_layer_degree_bound\")";
     ch.mix_felts(sp.last_poly.data(), sp.last_poly.size());
 
@@ -335,7 +351,7 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
             if (c.size() > nq) return "Merkle(TooManyQueriedValues)";
             if (c.size() < nq) return "Merkle(TooFewQueriedValues)";
         }
-        if (cols.empty()) {
+        if (cols.empty() && !lift_all) {
             const Hash32 e = host::blake2s_bytes(nullptr, 0);
             if (!sp.decommitments[t].empty()) return "Merkle(WitnessTooLong)";
             if (memcmp(e.b, tree_root(t).b, 32) != 0) return "Merkle(RootMismatch)";
@@ -344,6 +360,7 @@ std::string verify_stark(const AirSpec& air, Channel& ch, const StarkProofData& 
         int height = 0;
         std::vector<int> logs;
         for (auto& c : cols) { logs.push_back(c.log + blow); height = std::max(height, c.log + blow); }
+        if (lift_all) height = m;
         // leaf positions on this tree and, per leaf, the values of all columns (a column of a smaller size repeats its value
         // on all leaves that lift to the same index; the queried values must agree where queries collide)
         std::map<uint32_t, std::vector<uint32_t>> leaves;
