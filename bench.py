@@ -111,22 +111,54 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(log_sample, steps, warmup):
-    """Times the reference's own prover (oracle/_ref) on this box's host cores: 2^log_sample blocks per proof."""
+def _ref_worker(args):
+    """One reference proof in this process (the reference binary is single-threaded and keeps global state: one process each)."""
+    log_sample, rank = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_wasm
-    import numpy as np
-    key, nonce, counter, pt, ct = synth_inputs(log_sample, 0)
+    key, nonce, counter, pt, ct = synth_inputs(log_sample, rank)
     ptb, ctb = pt.tobytes(), ct.tobytes()
+    t0 = time.perf_counter()
+    res = ref_wasm.generate_chacha20_proof(key, nonce, counter, ptb, ctb)
+    dt = time.perf_counter() - t0
+    assert res.get("success") is True, res
+    return dt
+
+
+def cpu_reference_run(log_sample, steps, warmup, procs=1):
+    """Times the reference's own prover (oracle/_ref) on this box's host cores: 2^log_sample blocks per proof.
+    procs > 1: that many independent reference proofs at once, one process per host core (the reference has no threads of its
+    own -- no rayon in its Cargo.lock -- so independent proofs are the only way it uses more than one core).
+    Returns (seconds per step, proofs per step)."""
+    if procs <= 1:
+        times = []
+        for i in range(warmup + steps):
+            dt = _ref_worker((log_sample, 0))
+            if i >= warmup:
+                times.append(dt)
+        return sum(times) / len(times), 1
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        res = ref_wasm.generate_chacha20_proof(key, nonce, counter, ptb, ctb)
-        dt = time.perf_counter() - t0
-        assert res.get("success") is True, res
-        if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times)
+    with ctx.Pool(procs) as pool:
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(log_sample, r) for r in range(procs)])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), procs
+
+
+def host_parallelism(log_sample):
+    """Processes the reference arm can run at once: one per host core, bounded by memory (a 2^log_sample-block reference proof
+    needs ~0.4 MB per block of its wasm32 address space)."""
+    cores = os.cpu_count() or 1
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 8 << 30
+    per_proc = max(int(0.45e6 * (1 << log_sample)), 256 << 20)
+    return max(1, min(cores, int(avail * 0.7) // per_proc))
 
 
 def synth_aes_inputs(key_len, log_n, rank):
@@ -285,6 +317,86 @@ def aes_main(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def load_json(*parts):
+    try:
+        return json.load(open(os.path.join(ROOT, *parts)))
+    except Exception:
+        return None
+
+
+def int_peaks():
+    """Measured integer roofs of this GPU family (profiles/microbench/int_peak.cu run on a B200, result committed as
+    profiles/int_peak_r02.json): register-resident M31 butterflies/s and Blake2s half-G/s with every SM busy, plus the raw
+    ALU-pipe / FMA-pipe instruction rates they follow from."""
+    doc = load_json("profiles", "int_peak_r02.json")
+    if not doc:
+        return None
+    r = {x["op"]: x for x in doc["results"]}
+    return {"butterflies_per_s": r["BFLY_CUR"]["items_per_s"], "blake2s_half_g_per_s": r["BLAKE_G"]["items_per_s"],
+            "alu_pipe_thread_instr_per_s": r["LOP3"]["thread_instr_per_s"], "fma_pipe_imad_per_s": r["IMAD"]["thread_instr_per_s"],
+            "imad_wide_per_s": r["IMADWIDE"]["thread_instr_per_s"], "source": "profiles/int_peak_r02.json (profiles/microbench/int_peak.cu)"}
+
+
+def verify_proof(proof, nonce, counter, ptb, ctb):
+    """Checks the timed proof outside the timed region: the reference's own verifier when oracle/_ref travelled to this box
+    (checker only), else this repo's host verifier."""
+    import base64
+    import zk_symmetric_crypto_b200 as z
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_wasm
+        if ref_wasm.available():
+            t0 = time.perf_counter()
+            v = ref_wasm.verify_chacha20_proof(base64.b64encode(proof).decode(), nonce, counter, ptb, ctb)
+            return {"by": "reference", "ok": v == {"algorithm": "chacha20", "valid": True}, "seconds": round(time.perf_counter() - t0, 2),
+                    "verifier": "oracle/_ref verify_chacha20_proof (wasm_api.rs:609)"}
+    except Exception as ex:
+        note = "reference verifier unavailable: %s" % ex
+    else:
+        note = "oracle/_ref not on this box"
+    ok, err = z.verify_chacha20_raw(proof, nonce, counter, ptb, ctb)
+    return {"by": "host", "ok": bool(ok), "error": err, "note": note}
+
+
+def aes_measure(z, torch, local_rank, key_len, L, steps, warmup, rank=0):
+    """One AES-CTR workload on its own context: device-event time of `steps` proofs through the host-buffer C ABI (inputs are 16
+    bytes per row, so end to end is the only meaningful figure) and the per-stage times of one profiled proof."""
+    be = z.Backend(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    be.set_stream(stream.cuda_stream)
+    key, nonce, counter, pt, ct = synth_aes_inputs(key_len, L, rank)
+    try:
+        for _ in range(warmup):
+            proof = be.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
+        torch.cuda.synchronize()
+        l0 = be.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            proof = be.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = (be.launch_count() - l0) // steps
+        be.set_profile(True)
+        be.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
+        stages = be.stage_times()
+        ok, err = z.verify_aes_ctr_raw(proof, nonce, counter, pt, ct)
+    finally:
+        be.close()
+    return {"ms_per_proof": ms, "launches_per_proof": launches, "stage_ms": stages, "proof_bytes": len(proof),
+            "h2d_bytes": 2 * len(pt), "verified": {"by": "host", "ok": bool(ok), "error": err}}
+
+
+def aes_roofline(cols, L, stages, hbm_peak):
+    lde_ms = stages.get("trace_lde", 0.0)
+    alg = (cols + 1) * (1 << L) * 20   # SURVEY 8(d): 8CN (interpolate) + 12CN (evaluate on the blown-up domain) per column
+    gbs = alg / (lde_ms / 1000.0) / 1e9 if lde_ms else None
+    nk = (load_json("profiles", "ncu_kernels_r02.json") or {}).get("aes_trace_lde")
+    return {"kernel": "trace_lde", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if gbs else None,
+            "traffic": nk["dram_bytes"] if nk else None, "algorithmic_bytes_per_proof": alg}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,8 +404,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--log-size", type=int, default=int(os.environ.get("S2C_BENCH_LOG", "20")))
-    ap.add_argument("--cpu-log-size", type=int, default=10, help="size of the bounded CPU-reference sample")
+    ap.add_argument("--cpu-log-size", type=int, default=None, help="size of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the AES-CTR / proof-batch / sharded sub-records")
     ap.add_argument("--workload", default="chacha20", choices=["chacha20", "chacha20_sharded", "aes128", "aes256"],
                     help="chacha20 (BASELINE configs[1], the headline) or an AES-CTR AIR (configs[2])")
     args = ap.parse_args()
@@ -312,18 +425,28 @@ def main():
                            "leaf hashing / constraints" if sharded else "independent proofs, one per rank, no data-path collective")}
 
     if args.impl == "reference":
+        # The reference's own prover on this box's host cores.  It cannot hold the workload (2^20 blocks need ~560 GB; its
+        # wasm32 build stops at 2^13), so each step is a bounded sample: the LARGEST trace it proves within the time budget
+        # (2^12 blocks, ~40 s), on every host core at once (independent proofs, one process per core: it has no threads of its
+        # own), and the line says that the proofs/s figure is an extrapolation (linear in rows, optimistic for the CPU).
         if rank != 0:
             return
-        S = args.cpu_log_size
-        sec = cpu_reference_run(S, max(1, min(args.steps, 3)), 1 if args.warmup else 0)
-        # scale to the workload's unit: prover cost is ~linear in rows at fixed column count (optimistic for the CPU)
-        scaled = 1.0 / (sec * (1 << (L - S))) if L >= S else 1.0 / sec
+        S = args.cpu_log_size if args.cpu_log_size is not None else min(L, 12)
+        procs = host_parallelism(S)
+        sec, per_step = cpu_reference_run(S, max(1, min(args.steps, 2)), 0, procs)
+        sec1, _ = cpu_reference_run(min(S, 10), 1, 0, 1)
+        scale = (1 << (L - S)) if L >= S else 1
+        scaled = per_step / (sec * scale)
         line = {"impl": "reference", "metric": "chacha20_proofs_per_sec", "value": scaled, "unit": "proofs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / scaled, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32(M31)", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": scaled, "unit": "proofs/s", "cores": 1, "kind": "reference",
-                                 "sample": "reference prover (shipped WASM build compiled natively, single-threaded as shipped) on "
-                                           "2^%d blocks: %.3f s/proof, linearly scaled to 2^%d blocks" % (S, sec, L)},
+                "extrapolated": True, "from_log": S, "extrapolation": "measured at 2^%d blocks per proof, divided by %d (linear in rows)" % (S, scale),
+                "cpu_baseline": {"value": scaled, "unit": "proofs/s", "cores": procs, "host_cores": os.cpu_count(), "kind": "reference",
+                                 "extrapolated": True, "from_log": S,
+                                 "single_process_2^%d_blocks_s" % min(S, 10): sec1,
+                                 "sample": "reference prover (shipped WASM build compiled natively; no SIMD, no threads of its own) on "
+                                           "2^%d blocks per proof, %d independent proofs at once on %d of %d host cores: %.2f s per batch; "
+                                           "scaled linearly to 2^%d blocks" % (S, per_step, procs, os.cpu_count() or 0, sec, L)},
                 "e2e": {"value": scaled, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -341,24 +464,27 @@ def main():
     stream = torch.cuda.Stream(device=local_rank)
     be.set_stream(stream.cuda_stream)
     key, nonce, counter, pt, ct = synth_inputs(L, 0 if sharded else rank)
-    if sharded and world > 1:
+
+    def join_comm(backend_obj):
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.tensor(list(z.backend.comm_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
-        be.comm_init(rank, world, bytes(uid.cpu().tolist()))
+        backend_obj.comm_init(rank, world, bytes(uid.cpu().tolist()))
+
+    if sharded and world > 1:
+        join_comm(be)
     nbytes = pt.nbytes
     # pinned host copies (e2e path) and device-resident copies (value path)
     pt_pin = torch.from_numpy(pt.view(np.int32)).pin_memory()
     ct_pin = torch.from_numpy(ct.view(np.int32)).pin_memory()
     pt_dev = pt_pin.to("cuda:%d" % local_rank)
     ct_dev = ct_pin.to("cuda:%d" % local_rank)
-    pt_hash = hashlib.blake2s(pt.tobytes()).digest()
-    ct_hash = hashlib.blake2s(ct.tobytes()).digest()
 
     def step_dev():
-        return be.prove_chacha20_ptr(key, nonce, counter, pt_dev.data_ptr(), ct_dev.data_ptr(), nbytes, on_device=True,
-                                     pt_hash=pt_hash, ct_hash=ct_hash)
+        # inputs resident in HBM; the two public-input Blake2s hashes (host work in the reference too) are computed inside the
+        # call from a read-back of the buffers, so `value` skips nothing that `e2e` does except the H2D copies
+        return be.prove_chacha20_ptr(key, nonce, counter, pt_dev.data_ptr(), ct_dev.data_ptr(), nbytes, on_device=True)
 
     def step_e2e():
         return be.prove_chacha20_ptr(key, nonce, counter, pt_pin.data_ptr(), ct_pin.data_ptr(), nbytes)
@@ -399,65 +525,107 @@ def main():
     ms_e2e, wall_e2e, proof_e2e = timed(step_e2e, args.steps)
     if rank == 0 or not sharded:
         assert proof_e2e == proof, "host-input and device-input paths must give the same proof"
+    # the proof that was timed, checked outside the timed region
+    verified = verify_proof(proof, nonce, counter, pt.tobytes(), ct.tobytes()) if rank == 0 else None
     # one profiled step for the per-kernel breakdown (CUDA events on the launching stream around each kernel)
     be.set_profile(True)
     step_dev()
     stages = be.stage_times()
+    cnt = be.counters()
     be.set_profile(False)
 
-    if rank == 0:
-        peaks = {}
+    # ---- cfg-5 on the driver's hardware: under torchrun the same ranks additionally prove ONE trace together (rank 0's inputs)
+    #      and rank 0 checks the bytes against its own single-GPU proof of those inputs
+    sharded_rec = None
+    if world > 1 and not sharded and not args.no_extras and L >= 16:
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+            key0, nonce0, counter0, pt0, ct0 = synth_inputs(L, 0) if rank else (key, nonce, counter, pt, ct)
+            p0, c0 = pt0.tobytes(), ct0.tobytes()
+            join_comm(be)
+            times = []
+            for it in range(3):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sp = be.prove_chacha20_raw(key0, nonce0, counter0, p0, c0)
+                e1.record(stream)
+                barrier()
+                if it:
+                    times.append(sharding.max_over_ranks([e0.elapsed_time(e1)], device="cuda")[0])
+            be.set_profile(True)
+            be.prove_chacha20_raw(key0, nonce0, counter0, p0, c0)
+            sst = be.stage_times()
+            be.set_profile(False)
+            a2a = sharding.max_over_ranks([sst.get("all_to_all", 0.0)], device="cuda")[0]
+            be.comm_destroy()
+            if rank == 0:
+                sharded_rec = {"workload": "ONE chacha20 trace log_n_rows=%d over %d GPUs (column-sharded transforms, NCCL all-to-all of "
+                                           "LDE row shards, row-sharded hashing / constraints)" % (L, world),
+                               "ms": min(times), "ms_all": times, "parity": sp == proof, "single_gpu_ms": ms / args.steps,
+                               "speedup_vs_single_gpu": (ms / args.steps) / min(times), "all_to_all_ms": a2a,
+                               "stage_ms_rank0_profiled": sst, "h2d_bytes": 2 * nbytes,
+                               "timing": "CUDA events on the launching stream around the host-buffer C-ABI call, barrier on both sides, max over ranks"}
+        except Exception as ex:  # never lose the headline line to the extra record
+            if rank == 0:
+                sharded_rec = {"error": str(ex)[:300], "parity": False}
+
+    line = None
+    if rank == 0:
+        peaks = load_json("MEASURED_PEAKS.json") or {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         N = 1 << L
-        cnt = be.counters()
         cols_t = 32 * cnt.get("fft_words", 0)           # columns transformed from the packed witness (both passes)
-        n_dep_tiles = 2 * 336                            # adder-sum tiles combined (both passes)
-        tile_b = 32 * 2 * N * 4
-        # ALGORITHMIC bytes per proof of each kernel family: per column, iFFT reads the packed bits
-        # and writes N words, the strided pass reads N and writes 2N, the last pass reads and writes 2N (SURVEY 8d:
-        # 8CN + 12CN); leaves and constraints read every LDE value once.
+        # ALGORITHMIC bytes (SURVEY 8d / DESIGN.md section 5).  Transforms: per column interpolate reads N + writes N words and
+        # evaluate reads N + writes 2N = 20 N bytes (the three-pass pipeline's own scratch traffic is NOT algorithmic: it is
+        # reported as `pipeline_bytes`); columns recomputed on half of the domain count 14 N.  Leaves and constraints read every
+        # LDE value they use once.
+        half_words = cnt.get("fft_words_half", 0)
+        full_words = cnt.get("fft_words", 0) - half_words
+        fft_alg = 32 * N * (20 * full_words + 14 * half_words)
+        fft_pipeline = cols_t * N * ((1 / 8 + 4) + (4 + 8) + (8 + 8))
+        # butterflies per column: interpolate L layers of N/2, evaluate L layers of N/2 on each half of the 2N-point domain
+        butterflies = 32 * N * (full_words * 1.5 * L + half_words * 1.0 * L)
         alg = {
-            "ifft_low": cols_t * N * (1 / 8 + 4),
-            "fft_mid": cols_t * N * (4 + 8),
-            "fft_low": cols_t * N * (8 + 8),
-            "fft_small": cols_t * N * (1 / 8 + 8),
-            "combine": n_dep_tiles * 4 * tile_b,
-            "trace_merkle_leaves": N_COLS * 2 * N * 4 + 2 * (2 * N * 32) * 85,
-            "constraints": N_COLS * 2 * N * 4 + 2 * (4 * 2 * N * 4) * 85,
+            "fft": fft_alg,
+            "trace_merkle_leaves": N_COLS * 2 * N * 4 + 2 * N * 32,
+            "constraints": 22528 * N * 4 + 4 * 2 * N * 4,   # single-GPU mode evaluates storage rows [0, N)
         }
         fft_ms = sum(stages.get(k, 0.0) for k in ("ifft_low", "fft_mid", "fft_low", "fft_small"))
-        fft_bytes = sum(alg[k] for k in ("ifft_low", "fft_mid", "fft_low", "fft_small") if stages.get(k))
-        top = max((k for k in stages if k in alg), key=lambda k: stages[k], default=None)
-        roofline = None
-        if top:
-            achieved = alg[top] / (stages[top] / 1000.0) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_proof": alg[top], "kernel_ms_per_proof": stages[top],
-                        "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5 for instruction counts",
-                        "fft_all_passes": {"ms": fft_ms, "GB/s": fft_bytes / (fft_ms / 1000.0) / 1e9 if fft_ms else None,
-                                           "frac": fft_bytes / (fft_ms / 1000.0) / 1e9 / hbm_peak if fft_ms else None,
-                                           "columns_transformed": cols_t},
-                        "all_kernels_gbs": {k: alg[k] / (stages[k] / 1000.0) / 1e9 for k in stages if k in alg and stages[k] > 0},
-                        "counters": cnt}
-        if roofline:
-            # measured DRAM traffic / pipe utilisation of the same kernel from the committed ncu capture (one launch)
-            try:
-                nk = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels_r01.json"))).get(top)
-            except Exception:
-                nk = None
-            if nk and L == 20:
-                roofline["traffic"] = nk["dram_bytes"]
-                roofline["traffic_unit"] = "DRAM bytes read+written by ONE launch (ncu --set full); that launch's algorithmic bytes: %s" % (
-                    nk.get("launch_algorithmic_bytes"))
-                roofline["int_pipe"] = {k: nk[k] for k in ("kernel", "launch_ms", "issue_active_pct", "alu_pipe_pct", "fma_pipe_pct",
-                                                           "dram_pct", "registers") if k in nk}
-                roofline["int_pipe"]["source"] = "profiles/ncu_kernels_r01.json"
+        kern_ms = {"fft": fft_ms, "trace_merkle_leaves": stages.get("trace_merkle_leaves", 0.0), "constraints": stages.get("constraints", 0.0)}
+        top = max(kern_ms, key=lambda k: kern_ms[k])
+        ncu = load_json("profiles", "ncu_kernels_r02.json") or {}
+        ip = int_peaks()
+        compressions = 2 * N * (N_COLS * 4 // 64)
+        int_roof = {}
+        if ip:
+            # integer roofs, measured (profiles/int_peak_r02.json): a Blake2s compression is 160 half-G; a butterfly is the 7-instruction
+            # M31 butterfly of kernels_fft2.cu timed register-resident with every SM busy
+            if kern_ms["trace_merkle_leaves"]:
+                a = compressions / (kern_ms["trace_merkle_leaves"] / 1000.0)
+                pk = ip["blake2s_half_g_per_s"] / 160.0
+                int_roof["trace_merkle_leaves"] = {"bound": "int", "achieved": a / 1e9, "peak": pk / 1e9, "unit": "Gcompress/s", "frac": a / pk}
+            if fft_ms:
+                a = butterflies / (fft_ms / 1000.0)
+                pk = ip["butterflies_per_s"]
+                int_roof["fft"] = {"bound": "int", "achieved": a / 1e9, "peak": pk / 1e9, "unit": "Gbutterfly/s", "frac": a / pk}
+        achieved = alg[top] / (kern_ms[top] / 1000.0) / 1e9 if kern_ms[top] else None
+        nk = ncu.get({"fft": "fft_passes", "trace_merkle_leaves": "leaves_kernel", "constraints": "constraints_tiles_kernel"}[top])
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak if achieved else None,
+                    "traffic": nk.get("dram_bytes_per_proof") if nk else None,
+                    "traffic_source": (nk.get("source") if nk else None), "peak_source": peak_src,
+                    "algorithmic_bytes_per_proof": alg[top], "kernel_ms_per_proof": kern_ms[top],
+                    "int": int_roof.get(top),
+                    "note": "the dominant kernels are integer-pipe bound (Blake2s: ALU pipe; M31 butterflies: ALU + FMA pipes), so the "
+                            "integer fraction is the one that says how close the kernel is to its roof; see DESIGN.md section 5",
+                    "all_kernels": {k: {"ms": kern_ms[k], "algorithmic_bytes": alg[k],
+                                        "hbm_frac": alg[k] / (kern_ms[k] / 1000.0) / 1e9 / hbm_peak if kern_ms[k] else None,
+                                        "int": int_roof.get(k)} for k in kern_ms},
+                    "fft_all_passes": {"ms": fft_ms, "algorithmic_GB/s": fft_alg / (fft_ms / 1000.0) / 1e9 if fft_ms else None,
+                                       "frac": fft_alg / (fft_ms / 1000.0) / 1e9 / hbm_peak if fft_ms else None,
+                                       "pipeline_bytes": fft_pipeline, "columns_transformed": cols_t, "butterflies": butterflies},
+                    "int_peaks": ip, "counters": cnt}
         per_step = 1 if sharded else world
         value = per_step * args.steps / (ms / 1000.0)
         e2e_value = per_step * args.steps / (ms_e2e / 1000.0)
@@ -468,21 +636,90 @@ def main():
                 "blocks_per_sec": value * N, "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": len(proof_e2e),
                         "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1000.0 / args.steps},
-                "wall_ms_per_step": wall * 1000.0 / args.steps, "stage_ms": stages, "roofline": roofline}
+                "wall_ms_per_step": wall * 1000.0 / args.steps, "verified": verified, "stage_ms": stages, "roofline": roofline}
+        if sharded_rec:
+            line["sharded"] = sharded_rec
+    be.close()
+
+    # ---- sub-records the driver would otherwise never see (each on fresh contexts, after the headline's arena is released)
+    if not args.no_extras and not sharded:
+        extras = {}
+        try:
+            extras = extra_records(z, torch, dist, sharding, local_rank, rank, world, line)
+        except Exception as ex:
+            extras = {"error": str(ex)[:300]}
+        if rank == 0:
+            line.update(extras)
+
+    if rank == 0:
         if not args.no_cpu_baseline:
-            S = args.cpu_log_size
+            S = args.cpu_log_size if args.cpu_log_size is not None else min(L, 10)
             try:
-                sec = cpu_reference_run(S, 1, 0)
-                scaled = 1.0 / (sec * (1 << (L - S))) if L >= S else 1.0 / sec
-                line["cpu_baseline"] = {"value": scaled, "unit": "proofs/s", "cores": 1, "kind": "reference",
+                sec, _ = cpu_reference_run(S, 1, 0)
+                scale = (1 << (L - S)) if L >= S else 1
+                scaled = 1.0 / (sec * scale)
+                line["cpu_baseline"] = {"value": scaled, "unit": "proofs/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "reference",
+                                        "extrapolated": True, "from_log": S,
                                         "sample": "reference prover (oracle/_ref: shipped WASM build compiled natively, 1 thread as "
-                                                  "shipped) on 2^%d blocks: %.3f s/proof, linearly scaled to 2^%d blocks" % (S, sec, L)}
+                                                  "shipped) on 2^%d blocks: %.3f s/proof, linearly scaled to 2^%d blocks (the reference "
+                                                  "cannot hold more than 2^13)" % (S, sec, L)}
             except Exception as ex:  # oracle/_ref absent on this box
                 line["cpu_baseline"] = {"value": None, "unit": "proofs/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % ex}
         print(json.dumps(line))
-    be.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_records(z, torch, dist, sharding, local_rank, rank, world, line):
+    """BASELINE configs[2] (AES-128/256-CTR, log 16) and SURVEY 8(d) cfg-4 (batches of independent product-size proofs sharded
+    round-robin over the ranks) as sub-records of the default run."""
+    import hashlib
+    out = {}
+    peaks = load_json("MEASURED_PEAKS.json") or {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if rank == 0:
+        aes = {}
+        for name, key_len, cols in (("aes128", 16, 24480), ("aes256", 32, 34784)):
+            r = aes_measure(z, torch, local_rank, key_len, 16, 3, 2)
+            r["workload"] = "%s_ctr log_n_rows=16 blowup=2, one proof of 65,536 16-byte blocks through the host-buffer C ABI" % name
+            r["proofs_per_sec"] = 1000.0 / r["ms_per_proof"]
+            r["roofline"] = aes_roofline(cols, 16, r["stage_ms"], hbm_peak)
+            aes[name + "_log16"] = r
+        out["aes_ctr"] = aes
+    # cfg-4: n=4 x 4096 and n=12 x 64 independent ChaCha20 proofs, seeds 0..B-1, round-robin over the ranks, several contexts per GPU
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_golden import case_inputs
+    from zk_symmetric_crypto_b200.pool import ProverPool
+    batches = {}
+    for label, nb, count, nctx in (("log4_x4096", 2, 4096, 16), ("log12_x64", 4096, 64, 4)):
+        inputs = [case_inputs(nb, seed % 8) for seed in range(min(count, 8))]   # 8 distinct inputs cycled (host-side generation is slow)
+        mine = sharding.shard_indices(count, world, rank)
+        pool = ProverPool(local_rank, nctx)
+        try:
+            jobs = [("chacha20_raw",) + tuple(inputs[i % len(inputs)]) for i in mine]
+            pool.prove_many(jobs[:nctx])    # warm-up: twiddles, arenas
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            proofs = pool.prove_many(jobs)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            dt = time.perf_counter() - t0
+        finally:
+            pool.close()
+        dt = sharding.max_over_ranks([dt])[0] if world == 1 else sharding.max_over_ranks([dt], device="cuda")[0]
+        first = {}   # determinism check: equal inputs give equal proofs, whichever context proved them
+        same = all(first.setdefault(i % len(inputs), hashlib.sha256(p).digest()) == hashlib.sha256(p).digest() for i, p in zip(mine, proofs))
+        batches[label] = {"proofs": count, "blocks_per_proof": nb, "contexts_per_gpu": nctx, "seconds": dt, "proofs_per_sec": count / dt,
+                          "identical_inputs_identical_proofs": same,
+                          "timing": "host wall clock around the whole batch, barrier + synchronize on both sides, max over ranks"}
+    if rank == 0:
+        out["proof_batches_cfg4"] = batches
+    return out
 
 
 if __name__ == "__main__":

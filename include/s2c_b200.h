@@ -150,8 +150,10 @@ int s2c_prove_aes_ctr_raw(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
 /* Raw form used by the benchmark and tests: proof bytes (bincode StreamProof) instead of base64-in-JSON. */
 int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            const uint8_t* ciphertext, size_t len, uint8_t** proof_out, size_t* proof_len);
-/* Same, with plaintext/ciphertext already resident in device memory (pt_dev/ct_dev: len bytes each) and the two Blake2s
- * public-input hashes supplied by the caller; used to time the prover with inputs in HBM. */
+/* Same, with plaintext/ciphertext already resident in device memory (pt_dev/ct_dev: len bytes each); used to time the prover
+ * with inputs in HBM.  pt_hash/ct_hash: the two Blake2s public-input hashes (ChaChaPublicInputs::new, air_stream.rs:44-53) if the
+ * caller already has them, or both NULL: the library then reads the buffers back on a side stream and hashes them on host
+ * threads while the commitment pass runs (host work in the reference too). */
 int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const void* pt_dev,
                            const void* ct_dev, size_t len, const uint8_t pt_hash[32], const uint8_t ct_hash[32],
                            uint8_t** proof_out, size_t* proof_len);

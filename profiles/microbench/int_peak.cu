@@ -17,7 +17,8 @@ constexpr int CH = 8;   // independent chains per thread
 constexpr int RP = 16;  // unrolled repetitions per loop iteration
 
 enum Op { IADD3, LOP3, SHF, IMAD, IMADWIDE, IMADHI, VIADDMIN, LEAHI, PAIR_IADD_IMAD, PAIR_MIN_IMAD, PAIR_MIN_WIDE, PAIR_MIN_LOP, PAIR_WIDE_LOP, PAIR_HI_LOP,
-          BFLY_CUR, BFLY_ALU, BFLY_SHOUP, BFLY_MIX, BLAKE_G, N_OPS };
+          BFLY_CUR, BFLY_ALU, BFLY_SHOUP, BFLY_MIX, BLAKE_G,
+          DFMA, DADD, I2D, PAIR_DFMA_IMAD, PAIR_DFMA_LOP, MAC_WIDE, MAC_WIDE4, MAC_F64, MAC_F64_MAGIC, N_OPS };
 
 __device__ __forceinline__ uint32_t redp(uint32_t x) { return __viaddmin_u32(x, 0u - P, x); }
 __device__ __forceinline__ uint32_t mulw(uint32_t a, uint32_t w2) {
@@ -51,11 +52,19 @@ template <int OP>
 __global__ void __launch_bounds__(256) bench_kernel(uint32_t* out, uint32_t seed, int iters, uint32_t one, uint32_t mone) {
     uint32_t v[CH], u[CH];
     uint64_t acc[CH];
+    double dacc[CH], dm = (double)(seed & 0xffffu), da = (double)((seed >> 7) & 0xffffu);
+    // split-alpha tables as the constraint kernel uses them: 16-bit halves of 4 coordinates (integers / doubles)
+    const uint4 tl = make_uint4(seed & 0xffffu, (seed >> 3) & 0xffffu, (seed >> 5) & 0xffffu, (seed >> 7) & 0xffffu);
+    const uint4 th = make_uint4((seed >> 9) & 0xffffu, (seed >> 11) & 0xffffu, (seed >> 13) & 0xffffu, (seed >> 15) & 0xffffu);
+    const double tdl[4] = {(double)tl.x, (double)tl.y, (double)tl.z, (double)tl.w}, tdh[4] = {(double)th.x, (double)th.y, (double)th.z, (double)th.w};
+    uint64_t m8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double d8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < CH; i++) {
         v[i] = (seed * (threadIdx.x + 1) + i * 0x9e3779b9u) & P;
         u[i] = (seed * (blockIdx.x + 7) + threadIdx.x * 0x27d4eb2fu + i * 0x85ebca6bu) & P;
         acc[i] = v[i];
+        dacc[i] = (double)v[i];
     }
     const uint32_t w2 = ((seed * 77u) & P) << 1, w = (seed * 77u) & P, wp = (w << 1) + (2 * (uint64_t)w >= P);
     for (int it = 0; it < iters; it++) {
@@ -93,6 +102,35 @@ __global__ void __launch_bounds__(256) bench_kernel(uint32_t* out, uint32_t seed
                 else if (OP == BFLY_ALU) { bfly_alu(v[i], u[i], w2); }
                 else if (OP == BFLY_SHOUP) { bfly_shoup(v[i], u[i], w, wp, one, mone); }
                 else if (OP == BFLY_MIX) { if (i & 1) bfly_shoup(v[i], u[i], w, wp, one, mone); else bfly_cur(v[i], u[i], w2, one, mone); }
+                else if (OP == DFMA) { dacc[i] = fma(dacc[i], dm, da); }
+                else if (OP == DADD) { dacc[i] = dacc[i] + dm; }
+                else if (OP == I2D) { dacc[i] += (double)v[i]; v[i] ^= (uint32_t)__double2loint(dacc[i]); }  // I2F.F64.U32 + DADD + LOP3
+                else if (OP == PAIR_DFMA_IMAD) {
+                    dacc[i] = fma(dacc[i], dm, da);
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(seed), "r"(one));
+                } else if (OP == PAIR_DFMA_LOP) {
+                    dacc[i] = fma(dacc[i], dm, da);
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[i]) : "r"(seed), "r"(one));
+                } else if (OP == MAC_WIDE) {   // the constraint kernel's multiply-accumulate today: 8 IMAD.WIDE per constraint value
+                    const uint32_t C = v[i]; v[i] = v[i] * one + u[i];
+                    m8[0] += (uint64_t)C * tl.x; m8[1] += (uint64_t)C * tl.y; m8[2] += (uint64_t)C * tl.z; m8[3] += (uint64_t)C * tl.w;
+                    m8[4] += (uint64_t)C * th.x; m8[5] += (uint64_t)C * th.y; m8[6] += (uint64_t)C * th.z; m8[7] += (uint64_t)C * th.w;
+                } else if (OP == MAC_WIDE4) {  // unsplit coefficients: 4 IMAD.WIDE + a fold of the accumulators every 4 values
+                    const uint32_t C = v[i] & P; v[i] = v[i] * one + u[i];
+                    m8[0] += (uint64_t)C * tl.x * 3; m8[1] += (uint64_t)C * tl.y; m8[2] += (uint64_t)C * tl.z; m8[3] += (uint64_t)C * tl.w;
+                    if ((i & 3) == 3) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) m8[c] = (m8[c] & P) + (m8[c] >> 31);
+                    }
+                } else if (OP == MAC_F64) {    // the same in FP64: convert the value once, 8 DFMA
+                    const double C = (double)v[i]; v[i] = v[i] * one + u[i];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { d8[c] = fma(C, tdl[c], d8[c]); d8[4 + c] = fma(C, tdh[c], d8[4 + c]); }
+                } else if (OP == MAC_F64_MAGIC) {  // conversion by exponent trick (2^52 + C) - 2^52: one DADD instead of I2F
+                    const double C = __hiloint2double(0x43300000, (int)v[i]) - 4503599627370496.0; v[i] = v[i] * one + u[i];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { d8[c] = fma(C, tdl[c], d8[c]); d8[4 + c] = fma(C, tdh[c], d8[4 + c]); }
+                }
                 else if (OP == BLAKE_G) {  // one Blake2s half-G: a += b + m; d = rotr(d ^ a, 16); c += d; b = rotr(b ^ c, 12)
                     uint32_t a = v[i], b = u[i], c = (uint32_t)acc[i], d = (uint32_t)(acc[i] >> 32);
                     a = a * one + b; a = a * one + seed; d = __funnelshift_r(d ^ a, d ^ a, 16);
@@ -104,7 +142,9 @@ __global__ void __launch_bounds__(256) bench_kernel(uint32_t* out, uint32_t seed
     }
     uint32_t x = 0;
 #pragma unroll
-    for (int i = 0; i < CH; i++) x ^= v[i] ^ u[i] ^ (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
+    for (int i = 0; i < CH; i++)
+        x ^= v[i] ^ u[i] ^ (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32) ^ (uint32_t)__double2loint(dacc[i]) ^ (uint32_t)__double2hiint(dacc[i]) ^
+             (uint32_t)m8[i] ^ (uint32_t)(m8[i] >> 32) ^ (uint32_t)__double2loint(d8[i]) ^ (uint32_t)__double2hiint(d8[i]);
     if (x == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
@@ -157,6 +197,15 @@ int main(int argc, char** argv) {
     RUN(BFLY_SHOUP, 1, "M31 butterfly, Shoup multiply on the FMA pipe: IMAD.HI, 2 IMAD, 3 VIADDMNMX, 2 IMAD (3 ALU + 5 FMA)")
     RUN(BFLY_MIX, 1, "alternating the two butterflies (3.5 ALU + 4 FMA)")
     RUN(BLAKE_G, 1, "Blake2s half-G: 3 IMAD adds (FMA) + 2 LOP3 + 2 SHF (ALU)")
+    RUN(DFMA, 1, "DFMA (FP64 pipe)")
+    RUN(DADD, 1, "DADD (FP64 pipe)")
+    RUN(I2D, 3, "I2F.F64.U32 + DADD + LOP3")
+    RUN(PAIR_DFMA_IMAD, 2, "DFMA + IMAD (FP64 + FMA pipes)")
+    RUN(PAIR_DFMA_LOP, 2, "DFMA + LOP3 (FP64 + ALU pipes)")
+    RUN(MAC_WIDE, 1, "constraint multiply-accumulate as in kernels_stream.cu: 8 IMAD.WIDE per value (items = values)")
+    RUN(MAC_WIDE4, 1, "unsplit coefficients: 4 IMAD.WIDE per value + accumulator folds every 4 values")
+    RUN(MAC_F64, 1, "FP64 form: I2F + 8 DFMA per value")
+    RUN(MAC_F64_MAGIC, 1, "FP64 form with exponent-trick conversion: DADD + 8 DFMA per value")
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d, \"blocks\": %d, \"threads\": 256, \"results\": [\n", pr.name,
            pr.multiProcessorCount, clk, blocks);
     for (size_t i = 0; i < rs.size(); i++) {

@@ -29,6 +29,16 @@ CASES = [  # (name, n_blocks, seed)
 ]
 
 
+# Sizes only the GPU parity tests use (`python make_golden.py --large` regenerates them; ~2.5 minutes of reference proving):
+# log 12 (whole-column FFT kernel, byte-table kernels) and log 13 = 8,192 blocks, the largest trace the reference's wasm32
+# build can hold (3.06 GB of its 4 GB address space; 16,384 blocks trap with out-of-memory).  Log 13 is the smallest size that
+# runs the three-pass FFT kernels, the partial tile cache with half-tile recomputation and the cached-tile query path.
+LARGE_CASES = [
+    ("rand_4096blocks_log12", 4096, 100 + 4096),
+    ("rand_8192blocks_log13", 8192, 100 + 8192),
+]
+
+
 def case_inputs(n_blocks, seed):
     if seed is None:  # RFC 7539 2.3.2 key/nonce/counter (chacha/block.rs:116-139)
         key = bytes(range(32)); nonce = bytes([0, 0, 0, 9, 0, 0, 0, 0x4A, 0, 0, 0, 0]); counter = 1
@@ -42,8 +52,11 @@ def case_inputs(n_blocks, seed):
 
 
 def main():
+    path = os.path.join(HERE, "chacha20_golden.json")
+    large = "--large" in sys.argv
+    prev = json.load(open(path)) if os.path.exists(path) else {}
     out = []
-    for name, nb, seed in CASES:
+    for name, nb, seed in (LARGE_CASES if large else CASES):
         key, nonce, counter, pt, ct = case_inputs(nb, seed)
         res = ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)
         entry = {"name": name, "n_blocks": nb, "seed": seed}
@@ -60,8 +73,10 @@ def main():
             assert v.get("valid") is True, v
         out.append(entry)
         print(entry)
-    json.dump({"generator": "tests/golden/make_golden.py", "reference": "resources/stwo/s2circuits_bg.wasm via oracle/_ref",
-               "cases": out}, open(os.path.join(HERE, "chacha20_golden.json"), "w"), indent=1)
+    doc = {"generator": "tests/golden/make_golden.py", "reference": "resources/stwo/s2circuits_bg.wasm via oracle/_ref",
+           "cases": prev.get("cases", []), "large_cases": prev.get("large_cases", [])}
+    doc["large_cases" if large else "cases"] = out
+    json.dump(doc, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -292,6 +292,94 @@ def test_reference_verifier_accepts_gpu_proofs(backend, nb):
         assert ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)["proof"] == res["proof"]
 
 
+# ------------------------------------------------------------------------------ large sizes: every code path of the headline config
+_GOLD_DOC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chacha20_golden.json")))
+LARGE_GOLDEN = _GOLD_DOC.get("large_cases", [])
+
+
+def _with_cache_cap(be, cap, fn):
+    be._ck(be.L.cb_set_max_cached_tiles(be.ctx, cap))
+    try:
+        return fn()
+    finally:
+        be._ck(be.L.cb_set_max_cached_tiles(be.ctx, -1))
+
+
+@pytest.mark.parametrize("case", LARGE_GOLDEN, ids=lambda c: c["name"])
+def test_large_proofs_match_reference_prover_for_every_cache_size(backend, case):
+    """log 12 / log 13 proofs byte-identical to the REFERENCE PROVER's (fixtures from tests/golden/make_golden.py --large), with
+    the full tile cache and with caps 0 / 100 / 300: at log 13 that runs the three-pass FFT kernels inside the prover, the
+    partial cache with half-tile recomputation in the constraint pass, `gather_cached_kernel` and the uncached-word query path
+    -- every path a log 20 proof takes -- and pins them to the reference, not to the path itself."""
+    key, nonce, counter, pt, ct = case_inputs(case["n_blocks"], case["seed"])
+    for cap in (-1, 0, 100, 300):
+        proof = _with_cache_cap(backend, cap, lambda: backend.prove_chacha20_raw(key, nonce, counter, pt, ct))
+        assert len(proof) == case["proof_len"], cap
+        assert hashlib.sha256(proof).hexdigest() == case["proof_sha256"], "cache cap %d" % cap
+        if cap >= 0:
+            assert backend.counters()["cached_tiles"] <= cap
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not on this box")
+def test_log13_proof_equals_live_reference_prover(backend):
+    """The same comparison against the reference prover run live on this box (8,192 blocks: the largest trace its wasm32 build
+    holds; ~80 s of CPU), on inputs no fixture was made from."""
+    key, nonce, counter, pt, ct = case_inputs(8192, 4242)
+    want = ref_wasm.generate_chacha20_proof(key, nonce, counter, pt, ct)
+    assert want.get("success") is True, want
+    for cap in (-1, 200):
+        res = _with_cache_cap(backend, cap, lambda: backend.generate_chacha20_proof(key, nonce, counter, pt, ct))
+        assert res == want, "cache cap %d" % cap
+
+
+@pytest.mark.parametrize("log_n", [14, 16])
+def test_partial_cache_paths_equal_full_cache_at_log_14_16(backend, log_n):
+    """cb_set_max_cached_tiles in {0, 100, 300} at log 14 / 16 (three-pass FFT with 4 / 16 strided layers): the proof equals the
+    full-cache proof, and the reference's verifier accepts it."""
+    import bench
+    key, nonce, counter, pt, ct = bench.synth_inputs(log_n, 3)
+    ptb, ctb = pt.tobytes(), ct.tobytes()
+    want = backend.prove_chacha20_raw(key, nonce, counter, ptb, ctb)
+    assert backend.counters()["cached_tiles"] == 704
+    for cap in (0, 100, 300):
+        got = _with_cache_cap(backend, cap, lambda: backend.prove_chacha20_raw(key, nonce, counter, ptb, ctb))
+        assert got == want, "cache cap %d" % cap
+    import base64
+    import zk_symmetric_crypto_b200 as z
+    assert z.verify_chacha20_raw(want, nonce, counter, ptb, ctb) == (True, None)
+    if ref_wasm.available():
+        b64 = base64.b64encode(want).decode()
+        assert ref_wasm.verify_chacha20_proof(b64, nonce, counter, ptb, ctb) == {"algorithm": "chacha20", "valid": True}
+
+
+def test_headline_log20_proof_is_accepted_by_the_reference_verifier(backend):
+    """BASELINE configs[1] itself: the log_n_rows = 20 proof bench.py times (same synthetic inputs) is accepted by the
+    reference's own verifier (wasm_api.rs:609 -> air_stream.rs:343-421) and rejected for a plaintext with one flipped bit;
+    the partial tile cache (642 of 704 tiles fit one B200) is in use, and a smaller cache gives the same bytes."""
+    import base64
+    import bench
+    import zk_symmetric_crypto_b200 as z
+    key, nonce, counter, pt, ct = bench.synth_inputs(20, 0)
+    ptb, ctb = pt.tobytes(), ct.tobytes()
+    be = z.Backend(0)   # its own context: the ~170 GB tile arena is released again when it closes
+    try:
+        proof = be.prove_chacha20_raw(key, nonce, counter, ptb, ctb)
+        cnt = be.counters()
+        assert 0 < cnt["cached_tiles"] <= 704
+        again = _with_cache_cap(be, 500, lambda: be.prove_chacha20_raw(key, nonce, counter, ptb, ctb))
+    finally:
+        be.close()
+    assert again == proof, "log 20 proof depends on the tile-cache size"
+    bad = bytearray(ptb)
+    bad[12345] ^= 0x20
+    assert z.verify_chacha20_raw(proof, nonce, counter, ptb, ctb) == (True, None)
+    assert z.verify_chacha20_raw(proof, nonce, counter, bytes(bad), ctb) == (False, "OodsNotMatching")
+    if ref_wasm.available():
+        b64 = base64.b64encode(proof).decode()
+        assert ref_wasm.verify_chacha20_proof(b64, nonce, counter, ptb, ctb) == {"algorithm": "chacha20", "valid": True}
+        assert ref_wasm.verify_chacha20_proof(b64, nonce, counter, bytes(bad), ctb) == {"error": "OodsNotMatching", "valid": False}
+
+
 # ---------------------------------------------------------------------------------------------------- AES-CTR
 import aes_api as oracle_aes
 from make_golden_aes import aes_case_inputs

@@ -192,16 +192,19 @@ class Backend:
         """Raw-pointer form: host pointers (e.g. pinned memory) or, with on_device=True, device pointers plus the two
         public-input hashes.  Returns the proof bytes.  Both buffers must hold `nbytes` bytes (the caller owns them)."""
         self._check_raw(bytes(key), (32,), bytes(nonce), counter, nbytes, None, 64)
-        if on_device and (pt_hash is None or ct_hash is None or len(bytes(pt_hash)) != 32 or len(bytes(ct_hash)) != 32):
-            raise BackendError("device-input proving needs the two 32-byte public-input hashes")
+        if on_device and (pt_hash is None) != (ct_hash is None):
+            raise BackendError("give both public-input hashes or neither")
+        if on_device and pt_hash is not None and (len(bytes(pt_hash)) != 32 or len(bytes(ct_hash)) != 32):
+            raise BackendError("public-input hashes are 32 bytes each")
         kb, _ = _bytes(key)
         nb, _ = _bytes(nonce)
         out = ctypes.POINTER(ctypes.c_uint8)()
         n = ctypes.c_size_t()
         if on_device:
             rc = self.L.s2c_prove_chacha20_dev(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), ctypes.c_void_p(pt_ptr),
-                                               ctypes.c_void_p(ct_ptr), ctypes.c_size_t(nbytes), bytes(pt_hash), bytes(ct_hash),
-                                               ctypes.byref(out), ctypes.byref(n))
+                                               ctypes.c_void_p(ct_ptr), ctypes.c_size_t(nbytes),
+                                               bytes(pt_hash) if pt_hash is not None else None,
+                                               bytes(ct_hash) if ct_hash is not None else None, ctypes.byref(out), ctypes.byref(n))
         else:
             rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), ctypes.c_void_p(pt_ptr),
                                                ctypes.c_void_p(ct_ptr), ctypes.c_size_t(nbytes), ctypes.byref(out), ctypes.byref(n))

@@ -99,6 +99,32 @@ __device__ __forceinline__ void compress_fma(uint32_t h[8], const uint32_t m[16]
 }
 #endif
 
+// host: incremental form for data that arrives in chunks.  Every update() but the last must carry a multiple of 64 bytes.
+struct Incremental {
+    uint32_t h[8];
+    uint64_t total = 0;
+    Incremental() { init(h); }
+    // absorbs full blocks; when `more` is false the final (possibly partial, possibly empty only for an empty message) block is
+    // compressed with the last-block flag and the digest is written to out
+    void update(const uint8_t* data, size_t len, bool more, uint8_t* out = nullptr) {
+        uint32_t m[16];
+        size_t off = 0;
+        while (len - off > (more ? 63 : 64)) {
+            memcpy(m, data + off, 64);
+            off += 64;
+            total += 64;
+            compress(h, m, total, false);
+        }
+        if (more) return;
+        uint8_t buf[64] = {0};
+        memcpy(buf, data + off, len - off);
+        memcpy(m, buf, 64);
+        total += len - off;
+        compress(h, m, total, true);
+        memcpy(out, h, 32);
+    }
+};
+
 // host convenience: one-shot hash of a byte buffer (little-endian host assumed)
 inline void hash(const uint8_t* data, size_t len, uint8_t out[32]) {
     uint32_t h[8];

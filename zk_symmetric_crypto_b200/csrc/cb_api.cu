@@ -56,6 +56,7 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
     if (ctx->tw_shift_dev) cudaFree(ctx->tw_shift_dev);
     ctx->release_arena();
+    if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
     try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
@@ -417,8 +418,8 @@ const char* cb_counters(cb_ctx* ctx) {
     static thread_local std::string s;
     s.clear();
     if (!ctx) return "";
-    s = "fft_words=" + std::to_string(ctx->fft_words) + ";cached_tiles=" + std::to_string(ctx->cached_tiles) +
-        ";transient_tiles=" + std::to_string(ctx->transient_tiles) + ";";
+    s = "fft_words=" + std::to_string(ctx->fft_words) + ";fft_words_half=" + std::to_string(ctx->fft_words_half) + ";cached_tiles=" + std::to_string(ctx->cached_tiles) +
+        ";transient_tiles=" + std::to_string(ctx->transient_tiles) + ";hash_wait_us=" + std::to_string(ctx->hash_wait_us) + ";";
     return s.c_str();
 }
 
@@ -507,8 +508,10 @@ int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ProveOptions opt;
     opt.pt_dev = (const uint32_t*)pt_dev;
     opt.ct_dev = (const uint32_t*)ct_dev;
-    opt.pt_hash = pt_hash;
-    opt.ct_hash = ct_hash;
+    if (pt_hash && ct_hash) {  // both or neither: without them the library reads the buffers back and hashes them itself
+        opt.pt_hash = pt_hash;
+        opt.ct_hash = ct_hash;
+    }
     std::vector<uint8_t> proof;
     check_counter(counter, len / 64);
     std::string e = prove_chacha20(ctx, key, nonce, counter, nullptr, nullptr, len, proof, opt);

@@ -121,6 +121,11 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
                               const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0, int first_half_only = 0);
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
                                      const uint32_t* apr_hi, uint32_t* acc, int first, size_t rows = 0);
+// FP64-accumulate form: gtab = the launch's alpha table in consumption order (launch_cons_table), jobs.j[k].kx = offset of job k's
+// slice in it (in constraints)
+cudaError_t launch_constraints_tiles2(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const double* gtab, uint32_t* acc, int first,
+                                      size_t rows = 0);
+cudaError_t launch_cons_table(cudaStream_t st, const uint32_t* apr, const int* idx_dev, int n, double* gtab);
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi);
 cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0 = 0);
 struct TileRowJobs {

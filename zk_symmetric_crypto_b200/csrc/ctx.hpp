@@ -49,13 +49,16 @@ struct cb_ctx {
     int max_cached_tiles = -1;  // streaming prover: cap on LDE tiles kept between passes (-1 = as many as memory allows)
     uint64_t launches = 0;
     // counters of the last streaming proof: packed words transformed (x32 columns), tiles cached between passes, transient slots
-    uint64_t fft_words = 0;
+    uint64_t fft_words = 0, fft_words_half = 0;  // packed words transformed by the last streaming proof (of which: on half of the domain)
     int cached_tiles = 0, transient_tiles = 0;  // kernels launched by this context (reported by bench.py as gpu_launches)
 
     // persistent work arena of the streaming provers (LDE tile slots): allocated once with cudaMalloc and kept between
     // proofs -- re-allocating ~170 GB from the stream-ordered pool per proof costs up to 0.3 s when the pool has fragmented
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    // pinned staging for reading device-resident inputs back while they are hashed (two hasher threads x two chunks)
+    uint8_t* hash_stage = nullptr;
+    uint64_t hash_wait_us = 0;  // host time the last proof waited for the public-input hashes after the commitment pass
     void* ensure_arena(size_t bytes);
     void release_arena();
     void ensure_twiddles(int max_log);

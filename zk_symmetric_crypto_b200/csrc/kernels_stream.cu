@@ -19,6 +19,9 @@
 #ifndef CONS_MIN_BLOCKS
 #define CONS_MIN_BLOCKS 6
 #endif
+#ifndef CONS2_MIN_BLOCKS
+#define CONS2_MIN_BLOCKS 5
+#endif
 namespace strm {
 using namespace m31d;
 
@@ -122,6 +125,163 @@ __global__ void __launch_bounds__(128, CONS_MIN_BLOCKS) constraints_tiles_kernel
     }
 }
 
+// ---- v2: the same sum with the multiply-accumulate on the FP64 pipe ---------------------------------------------------------
+// Measured on B200 (profiles/int_peak_r02.json): IMAD.WIDE issues at 25 thread-instructions/clk/SM, DFMA at 58-63 on its own
+// pipe next to the integer pipes.  A constraint value C (< 2^32) times a 16-bit half of an alpha-power coordinate is < 2^48, so a
+// double holds the exact sum of 32 such products (2^53): the 8 IMAD.WIDE of AccSplit::mac become 8 DFMA, the integer pipes keep
+// only the constraint arithmetic itself, and the accumulators are folded into integers once per 32 constraints.
+// The alpha table of one launch is pre-arranged in consumption order (cons_table_kernel: 8 doubles per constraint = low and high
+// halves of the 4 coordinates) and every job's slice (<= 8 KB) is staged in shared memory once per block, so a constraint costs
+// four broadcast LDS.128 with immediate offsets instead of two global LDG.128 with computed addresses.
+struct AccF64 {
+    double a[8];            // lo halves x 4 coordinates, hi halves x 4 coordinates
+    uint64_t lo[4], hi[4];  // folded integer sums
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { lo[c] = hi[c] = 0; a[c] = a[4 + c] = 0.0; }
+    }
+    __device__ __forceinline__ void mac(const double* __restrict__ e, uint32_t C) {
+        const double c = __uint2double_rn(C);
+        const double2 l01 = *(const double2*)(e), l23 = *(const double2*)(e + 2), h01 = *(const double2*)(e + 4), h23 = *(const double2*)(e + 6);
+        a[0] = fma(c, l01.x, a[0]); a[1] = fma(c, l01.y, a[1]); a[2] = fma(c, l23.x, a[2]); a[3] = fma(c, l23.y, a[3]);
+        a[4] = fma(c, h01.x, a[4]); a[5] = fma(c, h01.y, a[5]); a[6] = fma(c, h23.x, a[6]); a[7] = fma(c, h23.y, a[7]);
+    }
+    __device__ __forceinline__ void fold() {  // after at most 32 mac() calls
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            lo[c] += __double2ull_rz(a[c]);
+            hi[c] += __double2ull_rz(a[4 + c]);
+            a[c] = a[4 + c] = 0.0;
+        }
+    }
+    __device__ __forceinline__ uint32_t result(int c) const { return addm(mulm(red64(hi[c]), 1u << 16), red64(lo[c])); }
+};
+
+// one adder (+ xor-rotate) job; table slice: step s -> [carry boolean, sum boolean(, xor, result boolean)] x 8 doubles
+template <bool HAS_X>
+__device__ __forceinline__ void addx_job2(const ConstraintJob& J, size_t row, size_t M, const double* __restrict__ tab, AccF64& A) {
+    const uint32_t* x = HAS_X ? J.t0 + row : nullptr;
+    const uint32_t* a = J.t1 + row;
+    const uint32_t* d = HAS_X ? J.t2 + row : nullptr;
+    const uint32_t* b = J.t3 + row;
+    const uint32_t* cy = J.t4 + row;
+    uint32_t* res = J.res + row;
+    constexpr int NE = HAS_X ? 4 : 2;
+    constexpr int SB = 4;  // steps per batch of loads (all loads of a batch are issued before its arithmetic)
+    uint32_t cin = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < 32; s0 += SB) {
+        uint32_t av[SB], bv[SB], cv[SB], xv[SB], dv[SB];
+#pragma unroll
+        for (int u = 0; u < SB; u++) {
+            const int s = s0 + u;
+            av[u] = a[(size_t)s * M];
+            bv[u] = b[(size_t)s * M];
+            cv[u] = cy[(size_t)s * M];
+            if (HAS_X) {
+                xv[u] = x[(size_t)((s + J.arg) & 31) * M];
+                dv[u] = d[(size_t)s * M];
+            }
+        }
+        const double* __restrict__ e = tab + (size_t)s0 * NE * 8;
+#pragma unroll
+        for (int u = 0; u < SB; u++) {
+            const int s = s0 + u;
+            const uint32_t c2 = cv[u] + cv[u];
+            const uint32_t sv = subm(redp(redp(av[u] + bv[u]) + cin), redp(c2));
+            cin = cv[u];
+            res[(size_t)s * M] = sv;
+            const uint32_t s2 = sv + sv;
+            A.mac(e + (u * NE) * 8, bool_c(cv[u], c2));
+            A.mac(e + (u * NE + 1) * 8, bool_c(sv, s2));
+            if (HAS_X) {
+                const uint64_t v = (uint64_t)dv[u] * s2;  // d * (2s) / 2 = s d (mulw form)
+                const uint32_t sd = redp((uint32_t)(v >> 32) + (((uint32_t)v) >> 1));
+                const uint32_t up = redp(redp(xv[u] + sd) + sd), dn = redp(sv + dv[u]);
+                A.mac(e + (u * NE + 2) * 8, up + P - dn);
+                A.mac(e + (u * NE + 3) * 8, bool_c(xv[u], xv[u] + xv[u]));
+            }
+        }
+        if ((s0 & SB) != 0) A.fold();  // every 8 steps: at most 32 products since the last fold
+    }
+}
+
+// jobs.j[k].kx = offset (in constraints) of job k's slice inside `gtab`; slice sizes: CJ_BOOL 32, CJ_ADDX 128 (64 without the xor
+// part), CJ_XOR/CJ_XORN 128 entries of 8 doubles
+__global__ void __launch_bounds__(128, CONS2_MIN_BLOCKS) constraints_tiles_kernel2(ConstraintJobs jobs, size_t M, const double* __restrict__ gtab,
+                                                                 uint32_t* __restrict__ acc, int first, size_t rows) {
+    __shared__ __align__(16) double stab[128 * 8];
+    const size_t row0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = row0 < rows;
+    const size_t row = live ? row0 : 0;  // idle threads of the last block still help staging (their results are not stored)
+    AccF64 A;
+    A.init();
+    for (int j = 0; j < jobs.n; j++) {
+        const ConstraintJob& J = jobs.j[j];
+        const int n_e = J.type == CJ_BOOL ? 32 : (J.type == CJ_ADDX && !J.t0 ? 64 : 128);
+        __syncthreads();
+        {
+            const double2* __restrict__ src = (const double2*)(gtab + (size_t)J.kx * 8);
+            for (int i = threadIdx.x; i < n_e * 4; i += blockDim.x) ((double2*)stab)[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        if (!live) continue;
+        if (J.type == CJ_ADDX) {
+            if (J.t0) addx_job2<true>(J, row, M, stab, A);
+            else addx_job2<false>(J, row, M, stab, A);
+        } else if (J.type == CJ_BOOL) {
+            const uint32_t* __restrict__ t = J.t0 + row;
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+                const uint32_t b = t[(size_t)i * M];
+                A.mac(stab + i * 8, bool_c(b, b + b));
+            }
+            A.fold();
+        } else {
+            const uint32_t* __restrict__ r = J.t0 + row;
+            const uint32_t* __restrict__ a = J.t1 + row;
+            const uint32_t* __restrict__ d = J.t2 + row;
+            const bool neg = J.type == CJ_XORN;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+#pragma unroll 4
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u, s = (i + 32 - J.arg) & 31;
+                    const uint32_t rv = r[(size_t)i * M], av = a[(size_t)s * M], dv = d[(size_t)s * M];
+                    const uint32_t ad = mulm(av, dv);
+                    uint32_t C = addm(subm(subm(rv, av), dv), dbl(ad));
+                    if (neg) C = subm(0, C);
+                    const double* e = stab + (i * 4) * 8;  // absent booleans have an all-zero table entry
+                    A.mac(e, C);
+                    A.mac(e + 8, bool_c(rv, rv + rv));
+                    A.mac(e + 16, bool_c(av, av + av));
+                    A.mac(e + 24, bool_c(dv, dv + dv));
+                }
+                A.fold();
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t v = A.result(c);
+        uint32_t* o = acc + (size_t)c * M + row;
+        if (!first) v = addm(v, *o);
+        *o = v;
+    }
+}
+
+// gtab[e][0..3] = low 16 bits, gtab[e][4..7] = high bits of the 4 coordinates of apr[idx[e]] as doubles (idx < 0: zeros)
+__global__ void cons_table_kernel(const uint4* __restrict__ apr, const int* __restrict__ idx, int n, double* __restrict__ gtab) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int k = idx[e];
+    const uint4 v = k >= 0 ? apr[k] : make_uint4(0, 0, 0, 0);
+    double* o = gtab + (size_t)e * 8;
+    o[0] = (double)(v.x & 0xffffu); o[1] = (double)(v.y & 0xffffu); o[2] = (double)(v.z & 0xffffu); o[3] = (double)(v.w & 0xffffu);
+    o[4] = (double)(v.x >> 16); o[5] = (double)(v.y >> 16); o[6] = (double)(v.z >> 16); o[7] = (double)(v.w >> 16);
+}
+
 // split a table of QM31 values (4 words each) into 16-bit halves
 __global__ void split16_kernel(const uint4* __restrict__ t, int n, uint4* __restrict__ lo, uint4* __restrict__ hi) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,6 +340,57 @@ __global__ void __launch_bounds__(256) bitcol_dot_kernel(const uint32_t* __restr
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             uint32_t v = acc[b][c];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v = addm(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][b * 4 + c] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int g = threadIdx.x >> 5, x = threadIdx.x & 31;  // x = bit*4 + c
+        uint32_t v = addm(red[2 * g][x], red[2 * g + 1][x]);
+        if (gridDim.y == 1) v = mulm(v, scale);
+        out[(size_t)blockIdx.y * slice_stride + (word * 32 + 8 * g) * 4 + x] = v;
+    }
+}
+
+// The same masked sums accumulated on the FP64 pipe: the weights are < 2^31, so a double holds the exact sum of 2^22 of them
+// (a thread adds N / 64 <= 2^18 rows); a set bit costs one predicated DADD per coordinate instead of mask + add + reduce on the
+// ALU pipe (15 ALU-pipe instructions per bit before, ~2 now; DADD issues at 63 thread-instructions/clk/SM next to them).
+__global__ void __launch_bounds__(256) bitcol_dot_kernel2(const uint32_t* __restrict__ W, size_t N, const uint32_t* __restrict__ wt,
+                                                          uint32_t scale, uint32_t* __restrict__ out, const int* __restrict__ words,
+                                                          size_t rows_per_slice, size_t slice_stride) {
+    const int lane = threadIdx.x & 63, bg = threadIdx.x >> 6;
+    const size_t word = words ? (size_t)words[blockIdx.x] : (size_t)blockIdx.x;
+    const uint32_t* __restrict__ wrow = W + word * N;
+    const size_t r_begin = (size_t)blockIdx.y * rows_per_slice;
+    const size_t r_end = r_begin + rows_per_slice < N ? r_begin + rows_per_slice : N;
+    double acc[8][4];
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[b][c] = 0.0;
+    for (size_t r = r_begin + lane; r < r_end; r += 64) {
+        const uint32_t w = __ldg(wrow + r) >> (8 * bg);
+        double t[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {  // converted once per row (volatile: ptxas would otherwise sink the conversion into each
+            const uint32_t x = __ldg(wt + (size_t)c * N + r);  // predicated add, 8 conversions instead of 1 on the slow XU pipe)
+            asm volatile("cvt.rn.f64.u32 %0, %1;" : "=d"(t[c]) : "r"(x));
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if ((w >> b) & 1u) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[b][c] += t[c];
+            }
+        }
+    }
+    __shared__ uint32_t red[8][32];
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t v = red64(__double2ull_rz(acc[b][c]));
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) v = addm(v, __shfl_xor_sync(0xffffffffu, v, o));
             if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][b * 4 + c] = v;
@@ -400,6 +611,19 @@ cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs
     return cudaGetLastError();
 }
 
+cudaError_t launch_constraints_tiles2(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const double* gtab, uint32_t* acc, int first,
+                                      size_t rows) {
+    if (rows == 0 || rows > M) rows = M;
+    int threads = rows >= 128 * 148 ? 128 : 32;
+    strm::constraints_tiles_kernel2<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(jobs, M, gtab, acc, first, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cons_table(cudaStream_t st, const uint32_t* apr, const int* idx_dev, int n, double* gtab) {
+    strm::cons_table_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint4*)apr, idx_dev, n, gtab);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi) {
     strm::split16_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint4*)table, n, (uint4*)lo, (uint4*)hi);
     return cudaGetLastError();
@@ -431,14 +655,17 @@ cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int 
     // (a byte-bucket variant - shared-memory atomics on 16-bit halves, 32 per row - measured 31 vs 18 ms; not kept)
     int slices = 1;
     while (n_words * slices < 2368 && (N / (2 * slices)) >= 8192) slices *= 2;  // >= 4 waves of 592 resident blocks
+    static const bool v1 = getenv("S2C_BITCOL_V1") != nullptr;  // A/B switch: the integer (masked add + reduce) accumulation
     if (slices == 1) {
-        strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        if (v1) strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        else strm::bitcol_dot_kernel2<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
         return cudaGetLastError();
     }
     uint32_t* partial = nullptr;
     cudaError_t e = cudaMallocAsync(&partial, slice_stride * slices * 4, st);
     if (e != cudaSuccess) return e;
-    strm::bitcol_dot_kernel<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    if (v1) strm::bitcol_dot_kernel<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    else strm::bitcol_dot_kernel2<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
     strm::bitcol_reduce_kernel<<<(n_words * 128 + 255) / 256, 256, 0, st>>>(partial, slice_stride, slices, scale, words_dev, n_words, out);
     e = cudaGetLastError();
     cudaFreeAsync(partial, st);

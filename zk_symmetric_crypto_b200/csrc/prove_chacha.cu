@@ -8,6 +8,7 @@
 // Output bytes = bincode(StreamProof{stmt, stark_proof}) exactly as the reference serialises it
 // (air_stream.rs:30-131, wasm_api.rs:588): byte-identical to the reference, checked in tests/.
 #include <array>
+#include <chrono>
 #include <thread>
 #include "prover.hpp"
 
@@ -191,6 +192,43 @@ std::vector<Group> build_plan() {
     return plan;
 }
 
+// Alpha-table entries of every group's jobs in the order the FP64 constraint kernel consumes them (constraints_tiles_kernel2):
+// per job 32 steps x {1 (CJ_BOOL), 2 (adder only), 4 (adder + xor-rotate, xor jobs)} constraint indices; -1 = no constraint.
+// job_off[g][j] = offset of job j of group g in the list.
+struct ConsTable {
+    std::vector<int> idx;
+    std::vector<std::vector<int>> job_off;
+};
+ConsTable build_cons_table(const std::vector<Group>& plan) {
+    ConsTable t;
+    for (auto& g : plan) {
+        t.job_off.emplace_back();
+        for (auto& c : g.cons) {
+            t.job_off.back().push_back((int)t.idx.size());
+            for (int s = 0; s < 32; s++) {
+                if (c.type == CJ_BOOL) {
+                    t.idx.push_back(c.kb0 + s * c.arg);
+                } else if (c.type == CJ_ADDX) {
+                    t.idx.push_back(c.kbc + 2 * s);
+                    t.idx.push_back(c.kb1 + s);
+                    if (c.w0 >= 0) {
+                        const int i = (s + c.arg) & 31;
+                        t.idx.push_back(c.kx + i);
+                        t.idx.push_back(c.kb0 + i);
+                    }
+                } else {  // CJ_XOR / CJ_XORN: step i reads operand bit (i - rot) mod 32
+                    const int i = s, sb = (i + 32 - c.arg) & 31;
+                    t.idx.push_back(c.kx + i);
+                    t.idx.push_back(c.kb0 >= 0 ? c.kb0 + i : -1);
+                    t.idx.push_back(c.kb1 >= 0 ? c.kb1 + sb : -1);
+                    t.idx.push_back(c.kb2 >= 0 ? c.kb2 + sb : -1);
+                }
+            }
+        }
+    }
+    return t;
+}
+
 // LDE tile slots: a cache of independent tiles that survives from the commitment pass to the constraint pass, plus
 // transient slots recycled as words die.
 struct Tiles {
@@ -329,9 +367,47 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         void join() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
         ~Hashers() { join(); }
     } hashers;
+    std::string hash_err;
     if (!opt.pt_hash && !opt.empty_public_hashes) {
-        hashers.a = std::thread([&] { pth = host::blake2s_bytes(plaintext, len); });
-        hashers.b = std::thread([&] { cth = host::blake2s_bytes(ciphertext, len); });
+        if (opt.pt_dev) {
+            // inputs resident in HBM and no hashes supplied: each thread reads its buffer back on its own non-blocking stream
+            // (2 x len bytes of D2H, hidden behind the commitment pass like the hashing itself)
+            constexpr size_t CHUNK = (size_t)4 << 20;
+            if (!ctx->hash_stage) CB_CUDA(cudaHostAlloc((void**)&ctx->hash_stage, 4 * CHUNK, cudaHostAllocDefault));
+            const int dev = ctx->device;
+            uint8_t* stage = ctx->hash_stage;
+            auto hash_dev = [dev, len, stage, &hash_err](const uint32_t* d, Hash32* out, int which) {
+                // double-buffered: chunk i+1 is copied on this thread's own non-blocking stream while chunk i is absorbed
+                uint8_t* buf[2] = {stage + (size_t)(2 * which) * CHUNK, stage + (size_t)(2 * which + 1) * CHUNK};
+                cudaStream_t s = nullptr;
+                cudaEvent_t ev[2] = {nullptr, nullptr};
+                cudaError_t e = cudaSetDevice(dev);
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+                for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+                const size_t n_chunks = (len + CHUNK - 1) / CHUNK;
+                auto fetch = [&](size_t i) {
+                    const size_t off = i * CHUNK, n = len - off < CHUNK ? len - off : CHUNK;
+                    cudaError_t r = cudaMemcpyAsync(buf[i & 1], (const uint8_t*)d + off, n, cudaMemcpyDeviceToHost, s);
+                    return r == cudaSuccess ? cudaEventRecord(ev[i & 1], s) : r;
+                };
+                blake2s::Incremental inc;
+                if (e == cudaSuccess) e = fetch(0);
+                for (size_t i = 0; i < n_chunks && e == cudaSuccess; i++) {
+                    e = cudaEventSynchronize(ev[i & 1]);
+                    if (e == cudaSuccess && i + 1 < n_chunks) e = fetch(i + 1);
+                    const size_t off = i * CHUNK, n = len - off < CHUNK ? len - off : CHUNK;
+                    if (e == cudaSuccess) inc.update(buf[i & 1], n, i + 1 < n_chunks, out->b);
+                }
+                for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+                if (s) cudaStreamDestroy(s);
+                if (e != cudaSuccess) hash_err = cudaGetErrorString(e);
+            };
+            hashers.a = std::thread(hash_dev, opt.pt_dev, &pth, 0);
+            hashers.b = std::thread(hash_dev, opt.ct_dev, &cth, 1);
+        } else {
+            hashers.a = std::thread([&] { pth = host::blake2s_bytes(plaintext, len); });
+            hashers.b = std::thread([&] { cth = host::blake2s_bytes(ciphertext, len); });
+        }
     }
 
     Channel ch;
@@ -439,6 +515,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     tiles.init(n_cache, peak_trans, tile_words, arena_p, want);
     tiles.lag = lag;
     ctx->fft_words = 0;
+    ctx->fft_words_half = 0;
     ctx->cached_tiles = n_cache;
     ctx->transient_tiles = peak_trans;
 
@@ -505,6 +582,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                                           pass == 2 && half_mode));
                 ctx->launches += nl;
                 ctx->fft_words += src.size();
+                if (pass == 2 && half_mode) ctx->fft_words_half += src.size();
                 if (overlap) {
                     CB_CUDA(cudaEventRecord(ctx->event(gi), sf));
                     CB_CUDA(cudaStreamWaitEvent(st, ctx->event(gi), 0));
@@ -596,7 +674,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     host::put_u32(stmt, (uint32_t)log_size);
     host::put_bytes(stmt, nonce, 12);
     host::put_u32(stmt, counter);
-    hashers.join();
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        hashers.join();
+        ctx->hash_wait_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (!hash_err.empty()) throw CbError("public-input hashing: " + hash_err);
     if (opt.pt_hash) {
         memcpy(pth.b, opt.pt_hash, 32);
         memcpy(cth.b, opt.ct_hash, 32);
@@ -623,9 +706,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     DBuf<uint32_t> acc_local;
     if (G > 1) acc_local = DBuf<uint32_t>(ctx, 4 * Mr);
     uint32_t* accp = G > 1 ? acc_local.p : acc.p;  // this rank's rows of the 4 accumulator columns
-    DBuf<uint32_t> apr_lo(ctx, (size_t)N_CONSTRAINTS * 4), apr_hi(ctx, (size_t)N_CONSTRAINTS * 4);
+    static const ConsTable ctab = build_cons_table(plan);
+    static const bool cons_v1 = getenv("S2C_CONS_V1") != nullptr;  // A/B switch: the integer (IMAD.WIDE) accumulation
+    DBuf<uint32_t> apr_lo(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4), apr_hi(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4);
+    DBuf<double> gtab(ctx, ctab.idx.size() * 8);
+    DBuf<int> d_cidx(ctx, ctab.idx.size());
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
-    CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
+    if (cons_v1) {
+        CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
+    } else {
+        CB_CUDA(cudaMemcpyAsync(d_cidx.p, ctab.idx.data(), ctab.idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CB_CUDA(launch_cons_table(st, apr.p, d_cidx.p, (int)ctab.idx.size(), gtab.p));
+    }
     ctx->launches += 2;
     std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);  // 1 / Z_H on the two halves of the (bit-reversed) evaluation domain
     for (uint32_t i = 0; i < den.size(); i++) {
@@ -652,7 +744,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                             c.kx, c.kb0, c.kb1, c.kb2, c.kbc, c.arg, c.type};
         if (cj.n == 0) return;
         ctx->stage_begin("constraints");
-        CB_CUDA(launch_constraints_tiles(st, cj, Mr, apr_lo.p, apr_hi.p, accp, gi == 0, cons_rows));
+        if (cons_v1) {
+            CB_CUDA(launch_constraints_tiles(st, cj, Mr, apr_lo.p, apr_hi.p, accp, gi == 0, cons_rows));
+        } else {
+            for (int k = 0; k < cj.n; k++) cj.j[k].kx = ctab.job_off[gi][k];
+            CB_CUDA(launch_constraints_tiles2(st, cj, Mr, gtab.p, accp, gi == 0, cons_rows));
+        }
         ctx->stage_end();
         ctx->launches++;
     });

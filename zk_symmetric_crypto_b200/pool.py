@@ -31,6 +31,8 @@ class ProverPool:
         be = self._be()
         if algorithm == "chacha20":
             return be.generate_chacha20_proof(key, nonce, counter, plaintext, ciphertext)
+        if algorithm == "chacha20_raw":   # proof bytes instead of the JSON result
+            return be.prove_chacha20_raw(key, nonce, counter, plaintext, ciphertext)
         if algorithm == "aes-128-ctr":
             return be.generate_aes128_ctr_proof(key, nonce, counter, plaintext, ciphertext)
         if algorithm == "aes-256-ctr":
