@@ -48,6 +48,15 @@ int cb_h2d(cb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int cb_d2h(cb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int cb_memset_zero(cb_ctx* ctx, void* dptr, size_t bytes);
 
+/* ColumnOps::bit_reverse_column (in place, 2^log_size words) and Column::{at, set} on a device column. */
+int cb_bit_reverse(cb_ctx* ctx, uint32_t* col, int log_size);
+int cb_col_at(cb_ctx* ctx, const uint32_t* col, size_t index, uint32_t* value_out_host);
+int cb_col_set(cb_ctx* ctx, uint32_t* col, size_t index, uint32_t value);
+/* FieldOps::batch_inverse: dst[i] = src[i]^-1.  QM31 columns are 4 coordinate columns `stride` words apart.  Reached by the
+ * reference through LogupTraceGenerator (aes/lookup/gen_ctr.rs:648-682). */
+int cb_batch_inverse_m31(cb_ctx* ctx, const uint32_t* src, uint32_t* dst, size_t n);
+int cb_batch_inverse_qm31(cb_ctx* ctx, const uint32_t* src, size_t src_stride, uint32_t* dst, size_t dst_stride, size_t n);
+
 /* ---- PolyOps ------------------------------------------------------------------------------------------------------ */
 /* PolyOps::precompute_twiddles for CanonicCoset(max_log).circle_domain().half_coset (and every smaller canonic domain);
  * cached in the context (air_stream.rs:185-189). */
@@ -66,6 +75,20 @@ int cb_commit_lde(cb_ctx* ctx, int src_kind, const uint32_t* src, size_t src_str
  * words (src_kind 1: 32 one-bit columns per word, 2: 4 byte columns per word); tiles_out = n_words tiles of
  * [32 or 4][2^(log_size+1)] LDE values.  This is the transform the streaming provers use (coefficients stay on chip). */
 int cb_lde_packed(cb_ctx* ctx, int src_kind, const uint32_t* src_words, int n_words, int log_size, uint32_t* tiles_out);
+/* PolyOps::extend: coefficient vectors zero-extended to 2^(log_size+log_ext) words. */
+int cb_extend(cb_ctx* ctx, const uint32_t* coeffs, size_t stride, int n_cols, int log_size, int log_ext, uint32_t* out, size_t out_stride);
+/* PolyOps::barycentric_weights / barycentric_eval_at_point: weights = 4 coordinate columns of 2^log_size words (device) such
+ * that f(point) = sum_i evals[i] * weights[i] for every f of the canonic domain of that size (evals in storage order);
+ * out_host = n_cols x 4 words. */
+int cb_barycentric_weights(cb_ctx* ctx, int log_size, const uint32_t point_host[8], uint32_t* weights_out);
+int cb_barycentric_eval_at_point(cb_ctx* ctx, const uint32_t* evals, size_t stride, int n_cols, int log_size, const uint32_t* weights,
+                                 uint32_t* out_host);
+/* PolyOps::precompute_twiddles for an arbitrary coset (initial index, log size) of the circle group: the flattened twiddle
+ * tree upstream's slow_precompute_twiddles builds (2^coset_log_size words each: per layer the x coordinates of the coset's
+ * first half in bit-reversed order, then a trailing 1) and its element-wise inverses.  The provers use the cached canonic
+ * towers of cb_precompute_twiddles. */
+int cb_precompute_twiddles_coset(cb_ctx* ctx, uint32_t coset_initial_index, int coset_log_size, uint32_t* twiddles_out,
+                                 uint32_t* itwiddles_out);
 /* ---- one large trace on several GPUs (BASELINE cfg-5) --------------------------------------------------
  * The ranks of a communicator prove ONE ChaCha20 trace together: every rank calls s2c_prove_chacha20_raw/_dev with the same
  * inputs; each rank transforms its share of the witness words (whole columns), the LDE tiles are exchanged with an NCCL
@@ -98,6 +121,12 @@ int cb_merkle_leaves_absorb(cb_ctx* ctx, const uint32_t* cols, size_t stride, in
 /* build_next_layer / legacy commit_on_layer(prev, no columns): n_parents node hashes from 2*n_parents children. */
 int cb_merkle_next_layer(cb_ctx* ctx, const uint32_t* prev_hashes, uint32_t n_parents, uint32_t* out_hashes);
 
+/* Legacy (non-lifted) MerkleOps::commit_on_layer: out[i] = Blake2s(prev[2i] || prev[2i+1] || col_0[i] || ... || col_k[i]) for the
+ * 2^log_size nodes of a layer (prev_or_null = hashes of the layer below, 2^(log_size+1) x 8 words; cols_host = host array of
+ * n_cols device column pointers).  The pinned reference commits through the lifted VCS only; kept for the BASELINE wording. */
+int cb_commit_on_layer(cb_ctx* ctx, int log_size, const uint32_t* prev_or_null, const uint32_t* const* cols_host, int n_cols,
+                       uint32_t* out);
+
 /* ---- ComponentProver::evaluate_constraint_quotients_on_domain + AccumulationOps ------------------------------------- */
 /* generate_secure_powers, reversed: out[k] = alpha^(n-1-k) (4 words each). */
 int cb_generate_secure_powers_rev(cb_ctx* ctx, const uint32_t alpha_host[4], int n, uint32_t* out_dev);
@@ -106,12 +135,57 @@ int cb_generate_secure_powers_rev(cb_ctx* ctx, const uint32_t alpha_host[4], int
 int cb_eval_constraints_chacha_stream(cb_ctx* ctx, const uint32_t* lde, size_t stride, int eval_log, int trace_log,
                                       const uint32_t* alpha_pows_rev, uint32_t* accum, size_t accum_stride, int accumulate);
 
+/* AccumulationOps::accumulate (dst += src over n_words words) and lift_and_accumulate (the 4 coordinate columns `small_cols` of a
+ * 2^small_log accumulation, 2^small_log words apart, are lifted onto the 2^big_log domain by the lifted-VCS index map and added). */
+int cb_accumulate(cb_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t n_words);
+int cb_lift_and_accumulate(cb_ctx* ctx, uint32_t* big, size_t big_stride, int big_log, const uint32_t* small_cols, int small_log);
+
+/* ---- AES-128/256-CTR AIR stages (aes/lookup/{gen_ctr,ctr}.rs, aes/sbox_table.rs) ------------------------------------------ */
+/* Column / constraint / lookup counts of the CTR component and the (input, output) trace columns of its S-box lookups in
+ * relation order (any out pointer may be NULL; the lookup arrays need n_lookups ints). */
+int cb_aes_ctr_layout(int key_len, int* n_cols, int* n_constraints, int* n_lookups, int* lookup_in_cols, int* lookup_out_cols);
+/* generate_aes{128,256}_ctr_trace_with_inputs (gen_ctr.rs:386-439, 491-544): trace_out = n_cols columns of 2^log_size words
+ * (`stride` apart, device), mults_out_host = the 256 S-box multiplicities, *valid = keystream xor plaintext == ciphertext. */
+int cb_gen_trace_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter, const uint8_t* pt_host,
+                         const uint8_t* ct_host, uint32_t n_blocks, int log_size, uint32_t* trace_out, size_t stride,
+                         uint32_t mults_out_host[256], int* valid);
+/* generate_ctr_sbox_interaction_trace (gen_ctr.rs:640-683): 4 * n_lookups / 2 coordinate columns, the last QM31 column finalised
+ * (LogupTraceGenerator::finalize_last); claimed_sum_out_host = the component's claimed sum. */
+int cb_gen_logup_interaction_aes_ctr(cb_ctx* ctx, int key_len, const uint32_t* trace, size_t stride, int log_size,
+                                     const uint32_t z_host[4], const uint32_t alpha_host[4], uint32_t* inter_out, size_t inter_stride,
+                                     uint32_t claimed_sum_out_host[4]);
+/* LogupTraceGenerator::finalize_last on one QM31 column (4 coordinate columns `stride` apart, device, in place): inclusive prefix
+ * sum in trace-coset order of (value - claimed_sum / N); returns the claimed sum. */
+int cb_logup_finalize_last(cb_ctx* ctx, uint32_t* col4, size_t stride, int log_size, uint32_t claimed_sum_out_host[4]);
+/* AESCtrEvalAtRow::ctr_block + finalize_logup_in_pairs (ctr.rs:320-364) on the 2^(trace_log+1) evaluation domain, divided by the
+ * trace-domain vanishing polynomial: lde = the CTR component's trace columns, inter_lde = its interaction columns,
+ * alpha_pows_rev = this component's n_constraints reversed powers of the composition random coefficient (device, 4 words each),
+ * accum = 4 coordinate columns (overwritten). */
+int cb_eval_constraints_aes_ctr(cb_ctx* ctx, int key_len, const uint32_t* lde, size_t stride, const uint32_t* inter_lde,
+                                size_t inter_stride, int trace_log, const uint32_t* alpha_pows_rev, const uint32_t z_host[4],
+                                const uint32_t alpha_host[4], const uint32_t claimed_sum_host[4], uint32_t* accum, size_t accum_stride);
+/* SboxTableEval::evaluate (sbox_table.rs:103-120) on its own 2^9 evaluation domain (columns of 512 words): preprocessed input /
+ * output columns, multiplicity column, the table's interaction columns (4, inter_stride apart), alpha_pow = the power of the
+ * composition random coefficient of its single constraint; accum = 4 x 512 words. */
+int cb_eval_constraints_sbox_table(cb_ctx* ctx, const uint32_t* pre_in_lde, const uint32_t* pre_out_lde, const uint32_t* mult_lde,
+                                   const uint32_t* inter_lde, size_t inter_stride, const uint32_t z_host[4], const uint32_t alpha_host[4],
+                                   const uint32_t claimed_sum_host[4], const uint32_t alpha_pow_host[4], uint32_t* accum);
+
 /* ---- QuotientOps / FriOps / GrindOps -------------------------------------------------------------------------------- */
 /* accumulate_quotients for one sample point shared by all columns (the ChaCha case): sampled_host = n_cols x 4 words,
  * point_host = {x[4], y[4]}, random_coeff_host[4]; out = 4 coordinate columns on the 2^domain_log domain. */
 int cb_accumulate_quotients(cb_ctx* ctx, const uint32_t* cols, size_t stride, int n_cols, int domain_log,
                             const uint32_t* sampled_host, const uint32_t point_host[8], const uint32_t random_coeff_host[4],
                             uint32_t* out, size_t out_stride);
+/* accumulate_quotients in its general form: columns of different sizes (col_ptrs_host[j] = device pointer, col_logs_host[j] =
+ * log size of the column's evaluation; smaller columns are read through the lifted-VCS index map), sample batches grouped by
+ * point (batch b owns entries [batch_offsets[b], batch_offsets[b+1])), and for every entry the column, its sampled value and the
+ * power of the quotient random coefficient assigned to that (column, sample) pair.  Batches are summed, as the pinned stwo rev
+ * does.  Used by the AES-CTR prover (mask [-1, 0] samples, periodicity samples, lifted S-box table columns). */
+int cb_accumulate_quotients_batches(cb_ctx* ctx, const uint32_t* const* col_ptrs_host, const int* col_logs_host, int n_cols,
+                                    int domain_log, int n_batches, const uint32_t* batch_points_host, const int* batch_offsets_host,
+                                    const int* entry_col_host, const uint32_t* entry_value_host, const uint32_t* entry_alpha_host,
+                                    uint32_t* out, size_t out_stride);
 int cb_fold_circle_into_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t alpha_host[4],
                              uint32_t* dst, size_t dst_stride, int dst_is_zero);
 int cb_fold_line(cb_ctx* ctx, const uint32_t* src, size_t src_stride, int src_log, const uint32_t alpha_host[4], uint32_t* dst,
@@ -157,6 +231,10 @@ int s2c_prove_chacha20_raw(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 int s2c_prove_chacha20_dev(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const void* pt_dev,
                            const void* ct_dev, size_t len, const uint8_t pt_hash[32], const uint8_t ct_hash[32],
                            uint8_t** proof_out, size_t* proof_len);
+/* prove_stream::<Blake2sMerkleChannel>(log_size, PcsConfig::default()) of the reference (air_stream.rs:237-289): its own test-data
+ * generator (key 00..1f, witness nonce 00 00 00 00 4a .., block r: counter r+1, plaintext word w = 16r + w; the statement binds an
+ * all-zero nonce, counter 1 and empty-string hashes).  Returns the bincode StreamProof the reference's generator returns. */
+int s2c_prove_chacha20_stream_testdata(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len);
 /* Per-stage device times (ms) of the last proof on ctx when profiling is enabled: "name=ms;name=ms;..." */
 int cb_set_profile(cb_ctx* ctx, int enable);
 const char* cb_stage_times(cb_ctx* ctx);

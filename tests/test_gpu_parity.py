@@ -255,6 +255,30 @@ def test_proof_matches_oracle_bytes(backend):
     assert got == want
 
 
+@pytest.mark.parametrize("log_size", [4, 6])
+def test_prove_stream_testdata_generator_matches_oracle(backend, log_size):
+    """s2c_prove_chacha20_stream_testdata = the reference's own `prove_stream` generator (air_stream.rs:237-289: key 00..1f, witness
+    nonce words [0, 0x4a, 0], counters r+1, plaintext word 16r+w, statement over an all-zero nonce and empty-string hashes),
+    against the oracle's prover on the same inputs; the host verifier accepts it for exactly those public inputs."""
+    import struct
+    import zk_symmetric_crypto_b200 as z
+    n = 1 << log_size
+    key = bytes(range(32))
+    wnonce = struct.pack("<3I", 0, 0x4A, 0)
+    pt = np.arange(16 * n, dtype=np.uint32).reshape(n, 16)
+    ks = np.frombuffer(ca.chacha20_keystream_bytes(key, wnonce, 1, n), dtype="<u4").reshape(n, 16)
+    ct = pt ^ ks
+    K = np.tile(np.frombuffer(key, dtype="<u4").astype(np.uint32), (n, 1))      # per-row arrays (the reference splats them)
+    NO = np.tile(np.array([0, 0x4A, 0], dtype=np.uint32), (n, 1))
+    C = (1 + np.arange(n)).astype(np.uint32)
+    pub = oracle_api.chacha_public_inputs(bytes(12), 1, b"", b"")
+    want = oracle_api.prove_stream_internal(log_size, K, NO, C, pt, ct, pub)
+    got = backend.prove_chacha20_stream_testdata(log_size)
+    assert got == want
+    assert z.verify_chacha20_raw(got, bytes(12), 1, b"", b"") == (True, None)
+    assert z.verify_chacha20_raw(got, wnonce, 1, b"", b"")[0] is False
+
+
 def test_proof_independent_of_tile_cache(backend):
     """The streaming prover recomputes LDE tiles that do not fit the cache; the proof must not depend on the cache size."""
     key, nonce, counter, pt, ct = case_inputs(16, 33)

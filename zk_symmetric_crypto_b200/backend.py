@@ -24,6 +24,11 @@ EXPORTED_SYMBOLS = [
     "s2c_verify_chacha20_proof", "s2c_verify_aes_ctr_proof", "s2c_verify_chacha20_raw", "s2c_verify_aes_ctr_raw",
     "s2c_prove_chacha20_encrypt", "s2c_prove_aes128_ctr_encrypt", "s2c_prove_aes256_ctr_encrypt",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
+    "s2c_prove_chacha20_stream_testdata",
+    "cb_bit_reverse", "cb_col_at", "cb_col_set", "cb_batch_inverse_m31", "cb_batch_inverse_qm31", "cb_extend",
+    "cb_barycentric_weights", "cb_barycentric_eval_at_point", "cb_precompute_twiddles_coset", "cb_commit_on_layer",
+    "cb_accumulate", "cb_lift_and_accumulate", "cb_accumulate_quotients_batches", "cb_aes_ctr_layout", "cb_gen_trace_aes_ctr",
+    "cb_gen_logup_interaction_aes_ctr", "cb_logup_finalize_last", "cb_eval_constraints_aes_ctr", "cb_eval_constraints_sbox_table",
 ]
 
 
@@ -180,6 +185,15 @@ class Backend:
         rc = self.L.s2c_prove_chacha20_raw(self.ctx, kb, nb, ctypes.c_uint32(counter & 0xFFFFFFFF), pb, cbuf,
                                            ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n))
         self._ck(rc)
+        proof = ctypes.string_at(out, n.value)
+        self.L.s2c_free(out)
+        return proof
+
+    def prove_chacha20_stream_testdata(self, log_size):
+        """The reference's `prove_stream` test-data generator (air_stream.rs:237-289) at `log_size`; returns the proof bytes."""
+        out = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self._ck(self.L.s2c_prove_chacha20_stream_testdata(self.ctx, int(log_size), ctypes.byref(out), ctypes.byref(n)))
         proof = ctypes.string_at(out, n.value)
         self.L.s2c_free(out)
         return proof

@@ -652,14 +652,12 @@ int s2c_prove_aes_ctr_raw(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     CB_CATCH(ctx)
 }
 
-int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
-                                 char** json_out, size_t* json_len) {
-    // wasm_api.rs:953-990: native block function (chacha/block.rs:95), hex of the 64 keystream bytes
-    if (key_len != 32 || nonce_len != 12) return ret_json(json_error("Invalid key or nonce length"), json_out, json_len);
+// native ChaCha20 block function (chacha/block.rs:95): out = keystream words of one block
+static void chacha_block_words(const uint32_t key[8], const uint32_t nonce[3], uint32_t counter, uint32_t out[16]) {
     uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u}, v[16];
-    for (int i = 0; i < 8; i++) s[4 + i] = host::load_le32(key + 4 * i);
+    for (int i = 0; i < 8; i++) s[4 + i] = key[i];
     s[12] = counter;
-    for (int i = 0; i < 3; i++) s[13 + i] = host::load_le32(nonce + 4 * i);
+    for (int i = 0; i < 3; i++) s[13 + i] = nonce[i];
     memcpy(v, s, sizeof v);
     auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
     auto qr = [&](int a, int b, int c, int d) {
@@ -670,14 +668,62 @@ int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8
         qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
         qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
     }
+    for (int i = 0; i < 16; i++) out[i] = v[i] + s[i];
+}
+
+int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
+                                 char** json_out, size_t* json_len) {
+    // wasm_api.rs:953-990: native block function, hex of the 64 keystream bytes
+    if (key_len != 32 || nonce_len != 12) return ret_json(json_error("Invalid key or nonce length"), json_out, json_len);
+    uint32_t kw[8], nw[3], ks[16];
+    for (int i = 0; i < 8; i++) kw[i] = host::load_le32(key + 4 * i);
+    for (int i = 0; i < 3; i++) nw[i] = host::load_le32(nonce + 4 * i);
+    chacha_block_words(kw, nw, counter, ks);
     static const char* H = "0123456789abcdef";
     std::string hex;
     for (int i = 0; i < 16; i++) {
-        uint32_t w = v[i] + s[i];
-        for (int b = 0; b < 4; b++) { uint8_t x = (uint8_t)(w >> (8 * b)); hex.push_back(H[x >> 4]); hex.push_back(H[x & 15]); }
+        for (int b = 0; b < 4; b++) { uint8_t x = (uint8_t)(ks[i] >> (8 * b)); hex.push_back(H[x >> 4]); hex.push_back(H[x & 15]); }
     }
     std::string js = "{\"counter\":" + std::to_string(counter) + ",\"key_len\":32,\"keystream_hex\":\"" + hex + "\",\"nonce_len\":12}";
     return ret_json(js, json_out, json_len);
+}
+
+// prove_stream::<Blake2sMerkleChannel>(log_size, PcsConfig::default()) of the reference (air_stream.rs:237-289): the test-data
+// generator behind its `bench_stream` / round-trip tests -- key 00..1f, witness nonce words [0, 0x4a, 0], block r (0-based) has
+// counter r + 1 and plaintext word w = r * 16 + w, ciphertext = its ChaCha20 encryption; the STATEMENT binds an all-zero nonce,
+// counter 1 and the hashes of empty strings.  Lets anyone with cargo compare bytes with the reference's own generator
+// (integration/rust/examples/prove_stream_dump.rs).
+int s2c_prove_chacha20_stream_testdata(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len) {
+    CtxUse use(ctx);
+    ctx = use.ctx;
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (log_size < 4 || log_size > 24) throw CbError("log_size must be in [4, 24]");
+    const size_t n_blocks = (size_t)1 << log_size;
+    uint32_t kw[8], nw[3] = {0, 0x4a, 0};
+    for (int i = 0; i < 8; i++) kw[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
+    std::vector<uint32_t> pt(n_blocks * 16), ct(n_blocks * 16);
+    for (size_t r = 0; r < n_blocks; r++) {
+        uint32_t ks[16];
+        chacha_block_words(kw, nw, (uint32_t)(r + 1), ks);
+        for (int w = 0; w < 16; w++) {
+            pt[r * 16 + w] = (uint32_t)(r * 16 + w);
+            ct[r * 16 + w] = pt[r * 16 + w] ^ ks[w];
+        }
+    }
+    uint8_t key[32], nonce[12];
+    static const uint8_t zero_nonce[12] = {0};
+    memcpy(key, kw, 32);
+    memcpy(nonce, nw, 12);
+    ProveOptions opt;
+    opt.empty_public_hashes = true;
+    opt.stmt_nonce = zero_nonce;
+    std::vector<uint8_t> proof;
+    std::string e = prove_chacha20(ctx, key, nonce, 1, (const uint8_t*)pt.data(), (const uint8_t*)ct.data(), n_blocks * 64, proof, opt);
+    if (!e.empty()) throw CbError(e);
+    give_proof(proof, proof_out, proof_len);
+    CB_CATCH(ctx)
 }
 
 int s2c_get_circuits_info(char** json_out, size_t* json_len) {

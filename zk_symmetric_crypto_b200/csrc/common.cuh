@@ -105,6 +105,15 @@ cudaError_t launch_aes_constraints(cudaStream_t st, const AesConsArgs& a);
 cudaError_t launch_aes_table_constraint(cudaStream_t st, const AesTableArgs& a);
 cudaError_t launch_lift_accumulate(cudaStream_t st, uint32_t* big, size_t big_stride, int big_log, const uint32_t* small, int small_log);
 
+// ---- small backend-trait kernels (kernels_ops.cu)
+cudaError_t launch_bit_reverse(cudaStream_t st, uint32_t* col, int log_size);
+cudaError_t launch_inverse_m31(cudaStream_t st, const uint32_t* src, uint32_t* dst, size_t n);
+cudaError_t launch_inverse_qm31(cudaStream_t st, const uint32_t* src, size_t s_stride, uint32_t* dst, size_t d_stride, size_t n);
+size_t logup_finalize_scratch_words(int log);
+cudaError_t launch_logup_finalize_last(cudaStream_t st, uint32_t* col, size_t stride, int log, uint32_t* scratch, uint32_t** claimed_dev);
+cudaError_t launch_commit_on_layer(cudaStream_t st, const uint32_t* prev, const uint32_t* const* cols_dev, int n_cols, uint32_t n_nodes,
+                                   uint32_t* out);
+
 // optional per-kernel profiling callback (begin=1 before a launch, begin=0 after it)
 struct StageHook {
     void (*fn)(void* user, const char* name, int begin);

@@ -131,6 +131,87 @@ __global__ void __launch_bounds__(256) leaves_kernel(LeafGroups groups, int lift
     }
 }
 
+// Streaming prover form: every group is a whole number of 64-byte blocks (a multiple of 16 columns) of lifting-size columns,
+// i.e. no lifting, no partially filled block between groups.  The hot loop has ONE compress call site: the general kernel
+// above inlines the 10 unrolled rounds (~18 KB of code each) at five places, and the two that alternate inside a quarter-round
+// group (fused adder sums / plain columns) thrash the instruction cache -- ncu showed `no_instruction` as its largest stall
+// reason (5.1 stalled warps per issue, profiles/ncu_r02_leaves_kernel.csv).
+template <bool FMA>
+__global__ void __launch_bounds__(128) leaves_tiles_kernel(LeafGroups groups, int lifting_log, uint32_t* __restrict__ h_state,
+                                                           uint64_t bytes_before, int is_first, int is_final,
+                                                           uint32_t* __restrict__ out, uint32_t one) {
+    const uint32_t n_leaves = 1u << lifting_log;
+    const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    uint32_t h[8];
+    if (is_first) {
+        blake2s::init(h);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) h[w] = h_state[(size_t)w * n_leaves + leaf];
+    }
+    uint64_t t = bytes_before;
+    int blocks_left = 0;
+    for (int gi = 0; gi < groups.n; gi++) blocks_left += groups.g[gi].ncols >> 4;
+    int gi = 0, c = 0;
+    uint32_t cin = 0;
+    const uint32_t *p = nullptr, *pb = nullptr, *pc = nullptr;
+    uint32_t* pr = nullptr;
+    size_t stride = 0;
+    int ncols = 0;
+#pragma unroll 1
+    for (; blocks_left > 0; blocks_left--) {
+        if (c == ncols) {  // next group
+            const LeafGroup& g = groups.g[gi++];
+            p = g.base + leaf;
+            pb = g.cy ? g.b + leaf : nullptr;
+            pc = g.cy ? g.cy + leaf : nullptr;
+            pr = g.cy ? g.res + leaf : nullptr;
+            stride = g.stride;
+            ncols = g.ncols;
+            c = 0;
+            cin = 0;
+        }
+        uint32_t m[16];
+        if (pc != nullptr) {
+            // adder-sum word computed on the fly from its operand tiles (8 columns at a time: all loads of a half first, the
+            // stores may alias an operand tile); plain loads: the operands may have been written by this thread earlier
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t av[8], bv[8], cv[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const size_t o = (size_t)(c + 8 * half + w) * stride;
+                    av[w] = p[o];
+                    bv[w] = pb[o];
+                    cv[w] = pc[o];
+                }
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const uint32_t v = m31d::subm(m31d::addm(m31d::addm(av[w], bv[w]), cin), m31d::dbl(cv[w]));
+                    pr[(size_t)(c + 8 * half + w) * stride] = v;
+                    m[8 * half + w] = v;
+                    cin = cv[w];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; w++) m[w] = __ldg(p + (size_t)(c + w) * stride);
+        }
+        c += 16;
+        t += 64;
+        const bool last = is_final && blocks_left == 1;
+        if (FMA) blake2s::compress_fma(h, m, t, last, one); else blake2s::compress(h, m, t, last);
+    }
+    if (is_final) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) out[(size_t)leaf * 8 + w] = h[w];
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) h_state[(size_t)w * n_leaves + leaf] = h[w];
+    }
+}
+
 // parent[i] = Blake2s(child[2i] || child[2i+1]); hashes are 8 consecutive u32
 __global__ void __launch_bounds__(256) nodes_kernel(const uint4* __restrict__ prev, uint32_t n_parents, uint4* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +233,15 @@ cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int 
     int threads = n >= 128 * 148 * 2 ? 128 : 64;
     if (n < 64) threads = 32;
     static const int variant = getenv("S2C_BLAKE_FMA") ? atoi(getenv("S2C_BLAKE_FMA")) : 1;
+    static const bool general_only = getenv("S2C_LEAVES_GENERAL") != nullptr;  // A/B switch
+    bool tiles = !general_only && groups.n > 0 && variant;
+    for (int gi = 0; gi < groups.n; gi++)
+        if (groups.g[gi].ncols % 16 != 0 || groups.g[gi].log_size != lifting_log) tiles = false;
+    if (tiles) {
+        merk::leaves_tiles_kernel<true><<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before,
+                                                                                         is_first, is_final, out, 1u);
+        return cudaGetLastError();
+    }
     if (variant)
         merk::leaves_kernel<true><<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before,
                                                                                    is_first, is_final, out, 1u);

@@ -102,6 +102,10 @@ AesLayout aes_make_layout(int nr) {
     L.n_constraints = k + (int)L.lk_in.size() / 2;
     return L;
 }
+// shared with the stage-level C ABI (cb_api_ext.cu)
+std::vector<uint8_t> aes_expand_key(const uint8_t* key, int key_len) { return expand_key(key, key_len); }
+const uint8_t* aes_sbox() { return tables().sbox; }
+
 namespace {
 using Layout = AesLayout;
 Layout make_layout(int nr) { return aes_make_layout(nr); }
@@ -316,11 +320,14 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         CB_CUDA(cudaMemcpyAsync(d_out.p, lay.lk_out.data(), NL * 4, cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_aes_interaction(st, T.p, N, n, d_in.p, d_out.p, NL, z, alpha, I.p, N));
         ctx->launches++;
-        std::vector<uint32_t> last(4 * N);
-        CB_CUDA(cudaMemcpyAsync(last.data(), I.p + (size_t)(NI - 4) * N, 4 * N * 4, cudaMemcpyDeviceToHost, st));
-        ctx->sync();
-        csum = finalize_last(last, n);
-        CB_CUDA(cudaMemcpyAsync(I.p + (size_t)(NI - 4) * N, last.data(), 4 * N * 4, cudaMemcpyHostToDevice, st));
+        {   // LogupTraceGenerator::finalize_last on the device: scan in coset order, claimed sum = its last element
+            DBuf<uint32_t> fscr(ctx, logup_finalize_scratch_words(n));
+            uint32_t* d_claimed = nullptr;
+            CB_CUDA(launch_logup_finalize_last(st, I.p + (size_t)(NI - 4) * N, N, n, fscr.p, &d_claimed));
+            ctx->launches += 3;
+            CB_CUDA(cudaMemcpyAsync(csum.v, d_claimed, 16, cudaMemcpyDeviceToHost, st));
+            ctx->sync();
+        }
         // table side: -mult / combine(i, SBOX[i]) over the 256 rows, one column
         std::vector<uint32_t> tcol(4 * 256);
         for (int i = 0; i < 256; i++) {

@@ -672,7 +672,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- statement (the two public-input hashes were computed on host threads while the GPU ran pass 1)
     std::vector<uint8_t> stmt;
     host::put_u32(stmt, (uint32_t)log_size);
-    host::put_bytes(stmt, nonce, 12);
+    host::put_bytes(stmt, opt.stmt_nonce ? opt.stmt_nonce : nonce, 12);
     host::put_u32(stmt, counter);
     {
         const auto t0 = std::chrono::steady_clock::now();

@@ -24,6 +24,8 @@ struct PcsConfig {
 struct ProveOptions {
     int force_log_size = 0;            // prove on a larger trace than the block count needs (rows beyond are default rows)
     bool empty_public_hashes = false;  // hash empty byte strings into the statement (reference test-data generator)
+    const uint8_t* stmt_nonce = nullptr;  // statement nonce when it differs from the witness nonce (the same generator:
+                                          // air_stream.rs:282-283 binds an all-zero nonce while the witness uses 00 00 00 00 4a ..)
     // plaintext/ciphertext already resident on the device (skips the H2D copies); the caller then supplies the two
     // Blake2s public-input hashes (ChaChaPublicInputs::new, air_stream.rs:44-53), which are host work in the reference too
     const uint32_t* pt_dev = nullptr;
@@ -60,6 +62,8 @@ struct AesLayout {
     std::vector<int> lk_in, lk_out;  // S-box lookup (input, output) columns in relation order
 };
 AesLayout aes_make_layout(int n_rounds);
+std::vector<uint8_t> aes_expand_key(const uint8_t* key, int key_len);  // aes/mod.rs:213-270
+const uint8_t* aes_sbox();                                             // aes/mod.rs:10-30
 
 // ChaCha20 stream AIR on QM31 mask values; alpha_powers_rev[k] = alpha^(K-1-k)
 m31::QM31 chacha_constraints_at_mask(const std::vector<m31::QM31>& mask, const std::vector<m31::QM31>& alpha_powers_rev);
