@@ -7,7 +7,7 @@ Restates (un-vendored stwo rev f117d487, module paths as embedded in the referen
   core/fri.rs, core/queries.rs, prover/air/accumulation.rs, constraint-framework prover/component_prover.rs.
 Reference call sites: /root/reference/stwo/src/chacha/bitwise/air_stream.rs:160-234 (prove_stream_internal),
 containers air_stream.rs:30-131, serialisation wasm_api.rs:588-601 (bincode 1.3 defaults + base64).
-Pinned byte-for-byte against oracle/_ref (tests/test_oracle_vs_reference.py).
+Pinned byte-for-byte against oracle/_ref (tests/test_oracle.py, tests/test_oracle_aes.py).
 """
 import struct
 import numpy as np

@@ -7,7 +7,7 @@ f117d487b39cd4441c2dbbdd7127b186f9c23564 (/root/reference/stwo/Cargo.toml:16-17)
 /root/reference, so every function below restates the *published* algorithm of that crate (module path given in
 each docstring, as embedded in the reference's WASM build) and is PINNED against the reference itself:
 oracle/_ref/libs2c_ref.so (the reference's shipped WASM, compiled natively) must produce byte-identical proofs
-(tests/test_oracle_vs_reference.py, tests/golden/).  Call sites in the reference: /root/reference/stwo/src/
+(tests/test_oracle.py, tests/test_oracle_aes.py, tests/golden/).  Call sites in the reference: /root/reference/stwo/src/
 chacha/bitwise/air_stream.rs:185-231 and aes/lookup/air_ctr.rs:328-414.
 """
 import hashlib

@@ -56,8 +56,9 @@ struct cb_ctx {
     // proofs -- re-allocating ~170 GB from the stream-ordered pool per proof costs up to 0.3 s when the pool has fragmented
     void* arena = nullptr;
     size_t arena_bytes = 0;
-    // pinned staging for reading device-resident inputs back while they are hashed (two hasher threads x two chunks)
+    // pinned staging for reading device-resident inputs back before they are hashed on the host
     uint8_t* hash_stage = nullptr;
+    size_t hash_stage_bytes = 0;
     uint64_t hash_wait_us = 0;  // host time the last proof waited for the public-input hashes after the commitment pass
     void* ensure_arena(size_t bytes);
     void release_arena();

@@ -155,33 +155,37 @@ __global__ void __launch_bounds__(128) leaves_tiles_kernel(LeafGroups groups, in
     for (int gi = 0; gi < groups.n; gi++) blocks_left += groups.g[gi].ncols >> 4;
     int gi = 0, c = 0;
     uint32_t cin = 0;
+    // Addresses are formed as (uniform 64-bit tile base) + 4 * (32-bit word index): one IMAD.WIDE on the FMA pipe per load
+    // instead of a 64-bit pointer increment (IADD3 + IADD3.X) on the ALU pipe, which is the pipe Blake2s saturates.
+    // A tile has at most 2^26 words (32 columns of 2^21 rows), so the index fits 32 bits.
     const uint32_t *p = nullptr, *pb = nullptr, *pc = nullptr;
     uint32_t* pr = nullptr;
-    size_t stride = 0;
+    uint32_t stride = 0;
     int ncols = 0;
 #pragma unroll 1
     for (; blocks_left > 0; blocks_left--) {
         if (c == ncols) {  // next group
             const LeafGroup& g = groups.g[gi++];
-            p = g.base + leaf;
-            pb = g.cy ? g.b + leaf : nullptr;
-            pc = g.cy ? g.cy + leaf : nullptr;
-            pr = g.cy ? g.res + leaf : nullptr;
-            stride = g.stride;
+            p = g.base;
+            pb = g.b;
+            pc = g.cy;
+            pr = g.res;
+            stride = (uint32_t)g.stride;
             ncols = g.ncols;
             c = 0;
             cin = 0;
         }
         uint32_t m[16];
+        const uint32_t i0 = (uint32_t)c * stride + leaf;
         if (pc != nullptr) {
-            // adder-sum word computed on the fly from its operand tiles (8 columns at a time: all loads of a half first, the
-            // stores may alias an operand tile); plain loads: the operands may have been written by this thread earlier
+            // adder-sum word computed on the fly from its operand tiles (8 columns at a time: all loads of a half first);
+            // plain loads: the operands may have been written by this thread earlier
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 uint32_t av[8], bv[8], cv[8];
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
-                    const size_t o = (size_t)(c + 8 * half + w) * stride;
+                    const uint32_t o = i0 + (uint32_t)(8 * half + w) * stride;
                     av[w] = p[o];
                     bv[w] = pb[o];
                     cv[w] = pc[o];
@@ -189,14 +193,14 @@ __global__ void __launch_bounds__(128) leaves_tiles_kernel(LeafGroups groups, in
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
                     const uint32_t v = m31d::subm(m31d::addm(m31d::addm(av[w], bv[w]), cin), m31d::dbl(cv[w]));
-                    pr[(size_t)(c + 8 * half + w) * stride] = v;
+                    pr[i0 + (uint32_t)(8 * half + w) * stride] = v;
                     m[8 * half + w] = v;
                     cin = cv[w];
                 }
             }
         } else {
 #pragma unroll
-            for (int w = 0; w < 16; w++) m[w] = __ldg(p + (size_t)(c + w) * stride);
+            for (int w = 0; w < 16; w++) m[w] = __ldg(p + (i0 + (uint32_t)w * stride));
         }
         c += 16;
         t += 64;

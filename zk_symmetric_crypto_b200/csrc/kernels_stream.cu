@@ -157,35 +157,39 @@ struct AccF64 {
     __device__ __forceinline__ uint32_t result(int c) const { return addm(mulm(red64(hi[c]), 1u << 16), red64(lo[c])); }
 };
 
-// one adder (+ xor-rotate) job; table slice: step s -> [carry boolean, sum boolean(, xor, result boolean)] x 8 doubles
+// one adder (+ xor-rotate) job; table slice: step s -> [carry boolean, sum boolean(, xor, result boolean)] x 8 doubles.
+// The 32 steps run in batches of SB (all loads of a batch are issued before its arithmetic).  CONS2_PREFETCH=1 issues the loads
+// of batch k+1 before the arithmetic of batch k (two register sets, ping-pong): measured SLOWER at every (SB, blocks per SM)
+// tried (70-78 ms vs 68 ms per proof at log 20, profiles/r02_summary.md) -- the extra registers cost more resident warps than
+// the earlier loads win; kept as a build switch.  No tile of a job aliases its sum tile (own slot in the arena).
+#ifndef CONS2_SB
+#define CONS2_SB 4
+#endif
+#ifndef CONS2_PREFETCH
+#define CONS2_PREFETCH 0
+#endif
 template <bool HAS_X>
-__device__ __forceinline__ void addx_job2(const ConstraintJob& J, size_t row, size_t M, const double* __restrict__ tab, AccF64& A) {
-    const uint32_t* x = HAS_X ? J.t0 + row : nullptr;
-    const uint32_t* a = J.t1 + row;
-    const uint32_t* d = HAS_X ? J.t2 + row : nullptr;
-    const uint32_t* b = J.t3 + row;
-    const uint32_t* cy = J.t4 + row;
-    uint32_t* res = J.res + row;
-    constexpr int NE = HAS_X ? 4 : 2;
-    constexpr int SB = 4;  // steps per batch of loads (all loads of a batch are issued before its arithmetic)
-    uint32_t cin = 0;
-#pragma unroll 1
-    for (int s0 = 0; s0 < 32; s0 += SB) {
-        uint32_t av[SB], bv[SB], cv[SB], xv[SB], dv[SB];
+struct AddxBatch {
+    uint32_t av[CONS2_SB], bv[CONS2_SB], cv[CONS2_SB], xv[CONS2_SB], dv[CONS2_SB];
+    __device__ __forceinline__ void load(const uint32_t* x, const uint32_t* a, const uint32_t* d, const uint32_t* b, const uint32_t* cy,
+                                         size_t M, int s0, int rot) {
 #pragma unroll
-        for (int u = 0; u < SB; u++) {
+        for (int u = 0; u < CONS2_SB; u++) {
             const int s = s0 + u;
             av[u] = a[(size_t)s * M];
             bv[u] = b[(size_t)s * M];
             cv[u] = cy[(size_t)s * M];
             if (HAS_X) {
-                xv[u] = x[(size_t)((s + J.arg) & 31) * M];
+                xv[u] = x[(size_t)((s + rot) & 31) * M];
                 dv[u] = d[(size_t)s * M];
             }
         }
+    }
+    __device__ __forceinline__ void compute(uint32_t* res, size_t M, int s0, uint32_t& cin, const double* __restrict__ tab, AccF64& A) const {
+        constexpr int NE = HAS_X ? 4 : 2;
         const double* __restrict__ e = tab + (size_t)s0 * NE * 8;
 #pragma unroll
-        for (int u = 0; u < SB; u++) {
+        for (int u = 0; u < CONS2_SB; u++) {
             const int s = s0 + u;
             const uint32_t c2 = cv[u] + cv[u];
             const uint32_t sv = subm(redp(redp(av[u] + bv[u]) + cin), redp(c2));
@@ -202,8 +206,41 @@ __device__ __forceinline__ void addx_job2(const ConstraintJob& J, size_t row, si
                 A.mac(e + (u * NE + 3) * 8, bool_c(xv[u], xv[u] + xv[u]));
             }
         }
-        if ((s0 & SB) != 0) A.fold();  // every 8 steps: at most 32 products since the last fold
     }
+};
+
+template <bool HAS_X>
+__device__ __forceinline__ void addx_job2(const ConstraintJob& J, size_t row, size_t M, const double* __restrict__ tab, AccF64& A) {
+    const uint32_t* x = HAS_X ? J.t0 + row : nullptr;
+    const uint32_t* a = J.t1 + row;
+    const uint32_t* d = HAS_X ? J.t2 + row : nullptr;
+    const uint32_t* b = J.t3 + row;
+    const uint32_t* cy = J.t4 + row;
+    uint32_t* res = J.res + row;
+    constexpr int SB = CONS2_SB;
+    constexpr int FOLD = (HAS_X ? 8 : 16);  // steps between folds: at most 32 products per accumulator
+    uint32_t cin = 0;
+#if CONS2_PREFETCH
+    AddxBatch<HAS_X> B0, B1;
+    B0.load(x, a, d, b, cy, M, 0, J.arg);
+#pragma unroll 1
+    for (int s0 = 0; s0 < 32; s0 += 2 * SB) {
+        B1.load(x, a, d, b, cy, M, s0 + SB, J.arg);
+        B0.compute(res, M, s0, cin, tab, A);
+        if ((s0 + SB) % FOLD == 0) A.fold();
+        if (s0 + 2 * SB < 32) B0.load(x, a, d, b, cy, M, s0 + 2 * SB, J.arg);
+        B1.compute(res, M, s0 + SB, cin, tab, A);
+        if ((s0 + 2 * SB) % FOLD == 0) A.fold();
+    }
+#else
+#pragma unroll 1
+    for (int s0 = 0; s0 < 32; s0 += SB) {
+        AddxBatch<HAS_X> B;
+        B.load(x, a, d, b, cy, M, s0, J.arg);
+        B.compute(res, M, s0, cin, tab, A);
+        if ((s0 + SB) % FOLD == 0) A.fold();
+    }
+#endif
 }
 
 // jobs.j[k].kx = offset (in constraints) of job k's slice inside `gtab`; slice sizes: CJ_BOOL 32, CJ_ADDX 128 (64 without the xor
@@ -382,6 +419,76 @@ __global__ void __launch_bounds__(256) bitcol_dot_kernel2(const uint32_t* __rest
             if ((w >> b) & 1u) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[b][c] += t[c];
+            }
+        }
+    }
+    __shared__ uint32_t red[8][32];
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t v = red64(__double2ull_rz(acc[b][c]));
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v = addm(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][b * 4 + c] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int g = threadIdx.x >> 5, x = threadIdx.x & 31;  // x = bit*4 + c
+        uint32_t v = addm(red[2 * g][x], red[2 * g + 1][x]);
+        if (gridDim.y == 1) v = mulm(v, scale);
+        out[(size_t)blockIdx.y * slice_stride + (word * 32 + 8 * g) * 4 + x] = v;
+    }
+}
+
+// v3: the FP64 form with the rows staged through shared memory.  v2 was latency-bound (ncu: 12.7 warps stalled on the long
+// scoreboard per issue, 2 blocks of 95 registers per SM): every thread waited for its own five loads before 32 short adds.  Here
+// the block loads a tile of 256 rows cooperatively (one row per thread, the four weights converted to double once per row instead
+// of once per byte group), the next tile's loads are in flight while the current one is summed, and the adds read shared memory.
+__global__ void __launch_bounds__(256) bitcol_dot_kernel3(const uint32_t* __restrict__ W, size_t N, const uint32_t* __restrict__ wt,
+                                                          uint32_t scale, uint32_t* __restrict__ out, const int* __restrict__ words,
+                                                          size_t rows_per_slice, size_t slice_stride) {
+    __shared__ uint32_t s_w[2][256];
+    __shared__ double s_t[2][4][256];
+    const int lane = threadIdx.x & 63, bg = threadIdx.x >> 6;
+    const size_t word = words ? (size_t)words[blockIdx.x] : (size_t)blockIdx.x;
+    const uint32_t* __restrict__ wrow = W + word * N;
+    const size_t r_begin = (size_t)blockIdx.y * rows_per_slice;
+    const size_t r_end = r_begin + rows_per_slice < N ? r_begin + rows_per_slice : N;
+    double acc[8][4];
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[b][c] = 0.0;
+    uint32_t pw = 0, pt[4] = {0, 0, 0, 0};
+    auto fetch = [&](size_t r0) {
+        const size_t r = r0 + threadIdx.x;
+        if (r < r_end) {
+            pw = __ldg(wrow + r);
+#pragma unroll
+            for (int c = 0; c < 4; c++) pt[c] = __ldg(wt + (size_t)c * N + r);
+        } else {
+            pw = 0;  // rows beyond the slice contribute nothing
+        }
+    };
+    fetch(r_begin);
+    int buf = 0;
+    for (size_t r0 = r_begin; r0 < r_end; r0 += 256, buf ^= 1) {
+        s_w[buf][threadIdx.x] = pw;
+#pragma unroll
+        for (int c = 0; c < 4; c++) s_t[buf][c][threadIdx.x] = __uint2double_rn(pt[c]);
+        __syncthreads();
+        if (r0 + 256 < r_end) fetch(r0 + 256);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int row = lane + 64 * j;
+            const uint32_t w = s_w[buf][row] >> (8 * bg);
+            const double t0 = s_t[buf][0][row], t1 = s_t[buf][1][row], t2 = s_t[buf][2][row], t3 = s_t[buf][3][row];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                if ((w >> b) & 1u) {
+                    acc[b][0] += t0; acc[b][1] += t1; acc[b][2] += t2; acc[b][3] += t3;
+                }
             }
         }
     }
@@ -655,17 +762,21 @@ cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int 
     // (a byte-bucket variant - shared-memory atomics on 16-bit halves, 32 per row - measured 31 vs 18 ms; not kept)
     int slices = 1;
     while (n_words * slices < 2368 && (N / (2 * slices)) >= 8192) slices *= 2;  // >= 4 waves of 592 resident blocks
-    static const bool v1 = getenv("S2C_BITCOL_V1") != nullptr;  // A/B switch: the integer (masked add + reduce) accumulation
+    // A/B switch: 1 = integer accumulation (masked add + reduce), 2 = FP64 accumulation straight from global memory,
+    // 3 (default) = FP64 accumulation over shared-memory tiles
+    static const int ver = getenv("S2C_BITCOL_V") ? atoi(getenv("S2C_BITCOL_V")) : 3;
     if (slices == 1) {
-        if (v1) strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
-        else strm::bitcol_dot_kernel2<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        if (ver == 1) strm::bitcol_dot_kernel<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        else if (ver == 2) strm::bitcol_dot_kernel2<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
+        else strm::bitcol_dot_kernel3<<<n_words, 256, 0, st>>>(W, N, wt, scale, out, words_dev, N, 0);
         return cudaGetLastError();
     }
     uint32_t* partial = nullptr;
     cudaError_t e = cudaMallocAsync(&partial, slice_stride * slices * 4, st);
     if (e != cudaSuccess) return e;
-    if (v1) strm::bitcol_dot_kernel<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
-    else strm::bitcol_dot_kernel2<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    if (ver == 1) strm::bitcol_dot_kernel<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    else if (ver == 2) strm::bitcol_dot_kernel2<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
+    else strm::bitcol_dot_kernel3<<<dim3(n_words, slices), 256, 0, st>>>(W, N, wt, scale, partial, words_dev, N / slices, slice_stride);
     strm::bitcol_reduce_kernel<<<(n_words * 128 + 255) / 256, 256, 0, st>>>(partial, slice_stride, slices, scale, words_dev, n_words, out);
     e = cudaGetLastError();
     cudaFreeAsync(partial, st);

@@ -335,7 +335,6 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const uint32_t num_blocks = (uint32_t)(len / 64);
     int log_size = 4;
     while (((size_t)1 << log_size) < num_blocks) log_size++;
-    if (opt.force_log_size > log_size) log_size = opt.force_log_size;
     if (log_size > 24) return "log_size (" + std::to_string(log_size) + ") must be <= MAX_LOG_SIZE (24)";
     const int n = log_size, m = n + cfg.log_blowup;  // trace / LDE domain logs
     const size_t N = (size_t)1 << n, M = (size_t)1 << m;
@@ -370,40 +369,21 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     std::string hash_err;
     if (!opt.pt_hash && !opt.empty_public_hashes) {
         if (opt.pt_dev) {
-            // inputs resident in HBM and no hashes supplied: each thread reads its buffer back on its own non-blocking stream
-            // (2 x len bytes of D2H, hidden behind the commitment pass like the hashing itself)
-            constexpr size_t CHUNK = (size_t)4 << 20;
-            if (!ctx->hash_stage) CB_CUDA(cudaHostAlloc((void**)&ctx->hash_stage, 4 * CHUNK, cudaHostAllocDefault));
-            const int dev = ctx->device;
-            uint8_t* stage = ctx->hash_stage;
-            auto hash_dev = [dev, len, stage, &hash_err](const uint32_t* d, Hash32* out, int which) {
-                // double-buffered: chunk i+1 is copied on this thread's own non-blocking stream while chunk i is absorbed
-                uint8_t* buf[2] = {stage + (size_t)(2 * which) * CHUNK, stage + (size_t)(2 * which + 1) * CHUNK};
-                cudaStream_t s = nullptr;
-                cudaEvent_t ev[2] = {nullptr, nullptr};
-                cudaError_t e = cudaSetDevice(dev);
-                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-                for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-                const size_t n_chunks = (len + CHUNK - 1) / CHUNK;
-                auto fetch = [&](size_t i) {
-                    const size_t off = i * CHUNK, n = len - off < CHUNK ? len - off : CHUNK;
-                    cudaError_t r = cudaMemcpyAsync(buf[i & 1], (const uint8_t*)d + off, n, cudaMemcpyDeviceToHost, s);
-                    return r == cudaSuccess ? cudaEventRecord(ev[i & 1], s) : r;
-                };
-                blake2s::Incremental inc;
-                if (e == cudaSuccess) e = fetch(0);
-                for (size_t i = 0; i < n_chunks && e == cudaSuccess; i++) {
-                    e = cudaEventSynchronize(ev[i & 1]);
-                    if (e == cudaSuccess && i + 1 < n_chunks) e = fetch(i + 1);
-                    const size_t off = i * CHUNK, n = len - off < CHUNK ? len - off : CHUNK;
-                    if (e == cudaSuccess) inc.update(buf[i & 1], n, i + 1 < n_chunks, out->b);
-                }
-                for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
-                if (s) cudaStreamDestroy(s);
-                if (e != cudaSuccess) hash_err = cudaGetErrorString(e);
-            };
-            hashers.a = std::thread(hash_dev, opt.pt_dev, &pth, 0);
-            hashers.b = std::thread(hash_dev, opt.ct_dev, &cth, 1);
+            // inputs resident in HBM and no hashes supplied: read both buffers back into the context's pinned staging area
+            // (2 x len bytes of D2H at PCIe speed, a few ms) and hash them on host threads like host-resident inputs
+            if (ctx->hash_stage_bytes < 2 * len) {
+                if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
+                ctx->hash_stage = nullptr;
+                ctx->hash_stage_bytes = 0;
+                CB_CUDA(cudaHostAlloc((void**)&ctx->hash_stage, 2 * len, cudaHostAllocDefault));
+                ctx->hash_stage_bytes = 2 * len;
+            }
+            CB_CUDA(cudaMemcpyAsync(ctx->hash_stage, opt.pt_dev, len, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(cudaMemcpyAsync(ctx->hash_stage + len, opt.ct_dev, len, cudaMemcpyDeviceToHost, st));
+            ctx->sync();
+            const uint8_t* hp = ctx->hash_stage;
+            hashers.a = std::thread([&pth, hp, len] { pth = host::blake2s_bytes(hp, len); });
+            hashers.b = std::thread([&cth, hp, len] { cth = host::blake2s_bytes(hp + len, len); });
         } else {
             hashers.a = std::thread([&] { pth = host::blake2s_bytes(plaintext, len); });
             hashers.b = std::thread([&] { cth = host::blake2s_bytes(ciphertext, len); });

@@ -22,7 +22,6 @@ struct PcsConfig {
 };
 
 struct ProveOptions {
-    int force_log_size = 0;            // prove on a larger trace than the block count needs (rows beyond are default rows)
     bool empty_public_hashes = false;  // hash empty byte strings into the statement (reference test-data generator)
     const uint8_t* stmt_nonce = nullptr;  // statement nonce when it differs from the witness nonce (the same generator:
                                           // air_stream.rs:282-283 binds an all-zero nonce while the witness uses 00 00 00 00 4a ..)
