@@ -556,11 +556,15 @@ def main():
             be.prove_chacha20_raw(key0, nonce0, counter0, p0, c0)
             sst = be.stage_times()
             be.set_profile(False)
-            a2a = sharding.max_over_ranks([sst.get("all_to_all", 0.0)], device="cuda")[0]
+            a2a = sharding.max_over_ranks([sst.get("all_to_all", 0.0) + sst.get("group_barrier", 0.0)], device="cuda")[0]
+            peer_windows = bool(be.counters().get("peer_windows", 0))
             be.comm_destroy()
             if rank == 0:
-                sharded_rec = {"workload": "ONE chacha20 trace log_n_rows=%d over %d GPUs (column-sharded transforms, NCCL all-to-all of "
-                                           "LDE row shards, row-sharded hashing / constraints)" % (L, world),
+                sharded_rec = {"workload": "ONE chacha20 trace log_n_rows=%d over %d GPUs (column-sharded transforms, row shards exchanged, "
+                                           "row-sharded hashing / constraints)" % (L, world),
+                               "exchange": ("peer-window stores over NVLink fused into the last transform pass (CUDA IPC), one 4-byte "
+                                            "all-reduce per plan group as the barrier" if peer_windows else
+                                            "NCCL grouped send/recv all-to-all of staged tiles"),
                                "ms": min(times), "ms_all": times, "parity": sp == proof, "single_gpu_ms": ms / args.steps,
                                "speedup_vs_single_gpu": (ms / args.steps) / min(times), "all_to_all_ms": a2a,
                                "stage_ms_rank0_profiled": sst, "h2d_bytes": 2 * nbytes,

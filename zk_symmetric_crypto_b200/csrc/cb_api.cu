@@ -55,6 +55,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_dev) cudaFree(ctx->tw_dev);
     if (ctx->tw_shift_dev) cudaFree(ctx->tw_shift_dev);
+    ctx->close_peers();
     ctx->release_arena();
     if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
     try { comm_destroy(ctx->comm); } catch (...) {}
@@ -205,6 +206,8 @@ int cb_comm_init(cb_ctx* ctx, int rank, int world, const uint8_t id[128]) {
     CB_TRY(ctx)
     CB_CUDA(cudaSetDevice(ctx->device));
     if (world < 1 || (world & (world - 1))) throw CbError("cb_comm_init: world size must be a power of two");
+    ctx->close_peers();
+    ctx->p2p_state = 0;
     comm_destroy(ctx->comm);
     if (world > 1) comm_init(ctx->comm, rank, world, id);
     CB_CATCH(ctx)
@@ -212,6 +215,8 @@ int cb_comm_init(cb_ctx* ctx, int rank, int world, const uint8_t id[128]) {
 int cb_comm_destroy(cb_ctx* ctx) {
     CB_TRY(ctx)
     ctx->sync();
+    ctx->close_peers();
+    ctx->p2p_state = 0;
     comm_destroy(ctx->comm);
     CB_CATCH(ctx)
 }
@@ -419,7 +424,8 @@ const char* cb_counters(cb_ctx* ctx) {
     s.clear();
     if (!ctx) return "";
     s = "fft_words=" + std::to_string(ctx->fft_words) + ";fft_words_half=" + std::to_string(ctx->fft_words_half) + ";cached_tiles=" + std::to_string(ctx->cached_tiles) +
-        ";transient_tiles=" + std::to_string(ctx->transient_tiles) + ";hash_wait_us=" + std::to_string(ctx->hash_wait_us) + ";";
+        ";transient_tiles=" + std::to_string(ctx->transient_tiles) + ";hash_wait_us=" + std::to_string(ctx->hash_wait_us) + ";peer_windows=" +
+        std::to_string(ctx->last_p2p ? 1 : 0) + ";";
     return s.c_str();
 }
 

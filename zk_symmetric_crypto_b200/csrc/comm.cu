@@ -80,6 +80,8 @@ void comm_init(Comm& c, int rank, int world, const uint8_t idb[128]) {
 }
 void comm_destroy(Comm& c) {
     if (c.comm) api().destroy(c.comm);
+    if (c.scratch) cudaFree(c.scratch);
+    c.scratch = nullptr;
     c.comm = nullptr;
     c.rank = 0;
     c.world = 1;
@@ -91,6 +93,40 @@ void comm_send_u32(const Comm& c, const uint32_t* p, size_t words, int peer, cud
 }
 void comm_recv_u32(const Comm& c, uint32_t* p, size_t words, int peer, cudaStream_t st) {
     ck(api().recv((void*)p, words, kUint32, peer, c.comm, st), "ncclRecv");
+}
+// all ranks' `words`-word blocks, rank-major, into recv_dev (grouped send/recv; the local block is copied)
+void comm_allgather_u32(const Comm& c, const uint32_t* send_dev, uint32_t* recv_dev, size_t words, cudaStream_t st) {
+    comm_group_start();
+    for (int r = 0; r < c.world; r++) {
+        if (r == c.rank) {
+            cudaMemcpyAsync(recv_dev + (size_t)r * words, send_dev, words * 4, cudaMemcpyDeviceToDevice, st);
+        } else {
+            comm_send_u32(c, send_dev, words, r, st);
+            comm_recv_u32(c, recv_dev + (size_t)r * words, words, r, st);
+        }
+    }
+    comm_group_end();
+}
+void comm_bcast_u32(const Comm& c, uint32_t* buf_dev, size_t words, int root, cudaStream_t st) {
+    if (!c.active()) return;
+    comm_group_start();
+    if (c.rank == root) {
+        for (int r = 0; r < c.world; r++)
+            if (r != root) comm_send_u32(c, buf_dev, words, r, st);
+    } else {
+        comm_recv_u32(c, buf_dev, words, root, st);
+    }
+    comm_group_end();
+}
+// stream-ordered barrier: a one-word all-reduce on the communicator's scratch word.  Work enqueued on `st` after it starts
+// only when every rank's work enqueued before it has finished (including stores it made into peer memory).
+void comm_barrier(Comm& c, cudaStream_t st) {
+    if (!c.active()) return;
+    if (!c.scratch) {
+        if (cudaMalloc(&c.scratch, 64) != cudaSuccess) throw std::runtime_error("cudaMalloc (comm scratch)");
+        cudaMemsetAsync(c.scratch, 0, 64, st);
+    }
+    ck(api().allreduce(c.scratch, c.scratch, 1, kInt32, kMin, c.comm, st), "ncclAllReduce (barrier)");
 }
 int comm_min_int(const Comm& c, int v, cudaStream_t st) {
     if (!c.active()) return v;

@@ -11,6 +11,7 @@
 struct Comm {
     void* comm = nullptr;  // ncclComm_t
     int rank = 0, world = 1;
+    int* scratch = nullptr;  // device word for comm_barrier
     bool active() const { return world > 1; }
 };
 
@@ -21,5 +22,8 @@ void comm_group_start();
 void comm_group_end();
 void comm_send_u32(const Comm& c, const uint32_t* p, size_t words, int peer, cudaStream_t st);
 void comm_recv_u32(const Comm& c, uint32_t* p, size_t words, int peer, cudaStream_t st);
+void comm_allgather_u32(const Comm& c, const uint32_t* send_dev, uint32_t* recv_dev, size_t words, cudaStream_t st);
+void comm_bcast_u32(const Comm& c, uint32_t* buf_dev, size_t words, int root, cudaStream_t st);
+void comm_barrier(Comm& c, cudaStream_t st);
 // minimum over ranks of a host int (synchronises `st`)
 int comm_min_int(const Comm& c, int v, cudaStream_t st);

@@ -126,8 +126,18 @@ cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n,
 void fft_init_attrs();
 void fft2_init_attrs();
 size_t fft_packed_scratch_words(int kind, int njobs, int log_n);
+// Peer windows of the row-sharded mode: with `peer` set, launch_fft_packed's last pass stores the transformed columns into the
+// tile slots of the ranks that own the rows (word offset off[j] inside every rank's arena, rows dealt in 2G "virtual shards"
+// of 2^lv rows: rank = v mod G, local rows [ (v div G) 2^lv, .. ) ), out[j] is then only the local staging tile.
+#define MAX_PEERS 8
+struct PeerDst {
+    uint32_t* base[MAX_PEERS];
+    int logG, lv;
+    const unsigned long long* off;  // host array, one entry per job
+};
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
-                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0, int first_half_only = 0);
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0,
+                              int first_half_only = 0, const PeerDst* peer = nullptr);
 cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const uint32_t* apr_lo,
                                      const uint32_t* apr_hi, uint32_t* acc, int first, size_t rows = 0);
 // FP64-accumulate form: gtab = the launch's alpha table in consumption order (launch_cons_table), jobs.j[k].kx = offset of job k's

@@ -60,6 +60,15 @@ struct cb_ctx {
     uint8_t* hash_stage = nullptr;
     size_t hash_stage_bytes = 0;
     uint64_t hash_wait_us = 0;  // host time the last proof waited for the public-input hashes after the commitment pass
+    // Peer windows of the row-sharded mode: every rank's arena mapped into this process with CUDA IPC, so that the last
+    // transform pass stores row shards straight into their owner's tile slots over NVLink (no staging, no all-to-all).
+    std::vector<uint32_t*> peer_arena;  // [world]; own entry = arena.  Empty: not mapped
+    int p2p_state = 0;                  // 0 not tried, 1 mapped, -1 unavailable on this box (the NCCL all-to-all path is used)
+    bool last_p2p = false;              // the last sharded proof used the peer windows
+    void close_peers();
+    // collective over ctx->comm: (re)allocates the arena when `realloc` says so on this rank and (re)maps all arenas when any
+    // rank re-allocated.  Returns false when peer mapping is unavailable (every rank gets the same answer).
+    bool sync_peer_arenas(bool realloc, size_t bytes);
     void* ensure_arena(size_t bytes);
     void release_arena();
     void ensure_twiddles(int max_log);

@@ -142,7 +142,20 @@ struct Jobs {
                               // tile layout [shards][cols][2^shard_log], so that a rank's row range of all columns is contiguous
     const uint32_t* src[MAX_FFT_JOBS];  // packed witness word row (2^n words)
     uint32_t* out[MAX_FFT_JOBS];        // LDE tile [cols_per_job][2^(n+1)]
+    // Row-sharded proving over peer windows (PeerDst): the last pass stores every contiguous chunk of the extended column
+    // straight into the tile slot of the rank that owns those rows, over NVLink, instead of writing it back in place; the
+    // column transform and the all-to-all that transposes columns into row shards are one kernel.
+    uint32_t* peer_base[MAX_PEERS];             // arena of rank r as mapped in this process; used when peer_on
+    unsigned long long peer_off[MAX_FFT_JOBS];  // word offset of job j's destination slot inside every rank's arena
+    int peer_on, peer_logG, peer_lv;
 };
+
+// destination of the chunk starting at global row `row0` of column `c0` of job `job` (column stride 2^(lv+1) words)
+__device__ __forceinline__ uint32_t* peer_dst(const Jobs& jobs, int job, int c0, size_t row0) {
+    const uint32_t v = (uint32_t)(row0 >> jobs.peer_lv);  // virtual shard; owner = v mod G, local half = v div G
+    const size_t lrow = ((size_t)(v >> jobs.peer_logG) << jobs.peer_lv) | (row0 & (((size_t)1 << jobs.peer_lv) - 1));
+    return jobs.peer_base[v & ((1u << jobs.peer_logG) - 1)] + jobs.peer_off[job] + ((size_t)c0 << (jobs.peer_lv + 1)) + lrow;
+}
 
 // value of column c of a packed word, times `scale`
 template <int KIND>
@@ -263,6 +276,14 @@ __global__ void __launch_bounds__(256) fft_low_kernel(Jobs jobs, int log_n, int 
     }
     __syncthreads();
     apply_layers<false, true>(s, nc, colstride, k1, 0, 0, k1, tw.X, tw.Y, m, 0, chunk);
+    if (jobs.peer_on) {
+        uint32_t* __restrict__ dst = peer_dst(jobs, job, c0, (size_t)chunk * T);
+        for (int idx = threadIdx.x; idx < nc * T; idx += blockDim.x) {
+            int c = idx >> k1, r = idx & (T - 1);
+            dst[((size_t)c << (jobs.peer_lv + 1)) + r] = s[c * colstride + padi(r)];
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < nc * T; idx += blockDim.x) {
         int c = idx >> k1, r = idx & (T - 1);
         data[soff(jobs.shard_log, cpj, c0 + c, (size_t)chunk * T + r)] = s[c * colstride + padi(r)];
@@ -411,7 +432,7 @@ __global__ void __launch_bounds__(256) ifft_low12_kernel(Jobs jobs, int log_n, i
 }
 
 // ---- pass C: forward layers [11..0] on 4096-point chunks of the extended column, in place -------------------------------------
-template <int NC>
+template <int NC, bool P2P>
 __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, int groups_per_job, FftTables tw) {
     extern __shared__ uint32_t s[];
     const int m = log_n + 1;
@@ -455,6 +476,7 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
     __syncthreads();
     {
         load_tw<4>(twr, tw.X, tw.Y, m, 0, (chunk << K1) | (uint32_t)(16 * p), 0);
+        uint32_t* __restrict__ dst = P2P ? peer_dst(jobs, job, c0, (size_t)chunk * T2) : nullptr;
         int va[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) va[i] = phys(16 * p + 4 * i);
@@ -466,9 +488,22 @@ __global__ void __launch_bounds__(256) fft_low12_kernel(Jobs jobs, int log_n, in
                 v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             }
             fwd_block<4>(v, twr, jobs.one, jobs.mone);
-            uint4* o = (uint4*)(data + ((size_t)c << lr) + 16 * p);
+            if (P2P) {
+                // Peer stores are not merged on the way (no local L2 in between): a thread's own 64 bytes would cross NVLink as
+                // four 16-byte writes.  The warp's 512 consecutive words go back through its shared-memory rows (warp-private,
+                // so a warp barrier is enough) and leave as 4 x 512 contiguous bytes per warp store.
 #pragma unroll
-            for (int i = 0; i < 4; i++) o[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 4; i++) *(uint4*)(s + c * COLW + va[i]) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                __syncwarp();
+                const int wbase = (p & ~31) * 16, lane = p & 31;
+                uint4* o = (uint4*)(dst + ((size_t)c << (jobs.peer_lv + 1)) + wbase);
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[i * 32 + lane] = *(const uint4*)(s + c * COLW + phys(wbase + i * 128 + 4 * lane));
+            } else {
+                uint4* o = (uint4*)(data + ((size_t)c << lr) + 16 * p);
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
         }
     }
 }
@@ -599,7 +634,8 @@ void fft2_init_attrs() {
     cudaFuncSetAttribute(fft_low_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     cudaFuncSetAttribute(ifft_low12_kernel<SRC_BITS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
     cudaFuncSetAttribute(ifft_low12_kernel<SRC_BYTES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
-    cudaFuncSetAttribute(fft_low12_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
+    cudaFuncSetAttribute(fft_low12_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
+    cudaFuncSetAttribute(fft_low12_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * COLW * 4);
     cudaFuncSetAttribute(mid12_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 32 * 4);
     cudaFuncSetAttribute(mid12_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 32 * 4);
 }
@@ -614,7 +650,8 @@ size_t fft_packed_scratch_words(int kind, int njobs, int log_n) {
 // apart, src[j] -> the first of them).  src[j]: packed word row of job j (2^log_n words);
 // out[j]: tile [cols][2^(log_n+1)].  Returns the number of kernels launched through *launches.
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
-                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log, int first_half_only) {
+                              const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log, int first_half_only,
+                              const PeerDst* peer) {
     using namespace fft2;
 #define HOOK(name, b) do { if (hook) hook->fn(hook->user, name, b); } while (0)
     const int cpj = kind == SRC_BITS ? 32 : 4;
@@ -627,6 +664,16 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         jobs.mone = 0xffffffffu;
         jobs.halves = (first_half_only && log_n > 12 && log_n <= 20 && !g_force_generic_fft && jobs.shard_log == log_n + 1) ? 1 : 2;
         for (int j = 0; j < jobs.n; j++) { jobs.src[j] = src[j0 + j]; jobs.out[j] = out[j0 + j]; }
+        jobs.peer_on = 0;
+        jobs.peer_logG = jobs.peer_lv = 0;
+        if (peer) {  // chunks of the last pass (2^12 or 2^k1 <= 2^13 rows) must lie inside one virtual shard
+            if (log_n <= 12 || peer->lv < 13 || peer->logG > 3) return cudaErrorInvalidValue;
+            jobs.peer_on = 1;
+            jobs.peer_logG = peer->logG;
+            jobs.peer_lv = peer->lv;
+            for (int r = 0; r < MAX_PEERS; r++) jobs.peer_base[r] = r < (1 << peer->logG) ? peer->base[r] : nullptr;
+            for (int j = 0; j < jobs.n; j++) jobs.peer_off[j] = peer->off[j0 + j];
+        }
         if (log_n <= 12) {
             const int big = 2 << log_n;
             int nc = 8192 / big;
@@ -667,7 +714,8 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
             HOOK("fft_mid", 0);
             dim3 gC(((unsigned)jobs.halves << log_n) / T2, jobs.n * gpj2);
             HOOK("fft_low", 1);
-            fft_low12_kernel<NC><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
+            if (jobs.peer_on) fft_low12_kernel<NC, true><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
+            else fft_low12_kernel<NC, false><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
             HOOK("fft_low", 0);
             nl += 3;
             continue;

@@ -424,7 +424,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     static const std::vector<Group> plan = build_plan();
     // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
     const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr && G == 1;
-    const int lag = overlap ? 2 : 0;
+    // Row-sharded mode over peer windows (G > 1, CUDA IPC available): LDE rows are dealt to the ranks in 2G "virtual shards" of
+    // Mv = M / 2G rows (rank r owns global rows [r Mv, (r+1) Mv) of the first half of the evaluation domain and the same range
+    // of the second half), the owner of a column writes them straight into the other ranks' tile slots from the last transform
+    // pass, and one tiny all-reduce per plan group orders producers and consumers.  A slot released in group g is written by
+    // remote ranks from group g+2 on (they passed the barrier of group g+1, which this rank entered after consuming group g).
+    const bool want_p2p = G > 1 && ctx->p2p_state >= 0 && getenv("S2C_NO_P2P") == nullptr;
+    const int lag = (overlap || want_p2p) ? 2 : 0;
     static const int peak_trans_none = plan_peak_transient(plan, 2, std::vector<char>(N_WORDS, 0));  // nothing cached
     cudaStream_t sf = overlap ? ctx->stream2 : st;
     // placement knobs (KiB) for measuring how the power-of-two strides of the transform passes interact with the DRAM
@@ -483,12 +489,21 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // tile slots + FFT scratch live in the context's persistent arena
     const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
     uint32_t* arena_p;
-    if (ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30))
+    const bool arena_ok = ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30);
+    bool p2p = false;
+    if (G > 1) {
+        p2p = ctx->sync_peer_arenas(!arena_ok, arena_words * 4) && want_p2p;
         arena_p = (uint32_t*)ctx->arena;
-    else {
+    } else if (arena_ok) {
+        arena_p = (uint32_t*)ctx->arena;
+    } else {
+        ctx->close_peers();
         ctx->release_arena();
         arena_p = (uint32_t*)ctx->ensure_arena(arena_words * 4);
     }
+    ctx->last_p2p = p2p;
+    const int lv = lr - 1;        // virtual shards (peer-window mode)
+    const size_t Mv = Mr >> 1;
     uint32_t* scratch_p = arena_p + (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words;
     uint32_t* stage_p = scratch_p + scratch_words;
     Tiles tiles;
@@ -501,7 +516,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // single-GPU mode evaluates the constraints on storage rows [0, N] only (see "half-domain evaluation" below): tiles
     // recomputed for the constraint pass need only their first half
-    const bool half_mode = G == 1;
+    const bool half_mode = G == 1 || p2p;
     auto run_pass = [&](int pass, auto&& consume) {
         const size_t NG = plan.size();
         tiles.flush();
@@ -513,7 +528,38 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             std::vector<int> jobs_w;
             for (int w : g.fft)
                 if (tiles.acquire(w, true, pass)) jobs_w.push_back(w);
-            if (G > 1 && !jobs_w.empty()) {
+            if (p2p) {
+                // column-sharded transform fused with the exchange: job j belongs to rank j mod G, whose last transform pass
+                // stores each 4096-row chunk into the slot of the rank owning those rows
+                std::vector<unsigned long long> offs;
+                int k = 0;
+                for (size_t j = 0; j < jobs_w.size(); j++)
+                    if ((int)(j % G) == R) {
+                        src.push_back(W.p + (size_t)jobs_w[j] * N);
+                        out.push_back(stage_p + (size_t)(k++) * 32 * M);
+                        offs.push_back((unsigned long long)(tiles.ptr(jobs_w[j]) - arena_p));
+                    }
+                if (!src.empty()) {
+                    PeerDst pd{};
+                    for (int r = 0; r < G; r++) pd.base[r] = ctx->peer_arena[r];
+                    pd.logG = logG;
+                    pd.lv = lv;
+                    pd.off = offs.data();
+                    int nl = 0;
+                    CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl, 0,
+                                              pass == 2, &pd));
+                    ctx->launches += nl;
+                    ctx->fft_words += src.size();
+                    if (pass == 2) ctx->fft_words_half += src.size();
+                }
+                if (pass == 1 || n_cache < N_INDEP_WORDS) {
+                    ctx->stage_begin("group_barrier");
+                    comm_barrier(ctx->comm, st);
+                    ctx->stage_end();
+                }
+                src.clear();
+                out.clear();
+            } else if (G > 1 && !jobs_w.empty()) {
                 // column-sharded transform: job j of the group belongs to rank j mod G, which transforms the whole columns
                 // into a staging tile laid out [G][32][Mr]; then the grouped send/recv all-to-all hands every rank its row
                 // shard of every tile of the group
@@ -604,34 +650,41 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             ctx->stage_end();
             ctx->launches++;
             bytes_before += 128ull * g.hash.size();
-            if (half_mode) {  // every column's value at storage row N (the one row of the second half the composition needs)
+            if (half_mode && R == 0) {  // every column's value at storage row N (the one row of the second half the composition needs)
                 TileRowJobs tj{};
                 for (int w : g.hash) { tj.word[tj.n] = w; tj.tile[tj.n] = tiles.ptr(w); tj.n++; }
-                CB_CUDA(launch_gather_tile_row(st, tj, M, N, d_rowN.p));
+                CB_CUDA(launch_gather_tile_row(st, tj, Mr, G > 1 ? Mv : N, d_rowN.p));  // global row N = local row Mv of rank 0
                 ctx->launches++;
             }
         });
         ctx->stage_begin("merkle_nodes");
-        for (int l = 0; l < lr; l++) {
+        // local subtrees: one over Mr leaves, or (virtual shards) two over Mv leaves each, whose roots are the two nodes of layer lv
+        const int local_top = p2p ? lv : lr;
+        for (int l = 0; l < local_top; l++) {
             CB_CUDA(launch_merkle_nodes(st, ln + local.layer_offset(l) * 8, 1u << (lr - l - 1), ln + local.layer_offset(l + 1) * 8));
             ctx->launches++;
         }
         if (G > 1) {
             comm_group_start();
-            for (int l = 0; l <= lr; l++) {
-                const size_t cnt = ((size_t)Mr >> l) * 8;
-                if (R == 0) {
-                    CB_CUDA(cudaMemcpyAsync(tree1.nodes.p + tree1.layer_offset(l) * 8, ln + local.layer_offset(l) * 8, cnt * 4,
-                                            cudaMemcpyDeviceToDevice, st));
-                    for (int r = 1; r < G; r++) comm_recv_u32(cm, tree1.nodes.p + tree1.layer_offset(l) * 8 + (size_t)r * cnt, cnt, r, st);
-                } else {
-                    comm_send_u32(cm, ln + local.layer_offset(l) * 8, cnt, 0, st);
+            for (int l = 0; l <= local_top; l++) {
+                // a rank's layer l = `parts` runs of cnt words; run i of rank r sits at position (i G + r) of the global layer
+                const int parts = p2p ? 2 : 1;
+                const size_t cnt = ((size_t)(p2p ? Mv : Mr) >> l) * 8;
+                for (int i = 0; i < parts; i++) {
+                    const uint32_t* mine = ln + local.layer_offset(l) * 8 + (size_t)i * cnt;
+                    uint32_t* glob = R == 0 ? tree1.nodes.p + tree1.layer_offset(l) * 8 + (size_t)i * G * cnt : nullptr;
+                    if (R == 0) {
+                        CB_CUDA(cudaMemcpyAsync(glob, mine, cnt * 4, cudaMemcpyDeviceToDevice, st));
+                        for (int r = 1; r < G; r++) comm_recv_u32(cm, glob + (size_t)r * cnt, cnt, r, st);
+                    } else {
+                        comm_send_u32(cm, mine, cnt, 0, st);
+                    }
                 }
             }
             comm_group_end();
             DBuf<uint32_t> d_root(ctx, 8);
             if (R == 0) {
-                for (int l = lr; l < m; l++) {
+                for (int l = local_top; l < m; l++) {
                     CB_CUDA(launch_merkle_nodes(st, tree1.nodes.p + tree1.layer_offset(l) * 8, 1u << (m - l - 1),
                                                 tree1.nodes.p + tree1.layer_offset(l + 1) * 8));
                     ctx->launches++;
@@ -714,7 +767,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // the shifted twiddle tower (host::make_twiddles(.., true)); one more row (row N, where Z_H = -v) separates c.
     // So only N + 1 of the 2N rows are evaluated; coefficients - and therefore the proof bytes - are unchanged.
     // (Row-sharded mode keeps the full-domain evaluation: the first-half rows live on half of the ranks only.)
-    const size_t cons_rows = half_mode ? N : 0;
+    const size_t cons_rows = half_mode ? (G > 1 ? Mv : N) : 0;  // virtual shards: local rows [0, Mv) are first-half rows
     run_pass(2, [&](size_t gi, const Group& g) {
         ConstraintJobs cj{};
         for (auto& c : g.cons)
@@ -733,7 +786,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         ctx->stage_end();
         ctx->launches++;
     });
-    CB_CUDA(launch_scale_rows(st, accp, Mr, n, d_den.p, (size_t)R * Mr));
+    CB_CUDA(launch_scale_rows(st, accp, Mr, n, d_den.p, p2p ? (size_t)R * Mv : (size_t)R * Mr));
     ctx->launches++;
     // reversed powers of the random coefficient on the host: the one-row evaluation below and prove()'s closing check
     std::vector<QM31> aprh(N_CONSTRAINTS);
@@ -742,7 +795,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         QM31 cur = qone();
         for (int e = 0; e < N_CONSTRAINTS; e++) { aprh[N_CONSTRAINTS - 1 - e] = cur; cur = qmul(cur, random_coeff); }
     }
-    if (half_mode) {  // the constraint sum at storage row N, on the host while the GPU works through the constraint pass
+    if (half_mode && R == 0) {  // the constraint sum at storage row N, on the host while the GPU works through the constraint pass
         std::vector<QM31> mask(N_COLS);
         for (int j = 0; j < N_COLS; j++) mask[j] = qfrom(rowN[j]);
         q_rowN = eval_constraints_at_mask(mask, aprh);
@@ -750,12 +803,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     if (G > 1) {
         // the row shards of the accumulator go to rank 0, which finishes the proof alone (4-8 columns from here on)
         comm_group_start();
+        const size_t rows_each = p2p ? Mv : Mr;  // virtual shards: only the first-half rows were evaluated
         for (int c = 0; c < 4; c++) {
             if (R == 0) {
-                CB_CUDA(cudaMemcpyAsync(acc.p + (size_t)c * M, accp + (size_t)c * Mr, Mr * 4, cudaMemcpyDeviceToDevice, st));
-                for (int r = 1; r < G; r++) comm_recv_u32(cm, acc.p + (size_t)c * M + (size_t)r * Mr, Mr, r, st);
+                CB_CUDA(cudaMemcpyAsync(acc.p + (size_t)c * M, accp + (size_t)c * Mr, rows_each * 4, cudaMemcpyDeviceToDevice, st));
+                for (int r = 1; r < G; r++) comm_recv_u32(cm, acc.p + (size_t)c * M + (size_t)r * rows_each, rows_each, r, st);
             } else {
-                comm_send_u32(cm, accp + (size_t)c * Mr, Mr, 0, st);
+                comm_send_u32(cm, accp + (size_t)c * Mr, rows_each, 0, st);
             }
         }
         comm_group_end();

@@ -54,6 +54,62 @@ void* cb_ctx::ensure_arena(size_t bytes) {
     arena_bytes = bytes;
     return arena;
 }
+void cb_ctx::close_peers() {
+    for (size_t r = 0; r < peer_arena.size(); r++)
+        if ((int)r != comm.rank && peer_arena[r]) cudaIpcCloseMemHandle(peer_arena[r]);
+    peer_arena.clear();
+    if (p2p_state == 1) p2p_state = 0;
+}
+
+bool cb_ctx::sync_peer_arenas(bool realloc, size_t bytes) {
+    static const bool disabled = getenv("S2C_NO_P2P") != nullptr;
+    const int G = comm.world, R = comm.rank;
+    const bool want = !disabled && p2p_state >= 0 && G <= MAX_PEERS;
+    // does any rank need a new arena or a first mapping?
+    const bool mine = realloc || (want && peer_arena.empty());
+    const bool any = comm_min_int(comm, mine ? 0 : 1, stream) == 0;
+    if (!any) return p2p_state == 1;
+    // nobody may keep a mapping of memory that is about to be freed
+    close_peers();
+    comm_barrier(comm, stream);
+    sync();
+    if (realloc) {
+        release_arena();
+        ensure_arena(bytes);
+    }
+    if (!want) return false;
+    // exchange the IPC handles (64 bytes each) through the communicator
+    cudaIpcMemHandle_t mine_h;
+    int ok = cudaIpcGetMemHandle(&mine_h, arena) == cudaSuccess ? 1 : 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DBuf<uint32_t> d_send(this, 16), d_recv(this, (size_t)16 * G);
+    CB_CUDA(cudaMemcpyAsync(d_send.p, &mine_h, 64, cudaMemcpyHostToDevice, stream));
+    comm_allgather_u32(comm, d_send.p, d_recv.p, 16, stream);
+    std::vector<cudaIpcMemHandle_t> all(G);
+    CB_CUDA(cudaMemcpyAsync(all.data(), d_recv.p, (size_t)64 * G, cudaMemcpyDeviceToHost, stream));
+    sync();
+    peer_arena.assign(G, nullptr);
+    peer_arena[R] = (uint32_t*)arena;
+    for (int r = 0; r < G && ok; r++) {
+        if (r == R) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        } else {
+            peer_arena[r] = (uint32_t*)p;
+        }
+    }
+    ok = comm_min_int(comm, ok, stream);
+    if (!ok) {
+        close_peers();
+        p2p_state = -1;
+        return false;
+    }
+    p2p_state = 1;
+    return true;
+}
+
 void cb_ctx::release_arena() {
     if (arena) {
         sync();
