@@ -60,9 +60,9 @@ void ck(int rc, const char* what) {
     }
 }
 #ifdef S2C_HAVE_NCCL_H
-constexpr int kUint32 = (int)ncclUint32, kInt32 = (int)ncclInt32, kMin = (int)ncclMin;
+constexpr int kUint32 = (int)ncclUint32, kInt32 = (int)ncclInt32, kMin = (int)ncclMin, kSum = (int)ncclSum;
 #else
-constexpr int kUint32 = 3, kInt32 = 2, kMin = 3;  // ncclUint32, ncclInt32, ncclMin (nccl.h of NCCL 2.x)
+constexpr int kUint32 = 3, kInt32 = 2, kMin = 3, kSum = 0;  // ncclUint32, ncclInt32, ncclMin (nccl.h of NCCL 2.x)
 #endif
 }  // namespace
 
@@ -127,6 +127,12 @@ void comm_barrier(Comm& c, cudaStream_t st) {
         cudaMemsetAsync(c.scratch, 0, 64, st);
     }
     ck(api().allreduce(c.scratch, c.scratch, 1, kInt32, kMin, c.comm, st), "ncclAllReduce (barrier)");
+}
+// in-place sum of u32 words over the ranks (used to merge partial results with disjoint support, so no carry or modular
+// reduction is involved)
+void comm_allreduce_sum_u32(const Comm& c, uint32_t* buf_dev, size_t words, cudaStream_t st) {
+    if (!c.active()) return;
+    ck(api().allreduce(buf_dev, buf_dev, words, kUint32, kSum, c.comm, st), "ncclAllReduce (sum)");
 }
 int comm_min_int(const Comm& c, int v, cudaStream_t st) {
     if (!c.active()) return v;

@@ -25,5 +25,6 @@ void comm_recv_u32(const Comm& c, uint32_t* p, size_t words, int peer, cudaStrea
 void comm_allgather_u32(const Comm& c, const uint32_t* send_dev, uint32_t* recv_dev, size_t words, cudaStream_t st);
 void comm_bcast_u32(const Comm& c, uint32_t* buf_dev, size_t words, int root, cudaStream_t st);
 void comm_barrier(Comm& c, cudaStream_t st);
+void comm_allreduce_sum_u32(const Comm& c, uint32_t* buf_dev, size_t words, cudaStream_t st);
 // minimum over ranks of a host int (synchronises `st`)
 int comm_min_int(const Comm& c, int v, cudaStream_t st);

@@ -159,6 +159,8 @@ cudaError_t launch_bitcol_dot(cudaStream_t st, const uint32_t* W, size_t N, int 
                               uint32_t* out, const int* words_dev = nullptr);
 cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int n_words, const uint32_t* coefs, uint32_t* g,
                                const int* words_dev = nullptr);
+// g[idx] = sum over p of partial[p][idx] (mod p): partial results over disjoint word sets ([parts][4][N])
+cudaError_t launch_bitrow_reduce(cudaStream_t st, const uint32_t* partial, size_t N, int parts, uint32_t* g);
 cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t stride, int ncols, size_t N, const uint32_t* coefs,
                                uint32_t* g, int accumulate);
 cudaError_t launch_basis4(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const uint32_t init[4],

@@ -685,6 +685,7 @@ __global__ void gather_cached_kernel(const uint32_t* __restrict__ arena, size_t 
     const int sl = slot[w];
     if (sl < 0 || c >= nq) return;
     const uint32_t r = c == 0 ? rows.x : c == 1 ? rows.y : c == 2 ? rows.z : rows.w;
+    if (r == 0xffffffffu) return;  // row-sharded tiles: that row lives on another rank
     out[idx] = arena[(size_t)sl * tile_words + (size_t)i * M + r];
 }
 
@@ -810,6 +811,11 @@ cudaError_t launch_bitrow_comb(cudaStream_t st, const uint32_t* W, size_t N, int
     cudaFreeAsync(T, st);
     if (partial) cudaFreeAsync(partial, st);
     return e;
+}
+
+cudaError_t launch_bitrow_reduce(cudaStream_t st, const uint32_t* partial, size_t N, int parts, uint32_t* g) {
+    strm::bitrow_reduce_kernel<<<(unsigned)((4 * N + 255) / 256), 256, 0, st>>>(partial, N, parts, g);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t stride, int ncols, size_t N, const uint32_t* coefs,

@@ -367,7 +367,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         ~Hashers() { join(); }
     } hashers;
     std::string hash_err;
-    if (!opt.pt_hash && !opt.empty_public_hashes) {
+    // (sharded mode: only rank 0 hashes and broadcasts the two digests - G processes x 2 hashing threads would fight for the
+    // host cores, and at 8 ranks the commitment pass is no longer than one 64 MiB hash)
+    if (!opt.pt_hash && !opt.empty_public_hashes && cm.rank == 0) {
         if (opt.pt_dev) {
             // inputs resident in HBM and no hashes supplied: read both buffers back into the context's pinned staging area
             // (2 x len bytes of D2H at PCIe speed, a few ms) and hash them on host threads like host-resident inputs
@@ -517,9 +519,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // single-GPU mode evaluates the constraints on storage rows [0, N] only (see "half-domain evaluation" below): tiles
     // recomputed for the constraint pass need only their first half
     const bool half_mode = G == 1 || p2p;
+    // peer-window mode, two streams: the transforms of group g+1 (whose last pass waits on NVLink) run on `stream2` while the
+    // consumer of group g runs on `stream`.  Per group, on stream2: transform, wait consumed(g-1), barrier, record ready(g).
+    const bool ov2 = p2p && ctx->stream2 != nullptr && !ctx->profile && getenv("S2C_P2P_1STREAM") == nullptr;
     auto run_pass = [&](int pass, auto&& consume) {
         const size_t NG = plan.size();
         tiles.flush();
+        cudaStream_t sp = ov2 ? ctx->stream2 : st;
+        if (ov2) {  // the producer stream starts after everything enqueued so far
+            CB_CUDA(cudaEventRecord(ctx->event(2 * NG), st));
+            CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG), 0));
+        }
         for (size_t gi = 0; gi < NG; gi++) {
             const Group& g = plan[gi];
             tiles.begin_group((int)gi);
@@ -546,7 +556,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     pd.lv = lv;
                     pd.off = offs.data();
                     int nl = 0;
-                    CB_CUDA(launch_fft_packed(st, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl, 0,
+                    CB_CUDA(launch_fft_packed(sp, SRC_BITS, src.data(), out.data(), (int)src.size(), n, ctx->tw, scratch_p, hkp, &nl, 0,
                                               pass == 2, &pd));
                     ctx->launches += nl;
                     ctx->fft_words += src.size();
@@ -554,8 +564,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 }
                 if (pass == 1 || n_cache < N_INDEP_WORDS) {
                     ctx->stage_begin("group_barrier");
-                    comm_barrier(ctx->comm, st);
+                    if (ov2 && gi >= 1) CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(NG + gi - 1), 0));
+                    comm_barrier(ctx->comm, sp);
                     ctx->stage_end();
+                    if (ov2) {
+                        CB_CUDA(cudaEventRecord(ctx->event(gi), sp));
+                        CB_CUDA(cudaStreamWaitEvent(st, ctx->event(gi), 0));
+                    }
                 }
                 src.clear();
                 out.clear();
@@ -616,11 +631,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             }
             for (auto& c : g.comb) tiles.acquire(c.res, false, pass);
             consume(gi, g);
-            if (overlap) CB_CUDA(cudaEventRecord(ctx->event(NG + gi), st));
+            if (overlap || ov2) CB_CUDA(cudaEventRecord(ctx->event(NG + gi), st));
             for (int w : g.free_after) tiles.release(w);
         }
         for (int w = 0; w < N_WORDS; w++) tiles.release(w);
         if (overlap) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(2 * NG - 1), 0));  // next pass's producer starts after this pass
+        if (ov2) CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG - 1), 0));
     };
 
     // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree.  Sharded mode: every rank builds
@@ -720,6 +736,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         pth = host::blake2s_bytes(nullptr, 0);
         cth = pth;
     }
+    if (G > 1) {
+        DBuf<uint32_t> d_h(ctx, 16);
+        uint8_t hb[64];
+        memcpy(hb, pth.b, 32);
+        memcpy(hb + 32, cth.b, 32);
+        if (R == 0) CB_CUDA(cudaMemcpyAsync(d_h.p, hb, 64, cudaMemcpyHostToDevice, st));
+        comm_bcast_u32(cm, d_h.p, 16, 0, st);
+        CB_CUDA(cudaMemcpyAsync(hb, d_h.p, 64, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
+        memcpy(pth.b, hb, 32);
+        memcpy(cth.b, hb + 32, 32);
+    }
     host::put_bytes(stmt, pth.b, 32);
     host::put_bytes(stmt, cth.b, 32);
     ch.mix_u64((uint64_t)log_size);
@@ -814,17 +842,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         }
         comm_group_end();
         ctx->sync();
-        if (R != 0) {
-            proof.clear();
-            ctx->collect_stages();
-            return "";
-        }
     }
+    // From here on 4-12 columns remain.  Rank 0 ("lead") owns them and the transcript; the other ranks of a sharded proof
+    // stay for the three passes that still touch all 33,280 trace columns - out-of-domain samples and the FRI numerator
+    // (both passes over the packed witness, split by witness word) and the queried values (read from the row-sharded tiles) -
+    // whose disjoint partial results are merged with a sum all-reduce.
+    const bool lead = R == 0;
 
     ctx->stage_begin("composition_commit");
     // interpolate the 4 coordinate columns (log m), split into halves, evaluate each half (log n) on the LDE domain
-    DBuf<uint32_t> comp_coef(ctx, 4 * M), comp_lde(ctx, 8 * M);
-    {
+    DBuf<uint32_t> comp_coef(ctx, lead ? 4 * M : 4), comp_lde(ctx, lead ? 8 * M : 8);
+    DevMerkle tree2;
+    if (lead) {
         DBuf<uint32_t> scratch4(ctx, 4 * M);
         ColSrc src{SRC_M31, acc.p, M, 0};
         if (half_mode) {
@@ -862,11 +891,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             CB_CUDA(launch_fft(st, cs, 4, n, cfg.log_blowup, 4, nullptr, 0, comp_lde.p + (size_t)half * 4 * M, M, ctx->tw, nullptr, 0));
         }
         ctx->launches += 6;
+        LeafGroups g2{};
+        g2.n = 1;
+        g2.g[0] = {comp_lde.p, M, 8, m};
+        tree2 = build_merkle(ctx, g2, m);
     }
-    LeafGroups g2{};
-    g2.n = 1;
-    g2.g[0] = {comp_lde.p, M, 8, m};
-    DevMerkle tree2 = build_merkle(ctx, g2, m);
+    if (G > 1) {
+        DBuf<uint32_t> d_r(ctx, 8);
+        if (lead) CB_CUDA(cudaMemcpyAsync(d_r.p, tree2.root.b, 32, cudaMemcpyHostToDevice, st));
+        comm_bcast_u32(cm, d_r.p, 8, 0, st);
+        CB_CUDA(cudaMemcpyAsync(tree2.root.b, d_r.p, 32, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
+    }
     ctx->stage_end();
     roots.push_back(tree2.root);
     ch.mix_root(tree2.root);
@@ -883,6 +919,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     std::vector<int> indep_words;
     for (auto& g : plan)
         for (int w : g.fft) indep_words.push_back(w);
+    if (G > 1) {  // this rank's share of the witness words
+        std::vector<int> mine;
+        for (size_t i = 0; i < indep_words.size(); i++)
+            if ((int)(i % G) == R) mine.push_back(indep_words[i]);
+        indep_words.swap(mine);
+    }
     DBuf<int> d_indep(ctx, indep_words.size());
     CB_CUDA(cudaMemcpyAsync(d_indep.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     {
@@ -894,9 +936,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         CB_CUDA(launch_basis(st, basis.p, N, n, maps.data()));
         ColSrc bs{SRC_M31, basis.p, N, 0};
         CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
+        if (G > 1) CB_CUDA(cudaMemsetAsync(d_sampled.p, 0, ((size_t)N_COLS + 8) * 16, st));
         CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)indep_words.size(), wt.p, inv_n, d_sampled.p, d_indep.p));
-        for (int half = 0; half < 2; half++)
-            CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
+        if (lead)
+            for (int half = 0; half < 2; half++)
+                CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
+        if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)N_COLS + 8) * 4, st);
         ctx->launches += n + 6;
         CB_CUDA(cudaMemcpyAsync(sampled.data(), d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
@@ -918,7 +963,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     //      witness (kernels_stream.cu fact 3); the 8 composition columns are read from their LDE
     QM31 rc = ch.draw_secure_felt();
     ctx->stage_begin("quotients");
-    DBuf<uint32_t> quot(ctx, 4 * M);
+    DBuf<uint32_t> quot(ctx, lead ? 4 * M : 4);
     {
         const size_t nc = sampled.size();
         std::vector<uint32_t> coefs(nc * 4);
@@ -954,9 +999,23 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                         }
                     }
             }
-        DBuf<uint32_t> d_coefs(ctx, (size_t)N_COLS * 4), g(ctx, 4 * N), g_lde(ctx, 4 * M), d_bc(ctx, 12 * 4);
+        DBuf<uint32_t> d_coefs(ctx, (size_t)N_COLS * 4), g(ctx, 4 * N), g_lde(ctx, lead ? 4 * M : 4), d_bc(ctx, 12 * 4);
         CB_CUDA(cudaMemcpyAsync(d_coefs.p, fc.data(), fc.size() * 4, cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_bitrow_comb(st, W.p, N, (int)indep_words.size(), d_coefs.p, g.p, d_indep.p));
+        if (G > 1) {  // the ranks' partial combinations (disjoint word sets) are added on the lead
+            DBuf<uint32_t> parts(ctx, lead ? (size_t)G * 4 * N : 4);
+            comm_group_start();
+            if (lead) {
+                CB_CUDA(cudaMemcpyAsync(parts.p, g.p, 4 * N * 4, cudaMemcpyDeviceToDevice, st));
+                for (int r = 1; r < G; r++) comm_recv_u32(cm, parts.p + (size_t)r * 4 * N, 4 * N, r, st);
+            } else {
+                comm_send_u32(cm, g.p, 4 * N, 0, st);
+            }
+            comm_group_end();
+            if (lead) CB_CUDA(launch_bitrow_reduce(st, parts.p, N, G, g.p));
+            ctx->launches++;
+        }
+        if (lead) {
         ColSrc gs{SRC_M31, g.p, N, 0};
         CB_CUDA(launch_fft(st, gs, 4, n, cfg.log_blowup, 1 | 4, nullptr, 0, g_lde.p, M, ctx->tw, g.p, N));
         uint32_t bc[12 * 4] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -972,30 +1031,60 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         CB_CUDA(cudaMemcpyAsync(d_qb.p, &qb, sizeof(qb), cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_quotients(st, g_lde.p, M, 4, comp_lde.p, M, d_qb.p, 1, m, ctx->tw, quot.p, M));
         ctx->launches += 5;
+        }
         ctx->sync();
     }
     ctx->stage_end();
 
-    // ---- FRI commit
-    ctx->stage_begin("fri_commit");
-    FriProverState fri = fri_commit(ctx, ch, cfg, std::move(quot), m);
-    ctx->stage_end();
+    FriProverState fri;
+    uint64_t pow_nonce = 0;
+    std::vector<uint32_t> queries;
+    if (lead) {
+        // ---- FRI commit
+        ctx->stage_begin("fri_commit");
+        fri = fri_commit(ctx, ch, cfg, std::move(quot), m);
+        ctx->stage_end();
 
-    // ---- proof of work, queries
-    ctx->stage_begin("grind");
-    uint64_t pow_nonce = grind(ctx, ch, cfg.pow_bits);
-    ctx->stage_end();
-    ch.mix_u64(pow_nonce);
-    std::vector<uint32_t> queries = host::queries_generate(ch, m, cfg.n_queries);
+        // ---- proof of work, queries
+        ctx->stage_begin("grind");
+        pow_nonce = grind(ctx, ch, cfg.pow_bits);
+        ctx->stage_end();
+        ch.mix_u64(pow_nonce);
+        queries = host::queries_generate(ch, m, cfg.n_queries);
+    }
+    if (G > 1) {  // the query positions go to every rank
+        std::vector<uint32_t> qb(cfg.n_queries + 1, 0);
+        if (lead) {
+            qb[0] = (uint32_t)queries.size();
+            for (size_t i = 0; i < queries.size(); i++) qb[1 + i] = queries[i];
+        }
+        DBuf<uint32_t> d_qs(ctx, qb.size());
+        if (lead) CB_CUDA(cudaMemcpyAsync(d_qs.p, qb.data(), qb.size() * 4, cudaMemcpyHostToDevice, st));
+        comm_bcast_u32(cm, d_qs.p, qb.size(), 0, st);
+        CB_CUDA(cudaMemcpyAsync(qb.data(), d_qs.p, qb.size() * 4, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
+        if (!lead) queries.assign(qb.begin() + 1, qb.begin() + 1 + qb[0]);
+    }
 
     // ---- decommit: queried LDE values of the trace columns.  Tiles that stayed cached since the commitment pass are read
     //      directly; adder-sum words follow from their operands (kernels_stream.cu fact 1, which holds row by row on the
     //      extended domain); only the independent words without a cached tile are evaluated from the packed witness like the
     //      OODS samples (all independent words when the tiles are row-sharded over several ranks).
     ctx->stage_begin("decommit");
-    std::vector<uint8_t> fri_bytes = fri_decommit(ctx, fri, cfg, queries);
-    std::vector<Hash32> dec1 = merkle_decommit(ctx, tree1, queries), dec2 = merkle_decommit(ctx, tree2, queries);
+    std::vector<uint8_t> fri_bytes;
+    std::vector<Hash32> dec1, dec2;
+    if (lead) {
+        fri_bytes = fri_decommit(ctx, fri, cfg, queries);
+        dec1 = merkle_decommit(ctx, tree1, queries);
+        dec2 = merkle_decommit(ctx, tree2, queries);
+    }
     const int nq = (int)queries.size();
+    // (rank, local row) holding global LDE row q of the row-sharded tiles
+    auto locate = [&](uint32_t q, int& owner, uint32_t& local) {
+        if (G == 1) { owner = 0; local = q; }
+        else if (p2p) { const uint32_t v = q >> lv; owner = (int)(v & (uint32_t)(G - 1)); local = ((v >> logG) << lv) | (q & (uint32_t)(Mv - 1)); }
+        else { owner = (int)(q >> lr); local = q & (uint32_t)(Mr - 1); }
+    };
     std::vector<uint32_t> qv1((size_t)N_COLS * nq), qv2((size_t)8 * nq);
     {
         std::vector<int> slot(N_WORDS, -1);
@@ -1005,7 +1094,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         std::vector<int> need;  // independent words whose tile is not cached (all of them when the tiles are row-sharded)
         for (int w = 0; w < N_WORDS; w++) {
             if (!indep[w]) continue;
-            if (G == 1 && tiles.cache_slot[w] >= 0) slot[w] = tiles.cache_slot[w];
+            if (tiles.cache_slot[w] >= 0) slot[w] = tiles.cache_slot[w];
             else need.push_back(w);
         }
         DBuf<int> d_slot(ctx, N_WORDS), d_need(ctx, need.size() + 1);
@@ -1015,7 +1104,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         std::vector<uint32_t> q4((size_t)N_COLS * 4);
         for (int q0 = 0; q0 < nq; q0 += 4) {
             const int nqc = nq - q0 < 4 ? nq - q0 : 4;
-            if (!need.empty()) {
+            if (G > 1) CB_CUDA(cudaMemsetAsync(d_q1.p, 0, (size_t)N_COLS * 16, st));
+            if (!need.empty() && lead) {
                 uint32_t init[4] = {0, 0, 0, 0};
                 std::vector<std::array<uint32_t, 4>> maps(n);
                 for (int c = 0; c < nqc; c++) {
@@ -1034,11 +1124,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 ctx->launches += n + 3;
             }
             if (need.size() < (size_t)N_INDEP_WORDS) {
-                uint32_t rows4[4] = {0, 0, 0, 0};
-                for (int c = 0; c < nqc; c++) rows4[c] = queries[q0 + c];
-                CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, M, d_slot.p, N_WORDS, rows4, nqc, d_q1.p));
+                uint32_t rows4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // 0xffffffff: row held by another rank
+                for (int c = 0; c < nqc; c++) {
+                    int owner;
+                    uint32_t local;
+                    locate(queries[q0 + c], owner, local);
+                    if (owner == R) rows4[c] = local;
+                }
+                CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, Mr, d_slot.p, N_WORDS, rows4, nqc, d_q1.p));
                 ctx->launches++;
             }
+            if (G > 1) comm_allreduce_sum_u32(cm, d_q1.p, (size_t)N_COLS * 4, st);
+            if (!lead) continue;
             CB_CUDA(cudaMemcpyAsync(q4.data(), d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
             for (auto& g : plan)
@@ -1054,6 +1151,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     }
             for (int j = 0; j < N_COLS; j++)
                 for (int c = 0; c < nqc; c++) qv1[(size_t)j * nq + q0 + c] = q4[(size_t)j * 4 + c];
+        }
+        if (!lead) {
+            ctx->sync();
+            ctx->stage_end();
+            proof.clear();
+            ctx->collect_stages();
+            return "";
         }
         CB_CUDA(cudaMemcpyAsync(d_rows.p, queries.data(), nq * 4, cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_gather_rows(st, comp_lde.p, M, 8, d_rows.p, nq, d_q2.p));
