@@ -240,6 +240,9 @@ int cb_set_profile(cb_ctx* ctx, int enable);
 const char* cb_stage_times(cb_ctx* ctx);
 /* Counters of the last streaming proof on ctx: "fft_words=..;cached_tiles=..;transient_tiles=..;" (packed witness words
  * transformed to LDE tiles over both passes, tiles kept between the passes, transient tile slots). */
+/* host wall-clock milliseconds between the stage marks of the last profiled proof ("stage=ms;..."; a stage's entry runs
+   from its begin to the next stage's begin, so it includes the host work and stream synchronisations in between) */
+const char* cb_host_times(cb_ctx* ctx);
 const char* cb_counters(cb_ctx* ctx);
 /* ---- verification and prove+verify (wasm_api.rs:609-648 verify_chacha20_proof, :904-946 verify_aes_ctr_proof,
  * :61-188 prove_chacha20_encrypt, :210-330 prove_aes128_ctr_encrypt, :343-463 prove_aes256_ctr_encrypt).

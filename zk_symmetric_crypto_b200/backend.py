@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "cb_accumulate_quotients", "cb_fold_circle_into_line", "cb_fold_line", "cb_grind_blake2s", "cb_gather_rows",
     "cb_gen_trace_chacha_stream",
     "s2c_generate_chacha20_proof", "s2c_generate_aes128_ctr_proof", "s2c_generate_aes256_ctr_proof", "s2c_prove_aes_ctr_raw",
-    "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_counters",
+    "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_host_times", "cb_counters",
     "s2c_verify_chacha20_proof", "s2c_verify_aes_ctr_proof", "s2c_verify_chacha20_raw", "s2c_verify_aes_ctr_raw",
     "s2c_prove_chacha20_encrypt", "s2c_prove_aes128_ctr_encrypt", "s2c_prove_aes256_ctr_encrypt",
     "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
@@ -53,6 +53,7 @@ def lib():
         L.cb_last_error.restype = ctypes.c_char_p
         L.cb_stage_times.restype = ctypes.c_char_p
         L.cb_counters.restype = ctypes.c_char_p
+        L.cb_host_times.restype = ctypes.c_char_p
         L.cb_launch_count.restype = ctypes.c_uint64
         L.s2c_free.argtypes = [ctypes.c_void_p]
         _LIB = L
@@ -140,6 +141,15 @@ class Backend:
         s = self.L.cb_stage_times(self.ctx).decode()
         out = {}
         for item in s.split(";"):
+            if "=" in item:
+                k, v = item.split("=")
+                out[k] = out.get(k, 0.0) + float(v)
+        return out
+
+    def host_times(self):
+        """Host wall-clock ms per stage of the last profiled proof (includes the synchronisations inside the stage)."""
+        out = {}
+        for item in self.L.cb_host_times(self.ctx).decode().split(";"):
             if "=" in item:
                 k, v = item.split("=")
                 out[k] = out.get(k, 0.0) + float(v)

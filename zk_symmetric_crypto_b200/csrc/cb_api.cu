@@ -57,6 +57,7 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->tw_shift_dev) cudaFree(ctx->tw_shift_dev);
     ctx->close_peers();
     ctx->release_arena();
+    if (ctx->chacha_consts) cudaFree(ctx->chacha_consts);
     if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
     try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -416,6 +417,15 @@ const char* cb_stage_times(cb_ctx* ctx) {
     s.clear();
     if (!ctx) return "";
     for (auto& st : ctx->stages) s += st.name + "=" + std::to_string(st.ms) + ";";
+    return s.c_str();
+}
+
+const char* cb_host_times(cb_ctx* ctx) {
+    static thread_local std::string s;
+    s.clear();
+    if (!ctx) return "";
+    for (size_t i = 0; i + 1 < ctx->host_marks.size(); i++)
+        s += ctx->host_marks[i].first + "=" + std::to_string((ctx->host_marks[i + 1].second - ctx->host_marks[i].second) * 1e3) + ";";
     return s.c_str();
 }
 

@@ -71,6 +71,46 @@ struct ConstraintJobs {
     int n;
 };
 
+// ---- ChaCha stream AIR as a constraint table (prove_chacha.cu build_cons_recs): constraint k on mask values v[.]
+//   CR_BOOL: v[c0] (1 - v[c0])                        CR_ADD: v[c0] + 2 v[c1] - v[c2] - v[c3] - v[c4]   (c4 = -1: no carry in)
+//   CR_XOR : v[c0] - v[c1] - v[c2] + 2 v[c1] v[c2]    CR_EQ : v[c0] + v[c1] - 2 v[c0] v[c1] - v[c2]
+enum { CR_BOOL = 0, CR_ADD = 1, CR_XOR = 2, CR_EQ = 3 };
+struct ConsRec {
+    int type, c0, c1, c2, c3, c4;
+};
+HD m31::QM31 cons_rec_eval(const ConsRec& r, const m31::QM31* v) {
+    using namespace m31;
+    switch (r.type) {
+        case CR_BOOL: return qmul(v[r.c0], qsub(qone(), v[r.c0]));
+        case CR_ADD: {
+            QM31 t = qsub(qsub(qadd(v[r.c0], qadd(v[r.c1], v[r.c1])), v[r.c2]), v[r.c3]);
+            return r.c4 >= 0 ? qsub(t, v[r.c4]) : t;
+        }
+        case CR_XOR: {
+            QM31 ab = qmul(v[r.c1], v[r.c2]);
+            return qadd(qsub(qsub(v[r.c0], v[r.c1]), v[r.c2]), qadd(ab, ab));
+        }
+        default: {
+            QM31 kp = qmul(v[r.c0], v[r.c1]);
+            return qsub(qsub(qadd(v[r.c0], v[r.c1]), qadd(kp, kp)), v[r.c2]);
+        }
+    }
+}
+// Tail kernels of the streaming ChaCha prover (kernels_tail.cu): the per-column QM31 loops of prove() that used to run on the host
+struct SumComb { int res, a, b, c; };  // adder sum word res = a + b + carry-in(c) - 2 c  (word indices)
+// out[4] = sum_k table[k](mask) * apr[k]; mask: [n_cols][4] QM31 values, or (mask_is_base) [n_cols] base-field values
+cudaError_t launch_mask_constraints(cudaStream_t st, const ConsRec* table, int K, const uint32_t* mask, int mask_is_base,
+                                    const uint32_t* apr, uint32_t* out);
+// sampled[res*32+i] = sampled[a*32+i] + sampled[b*32+i] + sampled[c*32+i-1] - 2 sampled[c*32+i], in list order
+cudaError_t launch_oods_fill_sums(cudaStream_t st, uint32_t* sampled, const SumComb* combs, int n_combs);
+// FRI quotient line coefficients of every sampled column at the OODS point z (upstream pcs/quotients.rs column_line_coeffs +
+// the random-coefficient powers): coefs[j] = rc^j c, lin[0..4) = sum_j rc^j a_j, lin[4..8) = sum_j rc^j b_j with
+// c = conj(z.y) - z.y, a_j = conj(v_j) - v_j, b_j = v_j c - a_j z.y.  pw_rev[k] = rc^(nc-1-k).
+cudaError_t launch_quot_coefs(cudaStream_t st, const uint32_t* sampled, int nc, const uint32_t* pw_rev, m31::QM31 zy, uint32_t* coefs,
+                              uint32_t* lin);
+// the sum columns' coefficients folded into their operands', reverse list order (fc: [n_cols][4])
+cudaError_t launch_quot_fold_sums(cudaStream_t st, uint32_t* fc, const SumComb* combs, int n_combs);
+
 // ---- AES-CTR AIR kernels (kernels_aes.cu); plain-data mirrors of the kernel argument structs
 struct AesConsArgs {
     const uint32_t* lde;

@@ -46,6 +46,9 @@ struct cb_ctx {
     bool profile = false;
     std::vector<StageTime> stages;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    // host wall-clock marks of the last profiled proof (stage name, seconds): where the host side of a small proof spends its time
+    std::vector<std::pair<std::string, double>> host_marks;
+    void host_mark(const char* name);
     int max_cached_tiles = -1;  // streaming prover: cap on LDE tiles kept between passes (-1 = as many as memory allows)
     uint64_t launches = 0;
     // counters of the last streaming proof: packed words transformed (x32 columns), tiles cached between passes, transient slots
@@ -69,6 +72,7 @@ struct cb_ctx {
     // collective over ctx->comm: (re)allocates the arena when `realloc` says so on this rank and (re)maps all arenas when any
     // rank re-allocated.  Returns false when peer mapping is unavailable (every rank gets the same answer).
     bool sync_peer_arenas(bool realloc, size_t bytes);
+    void* chacha_consts = nullptr;      // ChaCha AIR constraint table + adder-sum list (prove_chacha.cu chacha_dev)
     void* ensure_arena(size_t bytes);
     void release_arena();
     void ensure_twiddles(int max_log);

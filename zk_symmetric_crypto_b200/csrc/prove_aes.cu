@@ -190,6 +190,8 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     }
     ctx->ensure_twiddles(m);
     ctx->pending_events.clear();
+    ctx->host_marks.clear();
+    ctx->host_mark("setup");
     CB_CUDA(aes_upload_sbox(tables().sbox));
     const std::vector<uint8_t> rk = expand_key(key, key_len);
 

@@ -87,11 +87,89 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
     return A.acc;
 }
 
+// The same traversal recorded as a table: one ConsRec per constraint, in constraint order (ConsRec: common.cuh).  The table
+// is what both the device kernel (mask_constraints_kernel: prove()'s closing check and the row-N evaluation of the
+// half-domain composition) and the host verifier evaluate; the walk above stays as the generator's cross-check.
+std::vector<ConsRec> build_cons_recs() {
+    std::vector<ConsRec> T;
+    T.reserve(N_CONSTRAINTS);
+    int col = 0;
+    using U32 = std::array<int, 32>;
+    auto next_u32 = [&]() {
+        U32 r;
+        for (int i = 0; i < 32; i++) { r[i] = col++; T.push_back({CR_BOOL, r[i], -1, -1, -1, -1}); }
+        return r;
+    };
+    auto add_u32 = [&](const U32& a, const U32& b) {
+        U32 res = next_u32();
+        U32 car;
+        for (int i = 0; i < 32; i++) car[i] = col++;
+        for (int i = 0; i < 32; i++) {
+            T.push_back({CR_BOOL, car[i], -1, -1, -1, -1});
+            T.push_back({CR_ADD, res[i], car[i], a[i], b[i], i == 0 ? -1 : car[i - 1]});
+        }
+        return res;
+    };
+    auto xor_rotl = [&](const U32& a, const U32& b, int r) {
+        U32 res = next_u32();
+        for (int i = 0; i < 32; i++) {
+            int sft = (i + 32 - r) % 32;
+            T.push_back({CR_XOR, res[i], a[sft], b[sft], -1, -1});
+        }
+        return res;
+    };
+    std::array<U32, 16> init, st;
+    for (int i = 0; i < 16; i++) init[i] = next_u32();
+    st = init;
+    static const int QRS[8][4] = {{0, 4, 8, 12}, {1, 5, 9, 13}, {2, 6, 10, 14}, {3, 7, 11, 15},
+                                  {0, 5, 10, 15}, {1, 6, 11, 12}, {2, 7, 8, 13}, {3, 4, 9, 14}};
+    for (int rnd = 0; rnd < 10; rnd++)
+        for (auto& q : QRS) {
+            int a = q[0], b = q[1], c = q[2], d = q[3];
+            st[a] = add_u32(st[a], st[b]); st[d] = xor_rotl(st[a], st[d], 16);
+            st[c] = add_u32(st[c], st[d]); st[b] = xor_rotl(st[c], st[b], 12);
+            st[a] = add_u32(st[a], st[b]); st[d] = xor_rotl(st[a], st[d], 8);
+            st[c] = add_u32(st[c], st[d]); st[b] = xor_rotl(st[c], st[b], 7);
+        }
+    std::array<U32, 16> ks, pt, ct;
+    for (int i = 0; i < 16; i++) ks[i] = add_u32(st[i], init[i]);
+    for (int i = 0; i < 16; i++) pt[i] = next_u32();
+    for (int i = 0; i < 16; i++) ct[i] = next_u32();
+    for (int i = 0; i < 16; i++)
+        for (int b = 0; b < 32; b++) T.push_back({CR_EQ, ks[i][b], pt[i][b], ct[i][b], -1, -1});
+    if ((int)T.size() != N_CONSTRAINTS || col != N_COLS) throw CbError("internal: constraint table size");
+    return T;
+}
+
+const std::vector<ConsRec>& cons_recs() {
+    static const std::vector<ConsRec> T = [] {
+        std::vector<ConsRec> t = build_cons_recs();
+        // one-time cross-check against the walk on a pseudo-random mask
+        std::vector<QM31> mask(N_COLS), apr(N_CONSTRAINTS);
+        uint64_t x = 0x9e3779b97f4a7c15ull;
+        auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x % P); };
+        for (auto& m : mask) m = {{rnd(), rnd(), rnd(), rnd()}};
+        for (auto& a : apr) a = {{rnd(), rnd(), rnd(), rnd()}};
+        QM31 acc = qzero();
+        for (int k = 0; k < N_CONSTRAINTS; k++) acc = qadd(acc, qmul(cons_rec_eval(t[k], mask.data()), apr[k]));
+        if (!qeq(acc, eval_constraints_at_mask(mask, apr))) throw CbError("internal: constraint table differs from the AIR walk");
+        return t;
+    }();
+    return T;
+}
+
+QM31 eval_cons_table(const std::vector<QM31>& mask, const std::vector<QM31>& apr) {
+    const std::vector<ConsRec>& T = cons_recs();
+    QM31 acc = qzero();
+    for (int k = 0; k < N_CONSTRAINTS; k++) acc = qadd(acc, qmul(cons_rec_eval(T[k], mask.data()), apr[k]));
+    return acc;
+}
+
 }  // namespace
 
 // shared with the host verifier (verify.cu)
 QM31 chacha_constraints_at_mask(const std::vector<QM31>& mask, const std::vector<QM31>& alpha_powers_rev) {
-    return eval_constraints_at_mask(mask, alpha_powers_rev);
+    return eval_cons_table(mask, alpha_powers_rev);
 }
 
 // ------------------------------------------------------------------------------------------------ streaming plan
@@ -327,6 +405,28 @@ int plan_peak_transient(const std::vector<Group>& plan, int lag, const std::vect
 
 }  // namespace
 
+namespace {
+// constraint table + adder-sum list, uploaded once per context
+struct ChaChaDev {
+    const ConsRec* table;
+    const SumComb* combs;
+    int n_combs;
+};
+ChaChaDev chacha_dev(cb_ctx* ctx, const std::vector<Group>& plan) {
+    std::vector<SumComb> cl;
+    for (auto& g : plan)
+        for (auto& c : g.comb) cl.push_back({c.res, c.a, c.b, c.c});
+    const size_t tb = (size_t)N_CONSTRAINTS * sizeof(ConsRec);
+    if (!ctx->chacha_consts) {
+        const std::vector<ConsRec>& T = cons_recs();
+        CB_CUDA(cudaMalloc(&ctx->chacha_consts, tb + cl.size() * sizeof(SumComb)));
+        CB_CUDA(cudaMemcpy(ctx->chacha_consts, T.data(), tb, cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb, cl.data(), cl.size() * sizeof(SumComb), cudaMemcpyHostToDevice));
+    }
+    return {(const ConsRec*)ctx->chacha_consts, (const SumComb*)((char*)ctx->chacha_consts + tb), (int)cl.size()};
+}
+}  // namespace
+
 // Proves ChaCha20 encryption of `len` bytes (multiple of 64).  On success fills proof bytes (bincode StreamProof).
 // Returns "" on success, else the reference's error string.
 std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
@@ -351,6 +451,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     cudaStream_t st = ctx->stream;
     ctx->ensure_twiddles(m);
     ctx->pending_events.clear();
+    ctx->host_marks.clear();
+    ctx->host_mark("setup");
     StageHook hk = ctx->hook();
     const StageHook* hkp = ctx->profile ? &hk : nullptr;
 
@@ -424,6 +526,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
     static const std::vector<Group> plan = build_plan();
+    const ChaChaDev cdev = chacha_dev(ctx, plan);
     // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
     const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr && G == 1;
     // Row-sharded mode over peer windows (G > 1, CUDA IPC available): LDE rows are dealt to the ranks in 2G "virtual shards" of
@@ -755,8 +858,6 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ch.mix_u64(counter);
     for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
 
-    std::vector<uint32_t> rowN(half_mode ? N_COLS : 0);
-    if (half_mode) CB_CUDA(cudaMemcpyAsync(rowN.data(), d_rowN.p, (size_t)N_COLS * 4, cudaMemcpyDeviceToHost, st));
     ctx->sync();
     roots.push_back(tree1.root);
     ch.mix_root(tree1.root);
@@ -773,6 +874,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     DBuf<double> gtab(ctx, ctab.idx.size() * 8);
     DBuf<int> d_cidx(ctx, ctab.idx.size());
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
+    // the constraint sum at storage row N (half-domain evaluation below): one block over the AIR's constraint table
+    DBuf<uint32_t> d_qrow(ctx, 8);
+    if (half_mode && R == 0) {
+        CB_CUDA(launch_mask_constraints(st, cdev.table, N_CONSTRAINTS, d_rowN.p, 1, apr.p, d_qrow.p));
+        ctx->launches++;
+    }
     if (cons_v1) {
         CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
     } else {
@@ -816,18 +923,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     });
     CB_CUDA(launch_scale_rows(st, accp, Mr, n, d_den.p, p2p ? (size_t)R * Mv : (size_t)R * Mr));
     ctx->launches++;
-    // reversed powers of the random coefficient on the host: the one-row evaluation below and prove()'s closing check
-    std::vector<QM31> aprh(N_CONSTRAINTS);
     QM31 q_rowN = qzero();
-    if (R == 0) {
-        QM31 cur = qone();
-        for (int e = 0; e < N_CONSTRAINTS; e++) { aprh[N_CONSTRAINTS - 1 - e] = cur; cur = qmul(cur, random_coeff); }
-    }
-    if (half_mode && R == 0) {  // the constraint sum at storage row N, on the host while the GPU works through the constraint pass
-        std::vector<QM31> mask(N_COLS);
-        for (int j = 0; j < N_COLS; j++) mask[j] = qfrom(rowN[j]);
-        q_rowN = eval_constraints_at_mask(mask, aprh);
-    }
     if (G > 1) {
         // the row shards of the accumulator go to rank 0, which finishes the proof alone (4-8 columns from here on)
         comm_group_start();
@@ -871,6 +967,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             CB_CUDA(launch_oods_dot(st, comp_coef.p, M, 4, n, bas.p, N, d_e.p));
             uint32_t e16[16], qn[4], c0[4];
             CB_CUDA(cudaMemcpyAsync(e16, d_e.p, sizeof e16, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(cudaMemcpyAsync(q_rowN.v, d_qrow.p, 16, cudaMemcpyDeviceToHost, st));
             for (int c = 0; c < 4; c++) CB_CUDA(cudaMemcpyAsync(&c0[c], comp_coef.p + (size_t)c * M, 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
             for (int c = 0; c < 4; c++) qn[c] = mul(q_rowN.v[c], den[1]);
@@ -927,12 +1024,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     }
     DBuf<int> d_indep(ctx, indep_words.size());
     CB_CUDA(cudaMemcpyAsync(d_indep.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DBuf<uint32_t> d_sampled(ctx, ((size_t)N_COLS + 8) * 4), d_close(ctx, 4);
     {
         std::vector<QM31> maps(n);
         maps[0] = z.y;
         QM31 x = z.x;
         for (int j = 1; j < n; j++) { maps[j] = x; x = qsub(qmul_m(qmul(x, x), 2), qone()); }
-        DBuf<uint32_t> d_sampled(ctx, ((size_t)N_COLS + 8) * 4);
         CB_CUDA(launch_basis(st, basis.p, N, n, maps.data()));
         ColSrc bs{SRC_M31, basis.p, N, 0};
         CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
@@ -942,19 +1039,15 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             for (int half = 0; half < 2; half++)
                 CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
         if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)N_COLS + 8) * 4, st);
-        ctx->launches += n + 6;
+        CB_CUDA(launch_oods_fill_sums(st, d_sampled.p, cdev.combs, cdev.n_combs));  // the adder-sum words' samples, from their operands'
+        ctx->launches += n + 7;
         CB_CUDA(cudaMemcpyAsync(sampled.data(), d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
+        // prove()'s closing check (numerator): the AIR on the sampled mask, read back at the end
+        if (lead) {
+            CB_CUDA(launch_mask_constraints(st, cdev.table, N_CONSTRAINTS, d_sampled.p, 0, apr.p, d_close.p));
+            ctx->launches++;
+        }
         ctx->sync();
-        for (auto& g : plan)
-            for (auto& cb : g.comb) {
-                QM31 cin = qzero();
-                for (int i = 0; i < 32; i++) {
-                    const QM31 cv = sampled[(size_t)cb.c * 32 + i];
-                    sampled[(size_t)cb.res * 32 + i] =
-                        qsub(qadd(qadd(sampled[(size_t)cb.a * 32 + i], sampled[(size_t)cb.b * 32 + i]), cin), qadd(cv, cv));
-                    cin = cv;
-                }
-            }
     }
     ctx->stage_end();
     ch.mix_felts(sampled.data(), sampled.size());
@@ -965,43 +1058,20 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     ctx->stage_begin("quotients");
     DBuf<uint32_t> quot(ctx, lead ? 4 * M : 4);
     {
-        const size_t nc = sampled.size();
-        std::vector<uint32_t> coefs(nc * 4);
-        QM31 alpha = qone(), lin_a = qzero(), lin_b = qzero();
-        const QM31 c = qsub(qconj(z.y), z.y);
-        for (size_t j = 0; j < nc; j++) {
-            QM31 v = sampled[j];
-            QM31 a = qsub(qconj(v), v);
-            QM31 b = qsub(qmul(v, c), qmul(a, z.y));
-            lin_a = qadd(lin_a, qmul(alpha, a));
-            lin_b = qadd(lin_b, qmul(alpha, b));
-            QM31 ac = qmul(alpha, c);
-            for (int k = 0; k < 4; k++) coefs[j * 4 + k] = ac.v[k];
-            alpha = qmul(alpha, rc);
-        }
-        // fold the sum columns' coefficients into their operands' (reverse dependency order: a sum may feed a later sum)
-        std::vector<uint32_t> fc(coefs.begin(), coefs.begin() + (size_t)N_COLS * 4);
-        for (size_t gi = plan.size(); gi-- > 0;)
-            for (size_t ci = plan[gi].comb.size(); ci-- > 0;) {
-                const Comb& cb = plan[gi].comb[ci];
-                for (int i = 0; i < 32; i++)
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t kap = fc[((size_t)cb.res * 32 + i) * 4 + k];
-                        uint32_t& fa = fc[((size_t)cb.a * 32 + i) * 4 + k];
-                        fa = add(fa, kap);
-                        uint32_t& fb = fc[((size_t)cb.b * 32 + i) * 4 + k];
-                        fb = add(fb, kap);
-                        uint32_t& fcy = fc[((size_t)cb.c * 32 + i) * 4 + k];
-                        fcy = sub(fcy, add(kap, kap));
-                        if (i > 0) {
-                            uint32_t& fcp = fc[((size_t)cb.c * 32 + i - 1) * 4 + k];
-                            fcp = add(fcp, kap);
-                        }
-                    }
-            }
-        DBuf<uint32_t> d_coefs(ctx, (size_t)N_COLS * 4), g(ctx, 4 * N), g_lde(ctx, lead ? 4 * M : 4), d_bc(ctx, 12 * 4);
-        CB_CUDA(cudaMemcpyAsync(d_coefs.p, fc.data(), fc.size() * 4, cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_bitrow_comb(st, W.p, N, (int)indep_words.size(), d_coefs.p, g.p, d_indep.p));
+        // line coefficients of all 33,288 sampled columns, the powers of the random coefficient and the folding of the sum
+        // columns' coefficients into their operands': device kernels over the sampled values (kernels_tail.cu)
+        const int nc = (int)sampled.size();
+        DBuf<uint32_t> d_pw(ctx, (size_t)nc * 4), d_call(ctx, (size_t)nc * 4), d_lin(ctx, 8);
+        CB_CUDA(launch_secure_powers_rev(st, rc, nc, d_pw.p));
+        CB_CUDA(launch_quot_coefs(st, d_sampled.p, nc, d_pw.p, z.y, d_call.p, d_lin.p));
+        DBuf<uint32_t> g(ctx, 4 * N), g_lde(ctx, lead ? 4 * M : 4), d_bc(ctx, 12 * 4);
+        const uint32_t ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        CB_CUDA(cudaMemcpyAsync(d_bc.p, ident, sizeof ident, cudaMemcpyHostToDevice, st));
+        CB_CUDA(cudaMemcpyAsync(d_bc.p + 16, d_call.p + (size_t)N_COLS * 4, 8 * 16, cudaMemcpyDeviceToDevice, st));  // composition columns
+        CB_CUDA(launch_quot_fold_sums(st, d_call.p, cdev.combs, cdev.n_combs));
+        uint32_t* const d_coefs_p = d_call.p;
+        ctx->launches += 3;
+        CB_CUDA(launch_bitrow_comb(st, W.p, N, (int)indep_words.size(), d_coefs_p, g.p, d_indep.p));
         if (G > 1) {  // the ranks' partial combinations (disjoint word sets) are added on the lead
             DBuf<uint32_t> parts(ctx, lead ? (size_t)G * 4 * N : 4);
             comm_group_start();
@@ -1018,17 +1088,15 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         if (lead) {
         ColSrc gs{SRC_M31, g.p, N, 0};
         CB_CUDA(launch_fft(st, gs, 4, n, cfg.log_blowup, 1 | 4, nullptr, 0, g_lde.p, M, ctx->tw, g.p, N));
-        uint32_t bc[12 * 4] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-        for (int j = 0; j < 8; j++)
-            for (int k = 0; k < 4; k++) bc[(4 + j) * 4 + k] = coefs[((size_t)N_COLS + j) * 4 + k];
-        CB_CUDA(cudaMemcpyAsync(d_bc.p, bc, sizeof bc, cudaMemcpyHostToDevice, st));
         QuotBatch qb{};
         qb.prx = {z.x.v[0], z.x.v[1]}; qb.pix = {z.x.v[2], z.x.v[3]};
         qb.pry = {z.y.v[0], z.y.v[1]}; qb.piy = {z.y.v[2], z.y.v[3]};
-        qb.lin_a = lin_a; qb.lin_b = lin_b; qb.batch_coeff = qzero();
+        qb.lin_a = qzero(); qb.lin_b = qzero(); qb.batch_coeff = qzero();  // lin_a / lin_b: filled on the device below
         qb.coefs = d_bc.p; qb.col_idx = nullptr; qb.n_cols = 12;
         DBuf<QuotBatch> d_qb(ctx, 1);
         CB_CUDA(cudaMemcpyAsync(d_qb.p, &qb, sizeof(qb), cudaMemcpyHostToDevice, st));
+        static_assert(offsetof(QuotBatch, lin_b) == offsetof(QuotBatch, lin_a) + 16, "lin_a, lin_b contiguous");
+        CB_CUDA(cudaMemcpyAsync((char*)d_qb.p + offsetof(QuotBatch, lin_a), d_lin.p, 32, cudaMemcpyDeviceToDevice, st));
         CB_CUDA(launch_quotients(st, g_lde.p, M, 4, comp_lde.p, M, d_qb.p, 1, m, ctx->tw, quot.p, M));
         ctx->launches += 5;
         }
@@ -1169,8 +1237,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- prove()'s closing check: composition OODS value == constraints on the sampled mask / Z_H(z)
     {
-        std::vector<QM31> mask(sampled.begin(), sampled.begin() + N_COLS);
-        QM31 num = eval_constraints_at_mask(mask, aprh);
+        QM31 num;
+        CB_CUDA(cudaMemcpyAsync(num.v, d_close.p, 16, cudaMemcpyDeviceToHost, st));
+        ctx->sync();
         QM31 zh = coset_vanishing_q(n, z);
         QM31 expect = qmul(num, qinv(zh));
         const QM31 units[4] = {{{1, 0, 0, 0}}, {{0, 1, 0, 0}}, {{0, 0, 1, 0}}, {{0, 0, 0, 1}}};

@@ -1,4 +1,5 @@
 // Context plumbing and prover building blocks shared by the AIR-specific drivers.
+#include <chrono>
 #include "ctx.hpp"
 
 void cb_ctx::ensure_twiddles(int max_log) {
@@ -128,8 +129,13 @@ void cb_ctx::dfree(void* p) {
     if (p) cudaFreeAsync(p, stream);
 }
 
+void cb_ctx::host_mark(const char* name) {
+    if (!profile) return;
+    host_marks.push_back({name, std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count()});
+}
 void cb_ctx::stage_begin(const char* name) {
     if (!profile) return;
+    host_mark(name);
     cudaEvent_t a, b;
     CB_CUDA(cudaEventCreate(&a));
     CB_CUDA(cudaEventCreate(&b));
@@ -143,6 +149,7 @@ void cb_ctx::stage_end() {
 void cb_ctx::collect_stages() {
     if (!profile) return;
     sync();
+    host_mark("end");
     stages.clear();
     for (auto& e : pending_events) {
         float ms = 0;
