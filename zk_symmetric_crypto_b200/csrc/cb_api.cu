@@ -58,6 +58,9 @@ void cb_destroy(cb_ctx* ctx) {
     ctx->close_peers();
     ctx->release_arena();
     if (ctx->chacha_consts) cudaFree(ctx->chacha_consts);
+    if (ctx->small_jobs) cudaFree(ctx->small_jobs);
+    if (ctx->chacha_cidx) cudaFree(ctx->chacha_cidx);
+    if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
     if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
     try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);

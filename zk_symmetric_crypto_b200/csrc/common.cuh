@@ -163,6 +163,8 @@ struct StageHook {
 cudaError_t launch_fft(cudaStream_t st, const ColSrc& src, int ncols, int log_n, int ext, int mode, uint32_t* coef_out,
                        size_t coef_stride, uint32_t* eval_out, size_t eval_stride, const FftTables& tw, uint32_t* scratch,
                        size_t scratch_stride, const StageHook* hook = nullptr);
+cudaError_t launch_fft_packed_list(cudaStream_t st, const int* wlist_dev, int n_words, const uint32_t* src0, size_t src_stride,
+                                   uint32_t* out0, size_t out_stride, int log_n, const FftTables& tw);
 void fft_init_attrs();
 void fft2_init_attrs();
 size_t fft_packed_scratch_words(int kind, int njobs, int log_n);
@@ -184,6 +186,11 @@ cudaError_t launch_constraints_tiles(cudaStream_t st, const ConstraintJobs& jobs
 // slice in it (in constraints)
 cudaError_t launch_constraints_tiles2(cudaStream_t st, const ConstraintJobs& jobs, size_t M, const double* gtab, uint32_t* acc, int first,
                                       size_t rows = 0);
+// product-size traces: the whole AIR in one launch (job list in device memory, one block column per job) + a reduction
+cudaError_t launch_constraints_jobs(cudaStream_t st, const ConstraintJob* jobs_dev, int n_jobs, size_t M, const double* gtab,
+                                    uint32_t* partial, uint32_t* acc, size_t rows);
+cudaError_t launch_sum_tiles(cudaStream_t st, uint32_t* arena, size_t tile_words, size_t rows, const SumComb* combs, int n_combs);
+cudaError_t launch_merkle_leaves_seq(cudaStream_t st, const uint32_t* arena, size_t tile_words, int n_words, int lifting_log, uint32_t* out);
 cudaError_t launch_cons_table(cudaStream_t st, const uint32_t* apr, const int* idx_dev, int n, double* gtab);
 cudaError_t launch_split16(cudaStream_t st, const uint32_t* table, int n, uint32_t* lo, uint32_t* hi);
 cudaError_t launch_scale_rows(cudaStream_t st, uint32_t* acc, size_t M, int trace_log, const uint32_t* den_inv, size_t row0 = 0);

@@ -72,6 +72,13 @@ struct cb_ctx {
     // collective over ctx->comm: (re)allocates the arena when `realloc` says so on this rank and (re)maps all arenas when any
     // rank re-allocated.  Returns false when peer mapping is unavailable (every rank gets the same answer).
     bool sync_peer_arenas(bool realloc, size_t bytes);
+    void* small_jobs = nullptr;         // product-size ChaCha proofs: constraint job list of the whole AIR (device), valid for
+    void* small_jobs_arena = nullptr;   // this arena base and tile pitch
+    size_t small_jobs_tile_words = 0;
+    void* chacha_cidx = nullptr;        // ChaCha alpha-table index list (consumption order)
+    uint32_t* pin_buf = nullptr;        // pinned host staging for read-backs (pinned_words)
+    size_t pin_words = 0;
+    uint32_t* pinned_words(size_t words);
     void* chacha_consts = nullptr;      // ChaCha AIR constraint table + adder-sum list (prove_chacha.cu chacha_dev)
     void* ensure_arena(size_t bytes);
     void release_arena();

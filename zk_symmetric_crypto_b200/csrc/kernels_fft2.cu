@@ -148,6 +148,12 @@ struct Jobs {
     uint32_t* peer_base[MAX_PEERS];             // arena of rank r as mapped in this process; used when peer_on
     unsigned long long peer_off[MAX_FFT_JOBS];  // word offset of job j's destination slot inside every rank's arena
     int peer_on, peer_logG, peer_lv;
+    // product-size traces (small_kernel only): any number of jobs addressed through a device word list,
+    // job j: src = src0 + wlist[j] * src_stride, out = out0 + wlist[j] * out_stride
+    const int* wlist;
+    const uint32_t* src0;
+    uint32_t* out0;
+    size_t src_stride, out_stride;
 };
 
 // destination of the chunk starting at global row `row0` of column `c0` of job `job` (column stride 2^(lv+1) words)
@@ -171,7 +177,8 @@ __global__ void __launch_bounds__(256) small_kernel(Jobs jobs, int log_n, int nc
     const int n = 1 << log_n, m = log_n + 1, big = 2 << log_n;
     const int colstride = padi(big);
     const int job = blockIdx.x / groups_per_job, c0 = (blockIdx.x % groups_per_job) * nc;
-    const uint32_t* __restrict__ src = jobs.src[job];
+    const int wj = jobs.wlist ? jobs.wlist[job] : 0;
+    const uint32_t* __restrict__ src = jobs.wlist ? jobs.src0 + (size_t)wj * jobs.src_stride : jobs.src[job];
     const uint32_t scale = 1u << (31 - log_n), scale2 = scale << 1;
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         if (KIND == SRC_M31) {  // job = cols_per_job plain M31 columns, n words apart
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(256) small_kernel(Jobs jobs, int log_n, int nc
     }
     __syncthreads();
     apply_layers<false, true>(s, nc, colstride, m, 0, 0, log_n, tw.X, tw.Y, m, 0, 0);
-    uint32_t* __restrict__ out = jobs.out[job];
+    uint32_t* __restrict__ out = jobs.wlist ? jobs.out0 + (size_t)wj * jobs.out_stride : jobs.out[job];
     for (int idx = threadIdx.x; idx < nc * big; idx += blockDim.x) {
         int c = idx >> m, r = idx & (big - 1);
         out[(size_t)(c0 + c) * big + r] = s[c * colstride + padi(r)];
@@ -640,6 +647,34 @@ void fft2_init_attrs() {
     cudaFuncSetAttribute(mid12_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 32 * 4);
 }
 
+// Product-size traces (log_n <= 12): ONE launch transforms the packed words listed in wlist_dev (n_words of them), word w from
+// src0 + w * src_stride into the tile out0 + w * out_stride.
+cudaError_t launch_fft_packed_list(cudaStream_t st, const int* wlist_dev, int n_words, const uint32_t* src0, size_t src_stride,
+                                   uint32_t* out0, size_t out_stride, int log_n, const FftTables& tw) {
+    using namespace fft2;
+    if (log_n > 12 || n_words <= 0) return cudaErrorInvalidValue;
+    Jobs jobs{};
+    jobs.n = n_words;
+    jobs.one = 1u;
+    jobs.mone = 0xffffffffu;
+    jobs.halves = 2;
+    jobs.shard_log = log_n + 1;
+    jobs.wlist = wlist_dev;
+    jobs.src0 = src0;
+    jobs.out0 = out0;
+    jobs.src_stride = src_stride;
+    jobs.out_stride = out_stride;
+    const int cpj = 32, big = 2 << log_n;
+    int nc = 8192 / big;
+    if (nc > cpj) nc = cpj;
+    if (nc < 1) nc = 1;
+    const int gpj = cpj / nc;
+    const size_t smem = (size_t)nc * (big + (big >> 4)) * 4;
+    const int threads = (nc * big / 16) < 256 ? ((nc * big / 16) < 32 ? 32 : nc * big / 16) : 256;
+    small_kernel<SRC_BITS><<<n_words * gpj, threads, smem, st>>>(jobs, log_n, nc, gpj, tw);
+    return cudaGetLastError();
+}
+
 // words of scratch launch_fft_packed needs for `njobs` jobs at log size n
 size_t fft_packed_scratch_words(int kind, int njobs, int log_n) {
     if (log_n <= 12) return 0;
@@ -666,6 +701,7 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         for (int j = 0; j < jobs.n; j++) { jobs.src[j] = src[j0 + j]; jobs.out[j] = out[j0 + j]; }
         jobs.peer_on = 0;
         jobs.peer_logG = jobs.peer_lv = 0;
+        jobs.wlist = nullptr;
         if (peer) {  // chunks of the last pass (2^12 or 2^k1 <= 2^13 rows) must lie inside one virtual shard
             if (log_n <= 12 || peer->lv < 13 || peer->logG > 3) return cudaErrorInvalidValue;
             jobs.peer_on = 1;

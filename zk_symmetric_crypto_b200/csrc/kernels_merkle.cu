@@ -216,6 +216,38 @@ __global__ void __launch_bounds__(128) leaves_tiles_kernel(LeafGroups groups, in
     }
 }
 
+// Product-size traces with the whole LDE materialised: one launch absorbs all words of the tree, tile(w) = arena + w * tile_words,
+// [32][n_leaves].  A leaf's 2 n_words compressions are one dependent chain on a nearly empty GPU, so the next block's 16 column
+// loads are issued before the current compression.  The additions stay IADD3 here: the FMA-pipe form (two IMAD per 3-input add)
+// lengthens the chain and measured slower for a lone warp (2.6 vs 2.2 ms for the 2,080 compressions of a ChaCha leaf).
+__global__ void __launch_bounds__(64) leaves_seq_kernel(const uint32_t* __restrict__ arena, size_t tile_words, uint32_t n_leaves, int n_words,
+                                                        uint32_t* __restrict__ out) {
+    const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    uint32_t h[8];
+    blake2s::init(h);
+    const uint32_t* __restrict__ p = arena + leaf;
+    uint32_t nxt[16], m[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) nxt[w] = __ldg(p + (size_t)w * n_leaves);
+    const int n_blocks = 2 * n_words;
+    uint64_t t = 0;
+#pragma unroll 1
+    for (int b = 0; b < n_blocks; b++) {
+#pragma unroll
+        for (int w = 0; w < 16; w++) m[w] = nxt[w];
+        if (b + 1 < n_blocks) {
+            const uint32_t* __restrict__ q = p + (size_t)((b + 1) >> 1) * tile_words + (size_t)(((b + 1) & 1) * 16) * n_leaves;
+#pragma unroll
+            for (int w = 0; w < 16; w++) nxt[w] = __ldg(q + (size_t)w * n_leaves);
+        }
+        t += 64;
+        blake2s::compress(h, m, t, b + 1 == n_blocks);
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) out[(size_t)leaf * 8 + w] = h[w];
+}
+
 // parent[i] = Blake2s(child[2i] || child[2i+1]); hashes are 8 consecutive u32
 __global__ void __launch_bounds__(256) nodes_kernel(const uint4* __restrict__ prev, uint32_t n_parents, uint4* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,6 +284,13 @@ cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int 
     else
         merk::leaves_kernel<false><<<(n + threads - 1) / threads, threads, 0, st>>>(groups, lifting_log, h_state, bytes_before,
                                                                                     is_first, is_final, out, 1u);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merkle_leaves_seq(cudaStream_t st, const uint32_t* arena, size_t tile_words, int n_words, int lifting_log, uint32_t* out) {
+    const uint32_t n = 1u << lifting_log;
+    const int threads = n >= 64 * 148 ? 64 : 32;
+    merk::leaves_seq_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(arena, tile_words, n, n_words, out);
     return cudaGetLastError();
 }
 

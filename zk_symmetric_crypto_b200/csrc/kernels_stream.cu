@@ -245,6 +245,53 @@ __device__ __forceinline__ void addx_job2(const ConstraintJob& J, size_t row, si
 
 // jobs.j[k].kx = offset (in constraints) of job k's slice inside `gtab`; slice sizes: CJ_BOOL 32, CJ_ADDX 128 (64 without the xor
 // part), CJ_XOR/CJ_XORN 128 entries of 8 doubles
+// one job for one row: stage the job's slice of the alpha table (all threads of the block), then accumulate its constraints
+__device__ __forceinline__ void cons_job2(const ConstraintJob& J, size_t row, size_t M, const double* __restrict__ gtab, double* stab,
+                                          AccF64& A, bool live) {
+    const int n_e = J.type == CJ_BOOL ? 32 : (J.type == CJ_ADDX && !J.t0 ? 64 : 128);
+    __syncthreads();
+    {
+        const double2* __restrict__ src = (const double2*)(gtab + (size_t)J.kx * 8);
+        for (int i = threadIdx.x; i < n_e * 4; i += blockDim.x) ((double2*)stab)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (!live) return;
+    if (J.type == CJ_ADDX) {
+        if (J.t0) addx_job2<true>(J, row, M, stab, A);
+        else addx_job2<false>(J, row, M, stab, A);
+    } else if (J.type == CJ_BOOL) {
+        const uint32_t* __restrict__ t = J.t0 + row;
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+            const uint32_t b = t[(size_t)i * M];
+            A.mac(stab + i * 8, bool_c(b, b + b));
+        }
+        A.fold();
+    } else {
+        const uint32_t* __restrict__ r = J.t0 + row;
+        const uint32_t* __restrict__ a = J.t1 + row;
+        const uint32_t* __restrict__ d = J.t2 + row;
+        const bool neg = J.type == CJ_XORN;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+#pragma unroll 4
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u, s = (i + 32 - J.arg) & 31;
+                const uint32_t rv = r[(size_t)i * M], av = a[(size_t)s * M], dv = d[(size_t)s * M];
+                const uint32_t ad = mulm(av, dv);
+                uint32_t C = addm(subm(subm(rv, av), dv), dbl(ad));
+                if (neg) C = subm(0, C);
+                const double* e = stab + (i * 4) * 8;  // absent booleans have an all-zero table entry
+                A.mac(e, C);
+                A.mac(e + 8, bool_c(rv, rv + rv));
+                A.mac(e + 16, bool_c(av, av + av));
+                A.mac(e + 24, bool_c(dv, dv + dv));
+            }
+            A.fold();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, CONS2_MIN_BLOCKS) constraints_tiles_kernel2(ConstraintJobs jobs, size_t M, const double* __restrict__ gtab,
                                                                  uint32_t* __restrict__ acc, int first, size_t rows) {
     __shared__ __align__(16) double stab[128 * 8];
@@ -253,51 +300,7 @@ __global__ void __launch_bounds__(128, CONS2_MIN_BLOCKS) constraints_tiles_kerne
     const size_t row = live ? row0 : 0;  // idle threads of the last block still help staging (their results are not stored)
     AccF64 A;
     A.init();
-    for (int j = 0; j < jobs.n; j++) {
-        const ConstraintJob& J = jobs.j[j];
-        const int n_e = J.type == CJ_BOOL ? 32 : (J.type == CJ_ADDX && !J.t0 ? 64 : 128);
-        __syncthreads();
-        {
-            const double2* __restrict__ src = (const double2*)(gtab + (size_t)J.kx * 8);
-            for (int i = threadIdx.x; i < n_e * 4; i += blockDim.x) ((double2*)stab)[i] = __ldg(src + i);
-        }
-        __syncthreads();
-        if (!live) continue;
-        if (J.type == CJ_ADDX) {
-            if (J.t0) addx_job2<true>(J, row, M, stab, A);
-            else addx_job2<false>(J, row, M, stab, A);
-        } else if (J.type == CJ_BOOL) {
-            const uint32_t* __restrict__ t = J.t0 + row;
-#pragma unroll 8
-            for (int i = 0; i < 32; i++) {
-                const uint32_t b = t[(size_t)i * M];
-                A.mac(stab + i * 8, bool_c(b, b + b));
-            }
-            A.fold();
-        } else {
-            const uint32_t* __restrict__ r = J.t0 + row;
-            const uint32_t* __restrict__ a = J.t1 + row;
-            const uint32_t* __restrict__ d = J.t2 + row;
-            const bool neg = J.type == CJ_XORN;
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 8) {
-#pragma unroll 4
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + u, s = (i + 32 - J.arg) & 31;
-                    const uint32_t rv = r[(size_t)i * M], av = a[(size_t)s * M], dv = d[(size_t)s * M];
-                    const uint32_t ad = mulm(av, dv);
-                    uint32_t C = addm(subm(subm(rv, av), dv), dbl(ad));
-                    if (neg) C = subm(0, C);
-                    const double* e = stab + (i * 4) * 8;  // absent booleans have an all-zero table entry
-                    A.mac(e, C);
-                    A.mac(e + 8, bool_c(rv, rv + rv));
-                    A.mac(e + 16, bool_c(av, av + av));
-                    A.mac(e + 24, bool_c(dv, dv + dv));
-                }
-                A.fold();
-            }
-        }
-    }
+    for (int j = 0; j < jobs.n; j++) cons_job2(jobs.j[j], row, M, gtab, stab, A, live);
     if (!live) return;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -305,6 +308,47 @@ __global__ void __launch_bounds__(128, CONS2_MIN_BLOCKS) constraints_tiles_kerne
         uint32_t* o = acc + (size_t)c * M + row;
         if (!first) v = addm(v, *o);
         *o = v;
+    }
+}
+
+// Product-size traces (a few dozen to a few thousand rows): one thread per row walking all jobs is a long dependent chain on a
+// nearly empty GPU.  Here blockIdx.y = job (the whole AIR in ONE launch, job list in device memory) and every block writes its
+// job's partial sums, partial[(job * 4 + c) * rows + row]; cons_partial_reduce_kernel adds them up.
+__global__ void __launch_bounds__(128) constraints_jobs_kernel(const ConstraintJob* __restrict__ jobs, size_t M, const double* __restrict__ gtab,
+                                                               uint32_t* __restrict__ partial, size_t rows) {
+    __shared__ __align__(16) double stab[128 * 8];
+    const size_t row0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = row0 < rows;
+    const size_t row = live ? row0 : 0;
+    const ConstraintJob J = jobs[blockIdx.y];
+    AccF64 A;
+    A.init();
+    cons_job2(J, row, M, gtab, stab, A, live);
+    if (!live) return;
+#pragma unroll
+    for (int c = 0; c < 4; c++) partial[((size_t)blockIdx.y * 4 + c) * rows + row] = A.result(c);
+}
+__global__ void cons_partial_reduce_kernel(const uint32_t* __restrict__ partial, int n_jobs, size_t rows, size_t M, uint32_t* __restrict__ acc) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 4 * rows) return;
+    const size_t c = idx / rows, row = idx % rows;
+    uint32_t v = 0;
+    for (int j = 0; j < n_jobs; j++) v = addm(v, partial[((size_t)j * 4 + c) * rows + row]);
+    acc[c * M + row] = v;
+}
+
+// Adder-sum tiles of a fully materialised LDE (product-size traces): tile(res) = tile(a) + tile(b) + carry-in(c) - 2 tile(c),
+// in list order; tile(w) = arena + w * tile_words, [32][rows].  thread = (bit, row): it only reads sums it wrote itself.
+__global__ void sum_tiles_kernel(uint32_t* __restrict__ arena, size_t tile_words, size_t rows, const SumComb* __restrict__ combs, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 32 * rows) return;
+    const size_t i = idx / rows;
+    for (int t = 0; t < n; t++) {
+        const SumComb cb = combs[t];
+        const uint32_t* cy = arena + (size_t)cb.c * tile_words;
+        const uint32_t cv = cy[idx], cin = i ? cy[idx - rows] : 0;
+        const uint32_t av = arena[(size_t)cb.a * tile_words + idx], bv = arena[(size_t)cb.b * tile_words + idx];
+        arena[(size_t)cb.res * tile_words + idx] = subm(addm(addm(av, bv), cin), dbl(cv));
     }
 }
 
@@ -724,6 +768,18 @@ cudaError_t launch_constraints_tiles2(cudaStream_t st, const ConstraintJobs& job
     if (rows == 0 || rows > M) rows = M;
     int threads = rows >= 128 * 148 ? 128 : 32;
     strm::constraints_tiles_kernel2<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(jobs, M, gtab, acc, first, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_constraints_jobs(cudaStream_t st, const ConstraintJob* jobs_dev, int n_jobs, size_t M, const double* gtab,
+                                    uint32_t* partial, uint32_t* acc, size_t rows) {
+    const int threads = rows >= 128 ? 128 : 32;
+    strm::constraints_jobs_kernel<<<dim3((unsigned)((rows + threads - 1) / threads), n_jobs), threads, 0, st>>>(jobs_dev, M, gtab, partial, rows);
+    strm::cons_partial_reduce_kernel<<<(unsigned)((4 * rows + 127) / 128), 128, 0, st>>>(partial, n_jobs, rows, M, acc);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_tiles(cudaStream_t st, uint32_t* arena, size_t tile_words, size_t rows, const SumComb* combs, int n_combs) {
+    strm::sum_tiles_kernel<<<(unsigned)((32 * rows + 127) / 128), 128, 0, st>>>(arena, tile_words, rows, combs, n_combs);
     return cudaGetLastError();
 }
 

@@ -411,19 +411,25 @@ struct ChaChaDev {
     const ConsRec* table;
     const SumComb* combs;
     int n_combs;
+    const int* indep;  // the N_INDEP_WORDS transformed words, plan order
 };
 ChaChaDev chacha_dev(cb_ctx* ctx, const std::vector<Group>& plan) {
     std::vector<SumComb> cl;
     for (auto& g : plan)
         for (auto& c : g.comb) cl.push_back({c.res, c.a, c.b, c.c});
-    const size_t tb = (size_t)N_CONSTRAINTS * sizeof(ConsRec);
+    const size_t tb = (size_t)N_CONSTRAINTS * sizeof(ConsRec), cb = cl.size() * sizeof(SumComb);
     if (!ctx->chacha_consts) {
         const std::vector<ConsRec>& T = cons_recs();
-        CB_CUDA(cudaMalloc(&ctx->chacha_consts, tb + cl.size() * sizeof(SumComb)));
+        std::vector<int> iw;
+        for (auto& g : plan)
+            for (int w : g.fft) iw.push_back(w);
+        CB_CUDA(cudaMalloc(&ctx->chacha_consts, tb + cb + iw.size() * sizeof(int)));
         CB_CUDA(cudaMemcpy(ctx->chacha_consts, T.data(), tb, cudaMemcpyHostToDevice));
-        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb, cl.data(), cl.size() * sizeof(SumComb), cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb, cl.data(), cb, cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb + cb, iw.data(), iw.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
-    return {(const ConsRec*)ctx->chacha_consts, (const SumComb*)((char*)ctx->chacha_consts + tb), (int)cl.size()};
+    return {(const ConsRec*)ctx->chacha_consts, (const SumComb*)((char*)ctx->chacha_consts + tb), (int)cl.size(),
+            (const int*)((char*)ctx->chacha_consts + tb + cb)};
 }
 }  // namespace
 
@@ -488,6 +494,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             const uint8_t* hp = ctx->hash_stage;
             hashers.a = std::thread([&pth, hp, len] { pth = host::blake2s_bytes(hp, len); });
             hashers.b = std::thread([&cth, hp, len] { cth = host::blake2s_bytes(hp + len, len); });
+        } else if (len <= ((size_t)1 << 16)) {  // product-size inputs: cheaper than starting two threads
+            pth = host::blake2s_bytes(plaintext, len);
+            cth = host::blake2s_bytes(ciphertext, len);
         } else {
             hashers.a = std::thread([&] { pth = host::blake2s_bytes(plaintext, len); });
             hashers.b = std::thread([&] { cth = host::blake2s_bytes(ciphertext, len); });
@@ -547,8 +556,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const int n_stage = G > 1 ? (16 + G - 1) / G : 0;
     const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, G > 1 ? n_stage : MAX_FFT_JOBS, n);
     const size_t stage_words = (size_t)n_stage * 32 * M;
+    // Product-size traces (log_size <= 10): the whole LDE (1,040 tiles, <= 272 MB) is materialised, so each pass is a handful
+    // of launches over all words instead of 85 plan groups - at these sizes a proof is bound by launch count and by the dependent
+    // chains inside the per-row kernels, not by arithmetic (profiles/r02: log 4, 417 launches, 12 ms).
+    const bool small_mode = G == 1 && n <= 10 && getenv("S2C_NO_SMALL") == nullptr;
     int n_cache = N_INDEP_WORDS;
-    {
+    if (!small_mode) {
         size_t free_b = 0, total_b = 0;
         CB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         cudaMemPool_t pool;
@@ -589,10 +602,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         }
         n_cache = comm_min_int(cm, n_cache, st);  // every rank must take the same caching decisions
     }
-    const std::vector<char> want = cache_choice(plan, n_cache);
-    const int peak_trans = plan_peak_transient(plan, lag, want);
+    const std::vector<char> want = small_mode ? std::vector<char>(N_WORDS, 1) : cache_choice(plan, n_cache);
+    const int peak_trans = small_mode ? N_WORDS - N_INDEP_WORDS : plan_peak_transient(plan, lag, want);
     // tile slots + FFT scratch live in the context's persistent arena
-    const size_t arena_words = (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
+    const size_t arena_words = small_mode ? (size_t)N_WORDS * tile_words
+                                          : (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
     uint32_t* arena_p;
     const bool arena_ok = ctx->arena && ctx->arena_bytes >= arena_words * 4 && ctx->arena_bytes <= arena_words * 4 + ((size_t)8 << 30);
     bool p2p = false;
@@ -614,6 +628,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     Tiles tiles;
     tiles.init(n_cache, peak_trans, tile_words, arena_p, want);
     tiles.lag = lag;
+    if (small_mode)  // tile of word w = slot w, all live for the whole proof
+        for (int w = 0; w < N_WORDS; w++) tiles.slot_of[w] = tiles.cache_slot[w] = w;
     ctx->fft_words = 0;
     ctx->fft_words_half = 0;
     ctx->cached_tiles = n_cache;
@@ -621,7 +637,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // single-GPU mode evaluates the constraints on storage rows [0, N] only (see "half-domain evaluation" below): tiles
     // recomputed for the constraint pass need only their first half
-    const bool half_mode = G == 1 || p2p;
+    const bool half_mode = (G == 1 && !small_mode) || p2p;
     // peer-window mode, two streams: the transforms of group g+1 (whose last pass waits on NVLink) run on `stream2` while the
     // consumer of group g runs on `stream`.  Per group, on stream2: transform, wait consumed(g-1), barrier, record ready(g).
     const bool ov2 = p2p && ctx->stream2 != nullptr && !ctx->profile && getenv("S2C_P2P_1STREAM") == nullptr;
@@ -756,6 +772,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         uint32_t* ln = G > 1 ? local_nodes.p : tree1.nodes.p;  // unsharded: the local subtree IS the tree
         DBuf<uint32_t> hstate(ctx, 8 * Mr);
         uint64_t bytes_before = 0;
+        if (small_mode) {
+            ctx->stage_begin("fft_small");
+            CB_CUDA(launch_fft_packed_list(st, cdev.indep, N_INDEP_WORDS, W.p, N, arena_p, tile_words, n, ctx->tw));
+            CB_CUDA(launch_sum_tiles(st, arena_p, tile_words, M, cdev.combs, cdev.n_combs));
+            ctx->stage_end();
+            ctx->stage_begin("trace_merkle_leaves");
+            CB_CUDA(launch_merkle_leaves_seq(st, arena_p, tile_words, N_WORDS, m, ln));
+            ctx->stage_end();
+            ctx->launches += 3;
+            ctx->fft_words = N_INDEP_WORDS;
+        } else
         run_pass(1, [&](size_t gi, const Group& g) {
             LeafGroups lg{};
             lg.n = (int)g.hash.size();
@@ -872,7 +899,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     static const bool cons_v1 = getenv("S2C_CONS_V1") != nullptr;  // A/B switch: the integer (IMAD.WIDE) accumulation
     DBuf<uint32_t> apr_lo(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4), apr_hi(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4);
     DBuf<double> gtab(ctx, ctab.idx.size() * 8);
-    DBuf<int> d_cidx(ctx, ctab.idx.size());
+    if (!cons_v1 && !ctx->chacha_cidx) {  // consumption-order index list of the alpha table: static, uploaded once per context
+        CB_CUDA(cudaMalloc(&ctx->chacha_cidx, ctab.idx.size() * sizeof(int)));
+        CB_CUDA(cudaMemcpy(ctx->chacha_cidx, ctab.idx.data(), ctab.idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
     // the constraint sum at storage row N (half-domain evaluation below): one block over the AIR's constraint table
     DBuf<uint32_t> d_qrow(ctx, 8);
@@ -883,8 +913,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     if (cons_v1) {
         CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
     } else {
-        CB_CUDA(cudaMemcpyAsync(d_cidx.p, ctab.idx.data(), ctab.idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        CB_CUDA(launch_cons_table(st, apr.p, d_cidx.p, (int)ctab.idx.size(), gtab.p));
+        CB_CUDA(launch_cons_table(st, apr.p, (const int*)ctx->chacha_cidx, (int)ctab.idx.size(), gtab.p));
     }
     ctx->launches += 2;
     std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);  // 1 / Z_H on the two halves of the (bit-reversed) evaluation domain
@@ -903,6 +932,31 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // So only N + 1 of the 2N rows are evaluated; coefficients - and therefore the proof bytes - are unchanged.
     // (Row-sharded mode keeps the full-domain evaluation: the first-half rows live on half of the ranks only.)
     const size_t cons_rows = half_mode ? (G > 1 ? Mv : N) : 0;  // virtual shards: local rows [0, Mv) are first-half rows
+    if (small_mode) {
+        // the job list of the whole AIR (tile pointers into the arena), kept on the device while the arena does not move
+        int n_jobs = 0;
+        for (auto& g : plan) n_jobs += (int)g.cons.size();
+        if (ctx->small_jobs == nullptr || ctx->small_jobs_arena != (void*)arena_p || ctx->small_jobs_tile_words != tile_words) {
+            std::vector<ConstraintJob> jl;
+            for (size_t gi = 0; gi < plan.size(); gi++)
+                for (size_t k = 0; k < plan[gi].cons.size(); k++) {
+                    const CJ& c = plan[gi].cons[k];
+                    auto tp = [&](int w) -> uint32_t* { return w >= 0 ? arena_p + (size_t)w * tile_words : nullptr; };
+                    jl.push_back({tp(c.w0), tp(c.w1), tp(c.w2), tp(c.w3), tp(c.w4), tp(c.wres), ctab.job_off[gi][k], c.kb0, c.kb1, c.kb2,
+                                  c.kbc, c.arg, c.type});
+                }
+            if (!ctx->small_jobs) CB_CUDA(cudaMalloc(&ctx->small_jobs, jl.size() * sizeof(ConstraintJob)));
+            CB_CUDA(cudaMemcpyAsync(ctx->small_jobs, jl.data(), jl.size() * sizeof(ConstraintJob), cudaMemcpyHostToDevice, st));
+            ctx->sync();
+            ctx->small_jobs_arena = arena_p;
+            ctx->small_jobs_tile_words = tile_words;
+        }
+        DBuf<uint32_t> partial(ctx, (size_t)n_jobs * 4 * M);
+        ctx->stage_begin("constraints");
+        CB_CUDA(launch_constraints_jobs(st, (const ConstraintJob*)ctx->small_jobs, n_jobs, M, gtab.p, partial.p, accp, M));
+        ctx->stage_end();
+        ctx->launches += 2;
+    } else
     run_pass(2, [&](size_t gi, const Group& g) {
         ConstraintJobs cj{};
         for (auto& c : g.cons)
@@ -1022,8 +1076,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             if ((int)(i % G) == R) mine.push_back(indep_words[i]);
         indep_words.swap(mine);
     }
-    DBuf<int> d_indep(ctx, indep_words.size());
-    CB_CUDA(cudaMemcpyAsync(d_indep.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DBuf<int> d_indep_own(ctx, G > 1 ? indep_words.size() : 1);
+    if (G > 1) CB_CUDA(cudaMemcpyAsync(d_indep_own.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    struct { const int* p; } d_indep{G > 1 ? d_indep_own.p : cdev.indep};
     DBuf<uint32_t> d_sampled(ctx, ((size_t)N_COLS + 8) * 4), d_close(ctx, 4);
     {
         std::vector<QM31> maps(n);
@@ -1041,13 +1096,15 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)N_COLS + 8) * 4, st);
         CB_CUDA(launch_oods_fill_sums(st, d_sampled.p, cdev.combs, cdev.n_combs));  // the adder-sum words' samples, from their operands'
         ctx->launches += n + 7;
-        CB_CUDA(cudaMemcpyAsync(sampled.data(), d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
+        uint32_t* const pin = ctx->pinned_words(sampled.size() * 4);  // read-backs go through the context's pinned buffer
+        CB_CUDA(cudaMemcpyAsync(pin, d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         // prove()'s closing check (numerator): the AIR on the sampled mask, read back at the end
         if (lead) {
             CB_CUDA(launch_mask_constraints(st, cdev.table, N_CONSTRAINTS, d_sampled.p, 0, apr.p, d_close.p));
             ctx->launches++;
         }
         ctx->sync();
+        memcpy(sampled.data(), pin, sampled.size() * 16);
     }
     ctx->stage_end();
     ch.mix_felts(sampled.data(), sampled.size());
@@ -1204,8 +1261,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
             }
             if (G > 1) comm_allreduce_sum_u32(cm, d_q1.p, (size_t)N_COLS * 4, st);
             if (!lead) continue;
-            CB_CUDA(cudaMemcpyAsync(q4.data(), d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
+            uint32_t* const pin = ctx->pinned_words(q4.size());
+            CB_CUDA(cudaMemcpyAsync(pin, d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
             ctx->sync();
+            memcpy(q4.data(), pin, q4.size() * 4);
             for (auto& g : plan)
                 for (auto& cb : g.comb)
                     for (int c = 0; c < nqc; c++) {

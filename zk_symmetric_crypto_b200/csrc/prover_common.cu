@@ -55,6 +55,17 @@ void* cb_ctx::ensure_arena(size_t bytes) {
     arena_bytes = bytes;
     return arena;
 }
+uint32_t* cb_ctx::pinned_words(size_t words) {
+    if (pin_words < words) {
+        if (pin_buf) cudaFreeHost(pin_buf);
+        pin_buf = nullptr;
+        pin_words = 0;
+        CB_CUDA(cudaHostAlloc((void**)&pin_buf, words * 4, cudaHostAllocDefault));
+        pin_words = words;
+    }
+    return pin_buf;
+}
+
 void cb_ctx::close_peers() {
     for (size_t r = 0; r < peer_arena.size(); r++)
         if ((int)r != comm.rank && peer_arena[r]) cudaIpcCloseMemHandle(peer_arena[r]);
