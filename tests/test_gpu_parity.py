@@ -463,3 +463,22 @@ def test_pool_of_contexts_gives_identical_proofs(backend):
     finally:
         pool.close()
     assert out[0::2] == [want_c] * 4 and out[1::2] == [want_a] * 4
+
+
+@pytest.mark.skipif(not ref_wasm.available(), reason="oracle/_ref not on this box")
+@pytest.mark.parametrize("key_len,log_n", [(16, 18), (32, 18), (16, 19)])
+def test_reference_verifier_accepts_large_aes_proofs(backend, key_len, log_n):
+    """BASELINE configs[2] towards its stated sizes: the stored-LDE AES driver at log 18 (both key sizes) and log 19 (AES-128,
+    ~157 GB): the reference's own verifier accepts the proof and rejects it against a flipped ciphertext byte."""
+    import base64
+    import bench
+    import zk_symmetric_crypto_b200 as z
+    key, nonce, counter, pt, ct = bench.synth_aes_inputs(key_len, log_n, 0)
+    proof = backend.prove_aes_ctr_raw(key, nonce, counter, pt, ct)
+    b64 = base64.b64encode(proof).decode()
+    name = "aes128-ctr" if key_len == 16 else "aes256-ctr"
+    assert z.verify_aes_ctr_proof(b64, nonce, counter, pt, ct) == {"algorithm": name, "valid": True}
+    assert ref_wasm.verify_aes_ctr_proof(b64, nonce, counter, pt, ct) == {"algorithm": name, "valid": True}
+    bad = bytearray(ct)
+    bad[len(bad) // 2] ^= 1
+    assert ref_wasm.verify_aes_ctr_proof(b64, nonce, counter, pt, bytes(bad))["valid"] is False

@@ -9,7 +9,7 @@
 // powers of the quotient random coefficient) follows the CPU restatement of the test tree (aes_api.py, prover.py in the oracle directory), which reproduce the reference
 // binary byte for byte.  Output = bincode(AESCtrProof{stmt0, stmt1, stark_proof}) (air_ctr.rs:44-184).
 //
-// This driver stores the LDE of the trace (24,480 / 34,784 columns): it serves log_size <= 17 or so on one B200; the
+// This driver stores the LDE of the trace (24,480 / 34,784 columns): it serves log_size <= 19 (AES-128) / 18 (AES-256) on one B200; the
 // streaming (tile-by-tile) machinery of the ChaCha prover is not applied to the AES AIR yet.
 #include <array>
 #include <map>
@@ -183,6 +183,15 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         size_t free_b = 0, total_b = 0;
         CB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = ((size_t)C * 3 + NI * 3 + 2 * NL + 64) * N * 4 + ((size_t)1 << 30);
+        if (need > free_b) {  // give back what earlier proofs left cached in the stream-ordered pool (and the ChaCha tile arena)
+            ctx->sync();
+            ctx->close_peers();
+            ctx->release_arena();
+            cudaMemPool_t pool;
+            CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+            CB_CUDA(cudaMemPoolTrimTo(pool, 0));
+            CB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        }
         if (need > free_b + ctx->arena_bytes)
             throw CbError("AES-CTR proof at log_size " + std::to_string(n) + " needs " + std::to_string(need >> 30) +
                           " GiB for the stored LDE; the streaming path is not built for the AES AIR yet");
