@@ -29,8 +29,13 @@ int cb_init(int device, cb_ctx** out) {
     try {
         ctx->device = device;
         CB_CUDA(cudaSetDevice(device));
-        CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        // the consumer stream outranks the producer stream: when both have blocks waiting (row-sharded mode: the last transform
+        // pass of group g+1 is throttled by NVLink while the leaf hashing of group g wants the SMs), the consumer goes first
+        int prio_lo = 0, prio_hi = 0;
+        CB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+        CB_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo));
+        CB_CUDA(cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_lo));
         // measured on B200 at log 18/20: no gain (both kernels fill the GPU; the block scheduler runs them back to back), so
         // the second stream is opt-in
         ctx->overlap = getenv("S2C_OVERLAP") && atoi(getenv("S2C_OVERLAP"));
@@ -65,6 +70,7 @@ void cb_destroy(cb_ctx* ctx) {
     try { comm_destroy(ctx->comm); } catch (...) {}
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -176,6 +176,10 @@ struct PeerDst {
     uint32_t* base[MAX_PEERS];
     int logG, lv;
     const unsigned long long* off;  // host array, one entry per job
+    // optional: launch the last pass on its own stream (it is throttled by NVLink; the passes of the next group then start
+    // on the caller's stream meanwhile).  ab_done is recorded behind the second pass and awaited by last_stream.
+    cudaStream_t last_stream;
+    cudaEvent_t ab_done;
 };
 cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* src, uint32_t* const* out, int njobs, int log_n,
                               const FftTables& tw, uint32_t* scratch, const StageHook* hook, int* launches, int shard_log = 0,

@@ -31,6 +31,7 @@ struct cb_ctx {
     bool own_stream = true;
     // producer stream of the streaming provers: LDE tiles of group g+1 are transformed here while `stream` consumes group g
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream3 = nullptr;  // row-sharded mode: the last transform pass (peer stores) and the group barrier
     std::vector<cudaEvent_t> ev_pool;  // timing-disabled events for the producer/consumer hand-off
     cudaEvent_t event(size_t i);
     bool overlap = true;

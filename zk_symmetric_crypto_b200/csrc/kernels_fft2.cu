@@ -750,7 +750,15 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
             HOOK("fft_mid", 0);
             dim3 gC(((unsigned)jobs.halves << log_n) / T2, jobs.n * gpj2);
             HOOK("fft_low", 1);
-            if (jobs.peer_on) fft_low12_kernel<NC, true><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
+            cudaStream_t stC = st;
+            if (peer && peer->last_stream) {
+                cudaEventRecord(peer->ab_done, st);
+                cudaStreamWaitEvent(peer->last_stream, peer->ab_done, 0);
+                stC = peer->last_stream;
+            }
+            // (a persistent form of this pass with 1-2 resident blocks per SM, meant to leave room for the next group's passes
+            // while the stores wait on NVLink, measured slower at 4 GPUs: 225 / 201 ms vs 189 ms)
+            if (jobs.peer_on) fft_low12_kernel<NC, true><<<gC, 256, NC * COLW * 4, stC>>>(jobs, log_n, gpj2, tw);
             else fft_low12_kernel<NC, false><<<gC, 256, NC * COLW * 4, st>>>(jobs, log_n, gpj2, tw);
             HOOK("fft_low", 0);
             nl += 3;
@@ -783,7 +791,13 @@ cudaError_t launch_fft_packed(cudaStream_t st, int kind, const uint32_t* const* 
         HOOK("fft_mid", 0);
         dim3 gC((2u << log_n) / T, jobs.n * gpj);
         HOOK("fft_low", 1);
-        fft_low_kernel<<<gC, 256, smem_ac, st>>>(jobs, log_n, k1, nc, gpj, tw);
+        cudaStream_t stC = st;
+        if (peer && peer->last_stream) {
+            cudaEventRecord(peer->ab_done, st);
+            cudaStreamWaitEvent(peer->last_stream, peer->ab_done, 0);
+            stC = peer->last_stream;
+        }
+        fft_low_kernel<<<gC, 256, smem_ac, stC>>>(jobs, log_n, k1, nc, gpj, tw);
         HOOK("fft_low", 0);
         nl += 3;
     }

@@ -555,7 +555,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // sharded mode: whole transformed tiles ([G][32][Mr]) wait here for the all-to-all; at most ceil(16/G) jobs per rank and group
     const int n_stage = G > 1 ? (16 + G - 1) / G : 0;
     const size_t scratch_words = fft_packed_scratch_words(SRC_BITS, G > 1 ? n_stage : MAX_FFT_JOBS, n);
-    const size_t stage_words = (size_t)n_stage * 32 * M;
+    // (two sets in peer-window mode: the first two passes of group g+1 fill one while the last pass of group g drains the other)
+    const size_t stage_words = (size_t)n_stage * 32 * M * (want_p2p ? 2 : 1);
     // Product-size traces (log_size <= 10): the whole LDE (1,040 tiles, <= 272 MB) is materialised, so each pass is a handful
     // of launches over all words instead of 85 plan groups - at these sizes a proof is bound by launch count and by the dependent
     // chains inside the per-row kernels, not by arithmetic (profiles/r02: log 4, 417 launches, 12 ms).
@@ -638,16 +639,21 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // single-GPU mode evaluates the constraints on storage rows [0, N] only (see "half-domain evaluation" below): tiles
     // recomputed for the constraint pass need only their first half
     const bool half_mode = (G == 1 && !small_mode) || p2p;
-    // peer-window mode, two streams: the transforms of group g+1 (whose last pass waits on NVLink) run on `stream2` while the
-    // consumer of group g runs on `stream`.  Per group, on stream2: transform, wait consumed(g-1), barrier, record ready(g).
-    const bool ov2 = p2p && ctx->stream2 != nullptr && !ctx->profile && getenv("S2C_P2P_1STREAM") == nullptr;
+    // peer-window mode, three streams: passes A/B of the transforms on `stream2`, the last pass (throttled by NVLink) and the
+    // group barrier on `stream3`, the consumers on `stream` - so that the compute of group g+1 and the hashing of group g-1 fill
+    // the SMs while the stores of group g cross the links.  Per group g: stream2: wait stage set free, passes A/B, record;
+    // stream3: wait A/B, last pass -> peers, record set free, wait consumed(g-1), barrier, record ready(g); stream: wait ready(g).
+    const bool ov2 = p2p && ctx->stream2 != nullptr && ctx->stream3 != nullptr && !ctx->profile && getenv("S2C_P2P_1STREAM") == nullptr;
     auto run_pass = [&](int pass, auto&& consume) {
         const size_t NG = plan.size();
         tiles.flush();
-        cudaStream_t sp = ov2 ? ctx->stream2 : st;
-        if (ov2) {  // the producer stream starts after everything enqueued so far
+        cudaStream_t sp = ov2 ? ctx->stream2 : st;   // passes A/B
+        cudaStream_t sc = ov2 ? ctx->stream3 : st;   // last pass + barrier
+        int fft_seq = 0;                             // groups with local transform jobs so far (stage set = fft_seq & 1)
+        if (ov2) {  // the producer streams start after everything enqueued so far
             CB_CUDA(cudaEventRecord(ctx->event(2 * NG), st));
             CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG), 0));
+            CB_CUDA(cudaStreamWaitEvent(sc, ctx->event(2 * NG), 0));
         }
         for (size_t gi = 0; gi < NG; gi++) {
             const Group& g = plan[gi];
@@ -665,11 +671,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 for (size_t j = 0; j < jobs_w.size(); j++)
                     if ((int)(j % G) == R) {
                         src.push_back(W.p + (size_t)jobs_w[j] * N);
-                        out.push_back(stage_p + (size_t)(k++) * 32 * M);
+                        out.push_back(stage_p + ((size_t)(fft_seq & 1) * n_stage + (k++)) * 32 * M);
                         offs.push_back((unsigned long long)(tiles.ptr(jobs_w[j]) - arena_p));
                     }
                 if (!src.empty()) {
                     PeerDst pd{};
+                    const int set = fft_seq & 1;
+                    if (ov2) {
+                        pd.last_stream = sc;
+                        pd.ab_done = ctx->event(2 * NG + 1 + set);
+                        if (fft_seq >= 2) CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG + 3 + set), 0));  // the set's last reader
+                    }
                     for (int r = 0; r < G; r++) pd.base[r] = ctx->peer_arena[r];
                     pd.logG = logG;
                     pd.lv = lv;
@@ -680,14 +692,16 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     ctx->launches += nl;
                     ctx->fft_words += src.size();
                     if (pass == 2) ctx->fft_words_half += src.size();
+                    if (ov2) CB_CUDA(cudaEventRecord(ctx->event(2 * NG + 3 + set), sc));
+                    fft_seq++;
                 }
                 if (pass == 1 || n_cache < N_INDEP_WORDS) {
                     ctx->stage_begin("group_barrier");
-                    if (ov2 && gi >= 1) CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(NG + gi - 1), 0));
-                    comm_barrier(ctx->comm, sp);
+                    if (ov2 && gi >= 1) CB_CUDA(cudaStreamWaitEvent(sc, ctx->event(NG + gi - 1), 0));
+                    comm_barrier(ctx->comm, sc);
                     ctx->stage_end();
                     if (ov2) {
-                        CB_CUDA(cudaEventRecord(ctx->event(gi), sp));
+                        CB_CUDA(cudaEventRecord(ctx->event(gi), sc));
                         CB_CUDA(cudaStreamWaitEvent(st, ctx->event(gi), 0));
                     }
                 }
@@ -755,7 +769,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         }
         for (int w = 0; w < N_WORDS; w++) tiles.release(w);
         if (overlap) CB_CUDA(cudaStreamWaitEvent(sf, ctx->event(2 * NG - 1), 0));  // next pass's producer starts after this pass
-        if (ov2) CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG - 1), 0));
+        if (ov2) {
+            CB_CUDA(cudaStreamWaitEvent(sp, ctx->event(2 * NG - 1), 0));
+            CB_CUDA(cudaStreamWaitEvent(sc, ctx->event(2 * NG - 1), 0));
+        }
     };
 
     // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree.  Sharded mode: every rank builds
