@@ -618,8 +618,10 @@ def main():
         nk = ncu.get({"fft": "fft_passes", "trace_merkle_leaves": "leaves_kernel", "constraints": "constraints_tiles_kernel"}[top])
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak if achieved else None,
-                    "traffic": nk.get("dram_bytes_per_proof") if nk else None,
-                    "traffic_source": (nk.get("source") if nk else None), "peak_source": peak_src,
+                    "traffic": nk["traffic_over_algorithmic"] * alg[top] if nk else None,
+                    "traffic_source": ("DRAM bytes / algorithmic bytes of one captured launch (%s; %s: %.3f) x the algorithmic bytes of "
+                                       "this run" % (nk.get("launch"), nk.get("source"), nk["traffic_over_algorithmic"])) if nk else None,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_proof": alg[top], "kernel_ms_per_proof": kern_ms[top],
                     "int": int_roof.get(top),
                     "note": "the dominant kernels are integer-pipe bound (Blake2s: ALU pipe; M31 butterflies: ALU + FMA pipes), so the "

@@ -275,6 +275,13 @@ int s2c_prove_aes256_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len
                                  size_t ciphertext_len, char** json_out, size_t* json_len);
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len);
+/* Block-AIR variant of the ChaCha20 circuit (reference: stwo/src/chacha/bitwise/air.rs:53-171 prove_bitwise / verify_bitwise,
+   constraints.rs, gen.rs; `bench_bitwise` air.rs:201): 32,256 columns, 53,248 constraints, statement = log_size; the trace is the
+   reference generator's (key 00..1f, nonce 00 00 00 09 00 00 00 4a 00 00 00 00, counter = row).  Proof bytes = u32 log_size ||
+   bincode(StarkProof); free with s2c_free.  s2c_verify_chacha20_block returns 0 when the proof verifies, else 1 with the
+   reference's VerificationError rendering in *err_out (free with s2c_free). */
+int s2c_prove_chacha20_block(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len);
+int s2c_verify_chacha20_block(const uint8_t* proof, size_t proof_len, char** err_out, size_t* err_len);
 int s2c_get_circuits_info(char** json_out, size_t* json_len);
 void s2c_free(void* p);
 

@@ -73,15 +73,41 @@ def prove_stream_internal(log_size, key, nonce, counters, pt, ct, pub, config=No
     return stmt + proof
 
 
-def composition_oods_check(log_size, oods, sampled, random_coeff):
+def prove_bitwise(log_size, config=None):
+    """chacha/bitwise/air.rs:53-137 prove_bitwise: empty preprocessed tree, trace from the fixed generator, statement =
+    mix_u64(log_size), one component.  Returns u32 log_size || bincode(StarkProof) (the reference does not serialise
+    BitwiseProof; the layout follows StreamProof's)."""
+    config = config or PcsConfig()
+    channel = Blake2sChannel()
+    scheme = CommitmentSchemeProver(config)
+    scheme.commit_polys([], channel)
+    key_words = [0x03020100 + 0x04040404 * i for i in range(8)]
+    trace = ca.generate_block_trace(log_size, key_words, [0x09000000, 0x4a000000, 0])
+    channel.mix_u64(log_size)
+    tree1 = scheme.commit_evals(trace, channel)
+    random_coeff = channel.draw_secure_felt()
+    eval_log = log_size + 1
+    apr = secure_powers(random_coeff, ca.N_CONSTRAINTS_BLOCK)[::-1].copy()
+    acc = ca.evaluate_constraints(np.stack(tree1.evals, axis=0), apr, block=True)
+    from stwo_core import m_inv, q_mul_m31
+    acc = q_mul_m31(acc, m_inv(coset_vanishing_on_domain(log_size, eval_log)))
+    scheme.commit_polys(finalize_composition(acc, eval_log), channel)
+    oods = get_random_point(channel)
+    proof, info = prove_values(scheme, [[], [[oods]] * ca.N_COLS_BLOCK, [[oods]] * 8], channel, eval_log)
+    if not composition_oods_check(log_size, oods, info["sampled"], random_coeff, block=True):
+        raise ProofError("Proof generation failed: ConstraintsNotSatisfied")
+    return struct.pack("<I", log_size) + proof
+
+
+def composition_oods_check(log_size, oods, sampled, random_coeff, block=False):
     """Verifier-side identity (core/air/components.rs eval_composition_polynomial_at_point +
     core/verifier.rs): left(z) + pi^{n-1}(z.x) * right(z) == sum_k alpha^(K-1-k) C_k(mask(z)) / Z_H(z)."""
     from stwo_core import Coset, index_to_point
     from prover import secure_powers
     px, py = oods
     mask = np.array([[cv[0].v] for cv in sampled[1]], dtype=U64)          # [C,1,4]
-    apr = secure_powers(random_coeff, ca.N_CONSTRAINTS)[::-1].copy()
-    num = ca.evaluate_constraints(mask, apr)[0]
+    apr = secure_powers(random_coeff, ca.N_CONSTRAINTS_BLOCK if block else ca.N_CONSTRAINTS)[::-1].copy()
+    num = ca.evaluate_constraints(mask, apr, block)[0]
     num = QM31(*[int(v) for v in num])
     # coset_vanishing(CanonicCoset(n).coset, z)
     coset = Coset.odds(log_size)

@@ -139,7 +139,22 @@ class _Acc:
         self.k += m
 
 
-def evaluate_constraints(lde, alpha_pows_rev):
+N_COLS_BLOCK = 32256          # block AIR (chacha/bitwise/{gen,constraints,air}.rs): no plaintext / ciphertext columns
+N_CONSTRAINTS_BLOCK = 53248   # ... and no plaintext / ciphertext booleans, no xor equalities
+
+
+def generate_block_trace(log_size, key_words, nonce_words):
+    """chacha/bitwise/gen.rs generate_trace on prove_bitwise's inputs (air.rs:66-90): initial state = build_state(key, 0, nonce)
+    with word 12 = the row index.  The columns are the first 32,256 columns of the stream trace."""
+    n = 1 << log_size
+    key = np.tile(np.asarray(key_words, dtype=U64), (n, 1))
+    nonce = np.tile(np.asarray(nonce_words, dtype=U64), (n, 1))
+    zeros = np.zeros((n, 16), dtype=U64)
+    trace, _ = generate_stream_trace(log_size, key, nonce, np.arange(n, dtype=U64), zeros, zeros)
+    return trace[:N_COLS_BLOCK]
+
+
+def evaluate_constraints(lde, alpha_pows_rev, block=False):
     """lde: [N_COLS, R] uint64 M31 column values on the evaluation domain (any row order), or [N_COLS, R, 4]
     QM31 values (the verifier / prove()'s sanity check evaluate the same constraints on the OODS mask values).
     Returns acc[R,4] = sum_k alpha_pows_rev[k] * C_k(row), before multiplication by the vanishing inverse."""
@@ -197,6 +212,9 @@ def evaluate_constraints(lde, alpha_pows_rev):
             v[a] = add_u32(v[a], v[b]); v[d] = xor_rotl_u32(v[a], v[d], 8)
             v[c] = add_u32(v[c], v[d]); v[b] = xor_rotl_u32(v[c], v[b], 7)
     ks = [add_u32(v[i], init[i]) for i in range(16)]
+    if block:   # ChaChabitwiseEvalAtRow::eval (bitwise/constraints.rs:31-58) ends with the final additions
+        assert col[0] == N_COLS_BLOCK and A.k == N_CONSTRAINTS_BLOCK
+        return A.acc
     pt = [next_u32() for _ in range(16)]
     ct = [next_u32() for _ in range(16)]
     for i in range(16):

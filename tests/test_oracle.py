@@ -225,3 +225,18 @@ def test_adder_sum_words_follow_from_their_operands():
             if i > 0:
                 want = want + c[i - 1]
             assert s[i].v == want.v
+
+
+def test_block_air_oracle_proof_and_host_verifier():
+    """ChaCha20 block AIR (bitwise/air.rs prove_bitwise / verify_bitwise): the restatement's proof matches its fixture, the C++ host
+    verifier (an independent implementation of the same AIR as a constraint table) accepts it and rejects mutations."""
+    import zk_symmetric_crypto_b200 as z
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chacha20_block_golden.json")))["cases"][0]
+    proof = oracle_api.prove_bitwise(gold["log_size"])
+    assert len(proof) == gold["proof_bytes"] and hashlib.sha256(proof).hexdigest() == gold["sha256"]
+    assert z.verify_chacha20_block(proof) == ""
+    for pos, want in ((0, None), (300, None), (len(proof) // 2, None), (len(proof) - 40, None)):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert z.verify_chacha20_block(bytes(bad)) != ""
+    assert z.verify_chacha20_block(proof[:-1]).startswith("Invalid proof format")

@@ -62,9 +62,11 @@ void cb_destroy(cb_ctx* ctx) {
     if (ctx->tw_shift_dev) cudaFree(ctx->tw_shift_dev);
     ctx->close_peers();
     ctx->release_arena();
-    if (ctx->chacha_consts) cudaFree(ctx->chacha_consts);
+    for (int v = 0; v < 2; v++) {
+        if (ctx->chacha_consts[v]) cudaFree(ctx->chacha_consts[v]);
+        if (ctx->chacha_cidx[v]) cudaFree(ctx->chacha_cidx[v]);
+    }
     if (ctx->small_jobs) cudaFree(ctx->small_jobs);
-    if (ctx->chacha_cidx) cudaFree(ctx->chacha_cidx);
     if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
     if (ctx->hash_stage) cudaFreeHost(ctx->hash_stage);
     try { comm_destroy(ctx->comm); } catch (...) {}
@@ -749,6 +751,43 @@ int s2c_prove_chacha20_stream_testdata(cb_ctx* ctx, int log_size, uint8_t** proo
     if (!e.empty()) throw CbError(e);
     give_proof(proof, proof_out, proof_len);
     CB_CATCH(ctx)
+}
+
+// The reference's block-AIR entry points (chacha/bitwise/air.rs: prove_bitwise / verify_bitwise; reached only from its own tests
+// and `bench_bitwise`, not from the product API): the trace is generated from log_size alone - key bytes 00..1f, nonce
+// 00 00 00 09 00 00 00 4a 00 00 00 00, block counter = row index.  Proof bytes = u32 log_size || bincode(StarkProof) (the
+// reference does not serialise BitwiseProof; the layout follows its other proof containers).
+int s2c_prove_chacha20_block(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len) {
+    CtxUse use(ctx);
+    ctx = use.ctx;
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (log_size < 4 || log_size > 24) throw CbError("log_size must be in [4, 24]");
+    uint32_t kw[8];
+    for (int i = 0; i < 8; i++) kw[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
+    const uint32_t nw[3] = {0x09000000u, 0x4a000000u, 0};
+    uint8_t key[32], nonce[12];
+    memcpy(key, kw, 32);
+    memcpy(nonce, nw, 12);
+    ProveOptions opt;
+    opt.block_air = true;
+    std::vector<uint8_t> proof;
+    std::string e = prove_chacha20(ctx, key, nonce, 0, nullptr, nullptr, (size_t)64 << log_size, proof, opt);
+    if (!e.empty()) throw CbError(e);
+    give_proof(proof, proof_out, proof_len);
+    CB_CATCH(ctx)
+}
+// 0: verifies; 1: does not (err_out = the reference's rendering of its VerificationError, or "Invalid proof format: ..")
+int s2c_verify_chacha20_block(const uint8_t* proof, size_t proof_len, char** err_out, size_t* err_len) {
+    std::string e;
+    try {
+        e = verify_chacha20_block(proof, proof_len);
+    } catch (const std::exception& ex) {
+        e = std::string("Invalid proof format: ") + ex.what();
+    }
+    if (err_out) ret_json(e, err_out, err_len);
+    return e.empty() ? 0 : 1;
 }
 
 int s2c_get_circuits_info(char** json_out, size_t* json_len) {

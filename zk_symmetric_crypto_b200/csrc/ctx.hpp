@@ -76,11 +76,12 @@ struct cb_ctx {
     void* small_jobs = nullptr;         // product-size ChaCha proofs: constraint job list of the whole AIR (device), valid for
     void* small_jobs_arena = nullptr;   // this arena base and tile pitch
     size_t small_jobs_tile_words = 0;
-    void* chacha_cidx = nullptr;        // ChaCha alpha-table index list (consumption order)
+    int small_jobs_variant = -1;
+    void* chacha_cidx[2] = {nullptr, nullptr};  // ChaCha alpha-table index list (consumption order), per AIR variant
     uint32_t* pin_buf = nullptr;        // pinned host staging for read-backs (pinned_words)
     size_t pin_words = 0;
     uint32_t* pinned_words(size_t words);
-    void* chacha_consts = nullptr;      // ChaCha AIR constraint table + adder-sum list (prove_chacha.cu chacha_dev)
+    void* chacha_consts[2] = {nullptr, nullptr};  // ChaCha AIR constraint table + adder-sum list, per AIR variant (chacha_dev)
     void* ensure_arena(size_t bytes);
     void release_arena();
     void ensure_twiddles(int max_log);

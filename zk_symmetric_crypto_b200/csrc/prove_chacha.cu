@@ -18,10 +18,15 @@ using host::Hash32;
 
 namespace {
 
-constexpr int N_COLS = 33280;
-constexpr int N_WORDS = 1040;
-constexpr int N_CONSTRAINTS = 54784;
-constexpr int N_INDEP_WORDS = 704;  // words transformed from the packed witness (all but the 336 adder sum words)
+constexpr int N_WORDS = 1040;  // packed witness words of the stream AIR (the block AIR uses the first 1,008)
+// The two AIRs served here.  [0] stream AIR (chacha/bitwise/{gen_stream,constraints_stream,air_stream}.rs): state, 80 quarter
+// rounds, final additions, plaintext, ciphertext, keystream xor plaintext = ciphertext.  [1] block AIR
+// (chacha/bitwise/{gen,constraints,air}.rs, `prove_bitwise`): the same trace without the last 1,024 columns and the same
+// constraints without the plaintext / ciphertext booleans and the 512 xor equalities - a prefix of [0] in both orders.
+struct AirDims {
+    int words, cols, cons, indep;  // packed words, columns, constraints, words transformed (the rest are adder sums)
+};
+constexpr AirDims DIMS[2] = {{1040, 33280, 54784, 704}, {1008, 32256, 53248, 672}};
 
 // ---- host evaluation of the AIR on QM31 mask values (prove()'s closing sanity check; same sequence as the kernel) ----
 struct QAcc {
@@ -31,7 +36,7 @@ struct QAcc {
     void add(QM31 c) { acc = qadd(acc, qmul(c, apr[k++])); }
 };
 
-QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31>& apr) {
+QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31>& apr, bool block) {
     QAcc A{apr};
     int col = 0;
     const QM31 one = qone();
@@ -77,6 +82,7 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
         }
     std::array<U32, 16> ks, pt, ct;
     for (int i = 0; i < 16; i++) ks[i] = add_u32(s[i], init[i]);
+    if (block) return A.acc;
     for (int i = 0; i < 16; i++) pt[i] = next_u32();
     for (int i = 0; i < 16; i++) ct[i] = next_u32();
     for (int i = 0; i < 16; i++)
@@ -90,9 +96,10 @@ QM31 eval_constraints_at_mask(const std::vector<QM31>& v, const std::vector<QM31
 // The same traversal recorded as a table: one ConsRec per constraint, in constraint order (ConsRec: common.cuh).  The table
 // is what both the device kernel (mask_constraints_kernel: prove()'s closing check and the row-N evaluation of the
 // half-domain composition) and the host verifier evaluate; the walk above stays as the generator's cross-check.
-std::vector<ConsRec> build_cons_recs() {
+std::vector<ConsRec> build_cons_recs(bool block) {
+    const AirDims D = DIMS[block ? 1 : 0];
     std::vector<ConsRec> T;
-    T.reserve(N_CONSTRAINTS);
+    T.reserve(D.cons);
     int col = 0;
     using U32 = std::array<int, 32>;
     auto next_u32 = [&]() {
@@ -133,43 +140,47 @@ std::vector<ConsRec> build_cons_recs() {
         }
     std::array<U32, 16> ks, pt, ct;
     for (int i = 0; i < 16; i++) ks[i] = add_u32(st[i], init[i]);
-    for (int i = 0; i < 16; i++) pt[i] = next_u32();
-    for (int i = 0; i < 16; i++) ct[i] = next_u32();
-    for (int i = 0; i < 16; i++)
-        for (int b = 0; b < 32; b++) T.push_back({CR_EQ, ks[i][b], pt[i][b], ct[i][b], -1, -1});
-    if ((int)T.size() != N_CONSTRAINTS || col != N_COLS) throw CbError("internal: constraint table size");
+    if (!block) {
+        for (int i = 0; i < 16; i++) pt[i] = next_u32();
+        for (int i = 0; i < 16; i++) ct[i] = next_u32();
+        for (int i = 0; i < 16; i++)
+            for (int b = 0; b < 32; b++) T.push_back({CR_EQ, ks[i][b], pt[i][b], ct[i][b], -1, -1});
+    }
+    if ((int)T.size() != D.cons || col != D.cols) throw CbError("internal: constraint table size");
     return T;
 }
 
-const std::vector<ConsRec>& cons_recs() {
-    static const std::vector<ConsRec> T = [] {
-        std::vector<ConsRec> t = build_cons_recs();
+const std::vector<ConsRec>& cons_recs(bool block) {
+    auto make = [](bool blk) {
+        const AirDims D = DIMS[blk ? 1 : 0];
+        std::vector<ConsRec> t = build_cons_recs(blk);
         // one-time cross-check against the walk on a pseudo-random mask
-        std::vector<QM31> mask(N_COLS), apr(N_CONSTRAINTS);
+        std::vector<QM31> mask(D.cols), apr(D.cons);
         uint64_t x = 0x9e3779b97f4a7c15ull;
         auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (uint32_t)(x % P); };
         for (auto& m : mask) m = {{rnd(), rnd(), rnd(), rnd()}};
         for (auto& a : apr) a = {{rnd(), rnd(), rnd(), rnd()}};
         QM31 acc = qzero();
-        for (int k = 0; k < N_CONSTRAINTS; k++) acc = qadd(acc, qmul(cons_rec_eval(t[k], mask.data()), apr[k]));
-        if (!qeq(acc, eval_constraints_at_mask(mask, apr))) throw CbError("internal: constraint table differs from the AIR walk");
+        for (int k = 0; k < D.cons; k++) acc = qadd(acc, qmul(cons_rec_eval(t[k], mask.data()), apr[k]));
+        if (!qeq(acc, eval_constraints_at_mask(mask, apr, blk))) throw CbError("internal: constraint table differs from the AIR walk");
         return t;
-    }();
-    return T;
+    };
+    static const std::vector<ConsRec> T0 = make(false), T1 = make(true);
+    return block ? T1 : T0;
 }
 
-QM31 eval_cons_table(const std::vector<QM31>& mask, const std::vector<QM31>& apr) {
-    const std::vector<ConsRec>& T = cons_recs();
+QM31 eval_cons_table(const std::vector<QM31>& mask, const std::vector<QM31>& apr, bool block) {
+    const std::vector<ConsRec>& T = cons_recs(block);
     QM31 acc = qzero();
-    for (int k = 0; k < N_CONSTRAINTS; k++) acc = qadd(acc, qmul(cons_rec_eval(T[k], mask.data()), apr[k]));
+    for (size_t k = 0; k < T.size(); k++) acc = qadd(acc, qmul(cons_rec_eval(T[k], mask.data()), apr[k]));
     return acc;
 }
 
 }  // namespace
 
 // shared with the host verifier (verify.cu)
-QM31 chacha_constraints_at_mask(const std::vector<QM31>& mask, const std::vector<QM31>& alpha_powers_rev) {
-    return eval_cons_table(mask, alpha_powers_rev);
+QM31 chacha_constraints_at_mask(const std::vector<QM31>& mask, const std::vector<QM31>& alpha_powers_rev, bool block_air) {
+    return eval_cons_table(mask, alpha_powers_rev, block_air);
 }
 
 // ------------------------------------------------------------------------------------------------ streaming plan
@@ -188,7 +199,7 @@ struct Group {
     std::vector<int> free_after;  // tiles dead after this group
 };
 
-std::vector<Group> build_plan() {
+std::vector<Group> build_plan(bool block) {
     std::vector<Group> plan;
     int state[16];
     {
@@ -243,9 +254,11 @@ std::vector<Group> build_plan() {
             if (state[i] >= 16) g.free_after.push_back(state[i]);
             g.free_after.push_back(C);
             g.free_after.push_back(i);  // initial-state tile i is no longer needed
+            if (block) g.free_after.push_back(S);  // block AIR: the keystream word has no later consumer
         }
         plan.push_back(g);
     }
+    if (block) return plan;
     {
         Group g;
         for (int i = 0; i < 16; i++) {
@@ -413,23 +426,24 @@ struct ChaChaDev {
     int n_combs;
     const int* indep;  // the N_INDEP_WORDS transformed words, plan order
 };
-ChaChaDev chacha_dev(cb_ctx* ctx, const std::vector<Group>& plan) {
+ChaChaDev chacha_dev(cb_ctx* ctx, const std::vector<Group>& plan, bool block) {
+    void*& consts = ctx->chacha_consts[block ? 1 : 0];
+    const AirDims D = DIMS[block ? 1 : 0];
     std::vector<SumComb> cl;
     for (auto& g : plan)
         for (auto& c : g.comb) cl.push_back({c.res, c.a, c.b, c.c});
-    const size_t tb = (size_t)N_CONSTRAINTS * sizeof(ConsRec), cb = cl.size() * sizeof(SumComb);
-    if (!ctx->chacha_consts) {
-        const std::vector<ConsRec>& T = cons_recs();
+    const size_t tb = (size_t)D.cons * sizeof(ConsRec), cb = cl.size() * sizeof(SumComb);
+    if (!consts) {
+        const std::vector<ConsRec>& T = cons_recs(block);
         std::vector<int> iw;
         for (auto& g : plan)
             for (int w : g.fft) iw.push_back(w);
-        CB_CUDA(cudaMalloc(&ctx->chacha_consts, tb + cb + iw.size() * sizeof(int)));
-        CB_CUDA(cudaMemcpy(ctx->chacha_consts, T.data(), tb, cudaMemcpyHostToDevice));
-        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb, cl.data(), cb, cudaMemcpyHostToDevice));
-        CB_CUDA(cudaMemcpy((char*)ctx->chacha_consts + tb + cb, iw.data(), iw.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMalloc(&consts, tb + cb + iw.size() * sizeof(int)));
+        CB_CUDA(cudaMemcpy(consts, T.data(), tb, cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMemcpy((char*)consts + tb, cl.data(), cb, cudaMemcpyHostToDevice));
+        CB_CUDA(cudaMemcpy((char*)consts + tb + cb, iw.data(), iw.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
-    return {(const ConsRec*)ctx->chacha_consts, (const SumComb*)((char*)ctx->chacha_consts + tb), (int)cl.size(),
-            (const int*)((char*)ctx->chacha_consts + tb + cb)};
+    return {(const ConsRec*)consts, (const SumComb*)((char*)consts + tb), (int)cl.size(), (const int*)((char*)consts + tb + cb)};
 }
 }  // namespace
 
@@ -438,9 +452,14 @@ ChaChaDev chacha_dev(cb_ctx* ctx, const std::vector<Group>& plan) {
 std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof, ProveOptions opt) {
     const PcsConfig cfg;
+    const bool block_air = opt.block_air;
+    const int variant = block_air ? 1 : 0;
+    const AirDims D = DIMS[variant];
     const uint32_t num_blocks = (uint32_t)(len / 64);
     int log_size = 4;
     while (((size_t)1 << log_size) < num_blocks) log_size++;
+    if (block_air && (len != ((size_t)64 << log_size) || plaintext || ciphertext || opt.pt_dev))
+        return "block AIR: the trace is generated from log_size alone";
     if (log_size > 24) return "log_size (" + std::to_string(log_size) + ") must be <= MAX_LOG_SIZE (24)";
     const int n = log_size, m = n + cfg.log_blowup;  // trace / LDE domain logs
     const size_t N = (size_t)1 << n, M = (size_t)1 << m;
@@ -451,6 +470,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     const int G = cm.world, R = cm.rank;
     int logG = 0;
     while ((1 << logG) < G) logG++;
+    if (G > 1 && block_air) return "sharded proving serves the stream AIR only";
     if (G > 1 && n < 16) return "sharded proving needs log_size >= 16 (got " + std::to_string(n) + ")";
     const int lr = m - logG;             // log2 of the rows per shard
     const size_t Mr = M >> logG;
@@ -477,7 +497,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     std::string hash_err;
     // (sharded mode: only rank 0 hashes and broadcasts the two digests - G processes x 2 hashing threads would fight for the
     // host cores, and at 8 ranks the commitment pass is no longer than one 64 MiB hash)
-    if (!opt.pt_hash && !opt.empty_public_hashes && cm.rank == 0) {
+    if (!opt.pt_hash && !opt.empty_public_hashes && cm.rank == 0 && !block_air) {
         if (opt.pt_dev) {
             // inputs resident in HBM and no hashes supplied: read both buffers back into the context's pinned staging area
             // (2 x len bytes of D2H at PCIe speed, a few ms) and hash them on host threads like host-resident inputs
@@ -514,7 +534,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     DBuf<uint32_t> d_pt, d_ct, W(ctx, (size_t)N_WORDS * N);
     DBuf<int> d_invalid(ctx, 1);
     const uint32_t *pt_d = opt.pt_dev, *ct_d = opt.ct_dev;
-    if (!pt_d) {
+    if (block_air) {  // no plaintext / ciphertext columns: the witness kernel's last 32 words are written (zeros) and never read
+        d_pt = DBuf<uint32_t>(ctx, len / 4);
+        CB_CUDA(cudaMemsetAsync(d_pt.p, 0, len, st));
+        pt_d = ct_d = d_pt.p;
+    } else if (!pt_d) {
         d_pt = DBuf<uint32_t>(ctx, len / 4);
         d_ct = DBuf<uint32_t>(ctx, len / 4);
         CB_CUDA(cudaMemcpyAsync(d_pt.p, plaintext, len, cudaMemcpyHostToDevice, st));
@@ -529,13 +553,14 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     int invalid = 0;
     CB_CUDA(cudaMemcpyAsync(&invalid, d_invalid.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ctx->sync();
-    if (invalid) return "Ciphertext does not match encryption - invalid witness";
+    if (invalid && !block_air) return "Ciphertext does not match encryption - invalid witness";
     d_pt.release();
     d_ct.release();
 
     // ---- tile arena: as many independent tiles as fit stay cached between the two LDE passes
-    static const std::vector<Group> plan = build_plan();
-    const ChaChaDev cdev = chacha_dev(ctx, plan);
+    static const std::vector<Group> plans[2] = {build_plan(false), build_plan(true)};
+    const std::vector<Group>& plan = plans[variant];
+    const ChaChaDev cdev = chacha_dev(ctx, plan, block_air);
     // tiles are transformed on a second stream one group ahead of their consumer (not while per-kernel profiling is on)
     const bool overlap = ctx->overlap && !ctx->profile && ctx->stream2 != nullptr && G == 1;
     // Row-sharded mode over peer windows (G > 1, CUDA IPC available): LDE rows are dealt to the ranks in 2G "virtual shards" of
@@ -545,7 +570,9 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // remote ranks from group g+2 on (they passed the barrier of group g+1, which this rank entered after consuming group g).
     const bool want_p2p = G > 1 && ctx->p2p_state >= 0 && getenv("S2C_NO_P2P") == nullptr;
     const int lag = (overlap || want_p2p) ? 2 : 0;
-    static const int peak_trans_none = plan_peak_transient(plan, 2, std::vector<char>(N_WORDS, 0));  // nothing cached
+    static const int peak_none[2] = {plan_peak_transient(plans[0], 2, std::vector<char>(N_WORDS, 0)),
+                                     plan_peak_transient(plans[1], 2, std::vector<char>(N_WORDS, 0))};  // nothing cached
+    const int peak_trans_none = peak_none[variant];
     cudaStream_t sf = overlap ? ctx->stream2 : st;
     // placement knobs (KiB) for measuring how the power-of-two strides of the transform passes interact with the DRAM
     // address map: extra pitch between tile slots, offset of the FFT scratch behind the slots
@@ -561,7 +588,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // of launches over all words instead of 85 plan groups - at these sizes a proof is bound by launch count and by the dependent
     // chains inside the per-row kernels, not by arithmetic (profiles/r02: log 4, 417 launches, 12 ms).
     const bool small_mode = G == 1 && n <= 10 && getenv("S2C_NO_SMALL") == nullptr;
-    int n_cache = N_INDEP_WORDS;
+    int n_cache = D.indep;
     if (!small_mode) {
         size_t free_b = 0, total_b = 0;
         CB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -588,8 +615,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         // the largest cache whose tiles plus the transient slots the plan then needs fit
         // (n_cache + peak(n_cache) never decreases with n_cache: binary search; the answer is remembered per thread)
         static thread_local size_t memo_can = 0;
-        static thread_local int memo_in = -1, memo_lag = -1, memo_out = 0;
-        if (memo_can == can && memo_in == n_cache && memo_lag == lag) {
+        static thread_local int memo_in = -1, memo_lag = -1, memo_out = 0, memo_variant = -1;
+        if (memo_can == can && memo_in == n_cache && memo_lag == lag && memo_variant == variant) {
             n_cache = memo_out;
         } else {
             auto fits = [&](int c) { return (size_t)(c + plan_peak_transient(plan, lag, cache_choice(plan, c))) <= can; };
@@ -598,13 +625,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 const int mid = (lo + hi + 1) / 2;
                 if (fits(mid)) lo = mid; else hi = mid - 1;
             }
-            memo_can = can; memo_in = n_cache; memo_lag = lag; memo_out = lo;
+            memo_can = can; memo_in = n_cache; memo_lag = lag; memo_out = lo; memo_variant = variant;
             n_cache = lo;
         }
         n_cache = comm_min_int(cm, n_cache, st);  // every rank must take the same caching decisions
     }
     const std::vector<char> want = small_mode ? std::vector<char>(N_WORDS, 1) : cache_choice(plan, n_cache);
-    const int peak_trans = small_mode ? N_WORDS - N_INDEP_WORDS : plan_peak_transient(plan, lag, want);
+    const int peak_trans = small_mode ? D.words - D.indep : plan_peak_transient(plan, lag, want);
     // tile slots + FFT scratch live in the context's persistent arena
     const size_t arena_words = small_mode ? (size_t)N_WORDS * tile_words
                                           : (size_t)(n_cache + peak_trans) * tile_words + scratch_off_words + scratch_words + stage_words;
@@ -695,7 +722,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     if (ov2) CB_CUDA(cudaEventRecord(ctx->event(2 * NG + 3 + set), sc));
                     fft_seq++;
                 }
-                if (pass == 1 || n_cache < N_INDEP_WORDS) {
+                if (pass == 1 || n_cache < D.indep) {
                     ctx->stage_begin("group_barrier");
                     if (ov2 && gi >= 1) CB_CUDA(cudaStreamWaitEvent(sc, ctx->event(NG + gi - 1), 0));
                     comm_barrier(ctx->comm, sc);
@@ -777,7 +804,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- tree 1 (pass 1): LDE tiles in column order -> Blake2s leaf states -> Merkle tree.  Sharded mode: every rank builds
     //      the subtree over its Mr leaves; rank 0 collects the layers, adds the top log2(G) layers and broadcasts the root.
-    DBuf<uint32_t> d_rowN(ctx, half_mode ? (size_t)N_COLS : 1);
+    DBuf<uint32_t> d_rowN(ctx, half_mode ? (size_t)D.cols : 1);
     DevMerkle tree1;
     tree1.log_leaves = m;
     if (R == 0) tree1.nodes = DBuf<uint32_t>(ctx, (((size_t)2 << m) - 1) * 8);
@@ -791,14 +818,14 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         uint64_t bytes_before = 0;
         if (small_mode) {
             ctx->stage_begin("fft_small");
-            CB_CUDA(launch_fft_packed_list(st, cdev.indep, N_INDEP_WORDS, W.p, N, arena_p, tile_words, n, ctx->tw));
+            CB_CUDA(launch_fft_packed_list(st, cdev.indep, D.indep, W.p, N, arena_p, tile_words, n, ctx->tw));
             CB_CUDA(launch_sum_tiles(st, arena_p, tile_words, M, cdev.combs, cdev.n_combs));
             ctx->stage_end();
             ctx->stage_begin("trace_merkle_leaves");
-            CB_CUDA(launch_merkle_leaves_seq(st, arena_p, tile_words, N_WORDS, m, ln));
+            CB_CUDA(launch_merkle_leaves_seq(st, arena_p, tile_words, D.words, m, ln));
             ctx->stage_end();
             ctx->launches += 3;
-            ctx->fft_words = N_INDEP_WORDS;
+            ctx->fft_words = D.indep;
         } else
         run_pass(1, [&](size_t gi, const Group& g) {
             LeafGroups lg{};
@@ -868,6 +895,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- statement (the two public-input hashes were computed on host threads while the GPU ran pass 1)
     std::vector<uint8_t> stmt;
     host::put_u32(stmt, (uint32_t)log_size);
+    if (!block_air) {
     host::put_bytes(stmt, opt.stmt_nonce ? opt.stmt_nonce : nonce, 12);
     host::put_u32(stmt, counter);
     {
@@ -897,10 +925,13 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     }
     host::put_bytes(stmt, pth.b, 32);
     host::put_bytes(stmt, cth.b, 32);
-    ch.mix_u64((uint64_t)log_size);
-    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[4 + 4 * i]));
-    ch.mix_u64(counter);
-    for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
+    }
+    ch.mix_u64((uint64_t)log_size);  // BitwiseStatement::mix_into (bitwise/air.rs:45-47) stops here
+    if (!block_air) {
+        for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[4 + 4 * i]));
+        ch.mix_u64(counter);
+        for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[20 + 4 * i]));
+    }
 
     ctx->sync();
     roots.push_back(tree1.root);
@@ -908,29 +939,30 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
 
     // ---- composition polynomial (pass 2): constraint quotients accumulated tile by tile
     QM31 random_coeff = ch.draw_secure_felt();
-    DBuf<uint32_t> apr(ctx, (size_t)N_CONSTRAINTS * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, R == 0 ? 4 * M : 4);
+    DBuf<uint32_t> apr(ctx, (size_t)D.cons * 4), d_den(ctx, (size_t)1 << cfg.log_blowup), acc(ctx, R == 0 ? 4 * M : 4);
     DBuf<uint32_t> acc_local;
     if (G > 1) acc_local = DBuf<uint32_t>(ctx, 4 * Mr);
     uint32_t* accp = G > 1 ? acc_local.p : acc.p;  // this rank's rows of the 4 accumulator columns
-    static const ConsTable ctab = build_cons_table(plan);
+    static const ConsTable ctabs[2] = {build_cons_table(plans[0]), build_cons_table(plans[1])};
+    const ConsTable& ctab = ctabs[variant];
     static const bool cons_v1 = getenv("S2C_CONS_V1") != nullptr;  // A/B switch: the integer (IMAD.WIDE) accumulation
-    DBuf<uint32_t> apr_lo(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4), apr_hi(ctx, cons_v1 ? (size_t)N_CONSTRAINTS * 4 : 4);
+    DBuf<uint32_t> apr_lo(ctx, cons_v1 ? (size_t)D.cons * 4 : 4), apr_hi(ctx, cons_v1 ? (size_t)D.cons * 4 : 4);
     DBuf<double> gtab(ctx, ctab.idx.size() * 8);
-    if (!cons_v1 && !ctx->chacha_cidx) {  // consumption-order index list of the alpha table: static, uploaded once per context
-        CB_CUDA(cudaMalloc(&ctx->chacha_cidx, ctab.idx.size() * sizeof(int)));
-        CB_CUDA(cudaMemcpy(ctx->chacha_cidx, ctab.idx.data(), ctab.idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!cons_v1 && !ctx->chacha_cidx[variant]) {  // consumption-order index list of the alpha table: static, uploaded once per context
+        CB_CUDA(cudaMalloc(&ctx->chacha_cidx[variant], ctab.idx.size() * sizeof(int)));
+        CB_CUDA(cudaMemcpy(ctx->chacha_cidx[variant], ctab.idx.data(), ctab.idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
-    CB_CUDA(launch_secure_powers_rev(st, random_coeff, N_CONSTRAINTS, apr.p));
+    CB_CUDA(launch_secure_powers_rev(st, random_coeff, D.cons, apr.p));
     // the constraint sum at storage row N (half-domain evaluation below): one block over the AIR's constraint table
     DBuf<uint32_t> d_qrow(ctx, 8);
     if (half_mode && R == 0) {
-        CB_CUDA(launch_mask_constraints(st, cdev.table, N_CONSTRAINTS, d_rowN.p, 1, apr.p, d_qrow.p));
+        CB_CUDA(launch_mask_constraints(st, cdev.table, D.cons, d_rowN.p, 1, apr.p, d_qrow.p));
         ctx->launches++;
     }
     if (cons_v1) {
-        CB_CUDA(launch_split16(st, apr.p, N_CONSTRAINTS, apr_lo.p, apr_hi.p));
+        CB_CUDA(launch_split16(st, apr.p, D.cons, apr_lo.p, apr_hi.p));
     } else {
-        CB_CUDA(launch_cons_table(st, apr.p, (const int*)ctx->chacha_cidx, (int)ctab.idx.size(), gtab.p));
+        CB_CUDA(launch_cons_table(st, apr.p, (const int*)ctx->chacha_cidx[variant], (int)ctab.idx.size(), gtab.p));
     }
     ctx->launches += 2;
     std::vector<uint32_t> den((size_t)1 << cfg.log_blowup);  // 1 / Z_H on the two halves of the (bit-reversed) evaluation domain
@@ -953,7 +985,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         // the job list of the whole AIR (tile pointers into the arena), kept on the device while the arena does not move
         int n_jobs = 0;
         for (auto& g : plan) n_jobs += (int)g.cons.size();
-        if (ctx->small_jobs == nullptr || ctx->small_jobs_arena != (void*)arena_p || ctx->small_jobs_tile_words != tile_words) {
+        if (ctx->small_jobs == nullptr || ctx->small_jobs_arena != (void*)arena_p || ctx->small_jobs_tile_words != tile_words ||
+            ctx->small_jobs_variant != variant) {
             std::vector<ConstraintJob> jl;
             for (size_t gi = 0; gi < plan.size(); gi++)
                 for (size_t k = 0; k < plan[gi].cons.size(); k++) {
@@ -962,9 +995,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                     jl.push_back({tp(c.w0), tp(c.w1), tp(c.w2), tp(c.w3), tp(c.w4), tp(c.wres), ctab.job_off[gi][k], c.kb0, c.kb1, c.kb2,
                                   c.kbc, c.arg, c.type});
                 }
-            if (!ctx->small_jobs) CB_CUDA(cudaMalloc(&ctx->small_jobs, jl.size() * sizeof(ConstraintJob)));
+            if (!ctx->small_jobs) CB_CUDA(cudaMalloc(&ctx->small_jobs, 512 * sizeof(ConstraintJob)));
             CB_CUDA(cudaMemcpyAsync(ctx->small_jobs, jl.data(), jl.size() * sizeof(ConstraintJob), cudaMemcpyHostToDevice, st));
             ctx->sync();
+            ctx->small_jobs_variant = variant;
             ctx->small_jobs_arena = arena_p;
             ctx->small_jobs_tile_words = tile_words;
         }
@@ -1078,7 +1112,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- OODS sampling: f_j(z) = 2^-n <bits_j, (FFT with inverse twiddles)(basis(z))>  (kernels_stream.cu fact 2)
     host::CirclePointQ z = host::get_random_point(ch);
     ctx->stage_begin("oods");
-    std::vector<QM31> sampled((size_t)N_COLS + 8);
+    std::vector<QM31> sampled((size_t)D.cols + 8);
     const FftTables tw_t{ctx->tw.IX, ctx->tw.IY, ctx->tw.X, ctx->tw.Y, ctx->tw.max_log};  // transposed inverse transform
     DBuf<uint32_t> basis(ctx, 4 * N), wt(ctx, 4 * N);
     // the 336 adder-sum words are skipped in every pass over the packed witness: s_i = a_i + b_i + c_(i-1) - 2 c_i is an
@@ -1096,7 +1130,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     DBuf<int> d_indep_own(ctx, G > 1 ? indep_words.size() : 1);
     if (G > 1) CB_CUDA(cudaMemcpyAsync(d_indep_own.p, indep_words.data(), indep_words.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     struct { const int* p; } d_indep{G > 1 ? d_indep_own.p : cdev.indep};
-    DBuf<uint32_t> d_sampled(ctx, ((size_t)N_COLS + 8) * 4), d_close(ctx, 4);
+    DBuf<uint32_t> d_sampled(ctx, ((size_t)D.cols + 8) * 4), d_close(ctx, 4);
     {
         std::vector<QM31> maps(n);
         maps[0] = z.y;
@@ -1105,19 +1139,19 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         CB_CUDA(launch_basis(st, basis.p, N, n, maps.data()));
         ColSrc bs{SRC_M31, basis.p, N, 0};
         CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
-        if (G > 1) CB_CUDA(cudaMemsetAsync(d_sampled.p, 0, ((size_t)N_COLS + 8) * 16, st));
+        if (G > 1) CB_CUDA(cudaMemsetAsync(d_sampled.p, 0, ((size_t)D.cols + 8) * 16, st));
         CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)indep_words.size(), wt.p, inv_n, d_sampled.p, d_indep.p));
         if (lead)
             for (int half = 0; half < 2; half++)
-                CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)N_COLS + 4 * half) * 4));
-        if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)N_COLS + 8) * 4, st);
+                CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)D.cols + 4 * half) * 4));
+        if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)D.cols + 8) * 4, st);
         CB_CUDA(launch_oods_fill_sums(st, d_sampled.p, cdev.combs, cdev.n_combs));  // the adder-sum words' samples, from their operands'
         ctx->launches += n + 7;
         uint32_t* const pin = ctx->pinned_words(sampled.size() * 4);  // read-backs go through the context's pinned buffer
         CB_CUDA(cudaMemcpyAsync(pin, d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         // prove()'s closing check (numerator): the AIR on the sampled mask, read back at the end
         if (lead) {
-            CB_CUDA(launch_mask_constraints(st, cdev.table, N_CONSTRAINTS, d_sampled.p, 0, apr.p, d_close.p));
+            CB_CUDA(launch_mask_constraints(st, cdev.table, D.cons, d_sampled.p, 0, apr.p, d_close.p));
             ctx->launches++;
         }
         ctx->sync();
@@ -1141,7 +1175,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         DBuf<uint32_t> g(ctx, 4 * N), g_lde(ctx, lead ? 4 * M : 4), d_bc(ctx, 12 * 4);
         const uint32_t ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
         CB_CUDA(cudaMemcpyAsync(d_bc.p, ident, sizeof ident, cudaMemcpyHostToDevice, st));
-        CB_CUDA(cudaMemcpyAsync(d_bc.p + 16, d_call.p + (size_t)N_COLS * 4, 8 * 16, cudaMemcpyDeviceToDevice, st));  // composition columns
+        CB_CUDA(cudaMemcpyAsync(d_bc.p + 16, d_call.p + (size_t)D.cols * 4, 8 * 16, cudaMemcpyDeviceToDevice, st));  // composition columns
         CB_CUDA(launch_quot_fold_sums(st, d_call.p, cdev.combs, cdev.n_combs));
         uint32_t* const d_coefs_p = d_call.p;
         ctx->launches += 3;
@@ -1227,7 +1261,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         else if (p2p) { const uint32_t v = q >> lv; owner = (int)(v & (uint32_t)(G - 1)); local = ((v >> logG) << lv) | (q & (uint32_t)(Mv - 1)); }
         else { owner = (int)(q >> lr); local = q & (uint32_t)(Mr - 1); }
     };
-    std::vector<uint32_t> qv1((size_t)N_COLS * nq), qv2((size_t)8 * nq);
+    std::vector<uint32_t> qv1((size_t)D.cols * nq), qv2((size_t)8 * nq);
     {
         std::vector<int> slot(N_WORDS, -1);
         std::vector<char> indep(N_WORDS, 0);
@@ -1242,11 +1276,11 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         DBuf<int> d_slot(ctx, N_WORDS), d_need(ctx, need.size() + 1);
         CB_CUDA(cudaMemcpyAsync(d_slot.p, slot.data(), N_WORDS * sizeof(int), cudaMemcpyHostToDevice, st));
         CB_CUDA(cudaMemcpyAsync(d_need.p, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        DBuf<uint32_t> d_rows(ctx, nq), d_q2(ctx, qv2.size()), d_q1(ctx, (size_t)N_COLS * 4);
-        std::vector<uint32_t> q4((size_t)N_COLS * 4);
+        DBuf<uint32_t> d_rows(ctx, nq), d_q2(ctx, qv2.size()), d_q1(ctx, (size_t)D.cols * 4);
+        std::vector<uint32_t> q4((size_t)D.cols * 4);
         for (int q0 = 0; q0 < nq; q0 += 4) {
             const int nqc = nq - q0 < 4 ? nq - q0 : 4;
-            if (G > 1) CB_CUDA(cudaMemsetAsync(d_q1.p, 0, (size_t)N_COLS * 16, st));
+            if (G > 1) CB_CUDA(cudaMemsetAsync(d_q1.p, 0, (size_t)D.cols * 16, st));
             if (!need.empty() && lead) {
                 uint32_t init[4] = {0, 0, 0, 0};
                 std::vector<std::array<uint32_t, 4>> maps(n);
@@ -1265,7 +1299,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)need.size(), wt.p, inv_n, d_q1.p, d_need.p));
                 ctx->launches += n + 3;
             }
-            if (need.size() < (size_t)N_INDEP_WORDS) {
+            if (need.size() < (size_t)D.indep) {
                 uint32_t rows4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // 0xffffffff: row held by another rank
                 for (int c = 0; c < nqc; c++) {
                     int owner;
@@ -1276,7 +1310,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 CB_CUDA(launch_gather_cached(st, tiles.arena, tiles.tile_words, Mr, d_slot.p, N_WORDS, rows4, nqc, d_q1.p));
                 ctx->launches++;
             }
-            if (G > 1) comm_allreduce_sum_u32(cm, d_q1.p, (size_t)N_COLS * 4, st);
+            if (G > 1) comm_allreduce_sum_u32(cm, d_q1.p, (size_t)D.cols * 4, st);
             if (!lead) continue;
             uint32_t* const pin = ctx->pinned_words(q4.size());
             CB_CUDA(cudaMemcpyAsync(pin, d_q1.p, q4.size() * 4, cudaMemcpyDeviceToHost, st));
@@ -1293,7 +1327,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                             cin = cv;
                         }
                     }
-            for (int j = 0; j < N_COLS; j++)
+            for (int j = 0; j < D.cols; j++)
                 for (int c = 0; c < nqc; c++) qv1[(size_t)j * nq + q0 + c] = q4[(size_t)j * 4 + c];
         }
         if (!lead) {
@@ -1321,8 +1355,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         const QM31 units[4] = {{{1, 0, 0, 0}}, {{0, 1, 0, 0}}, {{0, 0, 1, 0}}, {{0, 0, 0, 1}}};
         QM31 left = qzero(), right = qzero();
         for (int k = 0; k < 4; k++) {
-            left = qadd(left, qmul(sampled[N_COLS + k], units[k]));
-            right = qadd(right, qmul(sampled[N_COLS + 4 + k], units[k]));
+            left = qadd(left, qmul(sampled[D.cols + k], units[k]));
+            right = qadd(right, qmul(sampled[D.cols + 4 + k], units[k]));
         }
         QM31 pix = z.x;
         for (int i = 0; i < n - 1; i++) pix = qsub(qmul_m(qmul(pix, pix), 2), qone());
@@ -1332,17 +1366,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     // ---- serialise: StreamProof{stmt, StarkProof(CommitmentSchemeProof{config, commitments, sampled_values, decommitments,
     //                 queried_values, proof_of_work, fri_proof})}
     proof.clear();
-    proof.reserve(stmt.size() + 64 + sampled.size() * 24 + (size_t)N_COLS * (8 + 4 * nq) + 4096);
+    proof.reserve(stmt.size() + 64 + sampled.size() * 24 + (size_t)D.cols * (8 + 4 * nq) + 4096);
     host::put_bytes(proof, stmt.data(), stmt.size());
     cfg.serialize(proof);
     host::put_u64(proof, roots.size());
     for (auto& r : roots) host::put_bytes(proof, r.b, 32);
     host::put_u64(proof, 3);
     host::put_u64(proof, 0);
-    host::put_u64(proof, N_COLS);
-    for (int j = 0; j < N_COLS; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[j]); }
+    host::put_u64(proof, D.cols);
+    for (int j = 0; j < D.cols; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[j]); }
     host::put_u64(proof, 8);
-    for (int j = 0; j < 8; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[N_COLS + j]); }
+    for (int j = 0; j < 8; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[D.cols + j]); }
     host::put_u64(proof, 3);
     host::put_u64(proof, 0);
     host::put_u64(proof, dec1.size());
@@ -1351,8 +1385,8 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     for (auto& h : dec2) host::put_bytes(proof, h.b, 32);
     host::put_u64(proof, 3);
     host::put_u64(proof, 0);
-    host::put_u64(proof, N_COLS);
-    for (int j = 0; j < N_COLS; j++) { host::put_u64(proof, nq); host::put_bytes(proof, &qv1[(size_t)j * nq], 4 * nq); }
+    host::put_u64(proof, D.cols);
+    for (int j = 0; j < D.cols; j++) { host::put_u64(proof, nq); host::put_bytes(proof, &qv1[(size_t)j * nq], 4 * nq); }
     host::put_u64(proof, 8);
     for (int j = 0; j < 8; j++) { host::put_u64(proof, nq); host::put_bytes(proof, &qv2[(size_t)j * nq], 4 * nq); }
     host::put_u64(proof, pow_nonce);

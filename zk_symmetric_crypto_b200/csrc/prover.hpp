@@ -32,6 +32,9 @@ struct ProveOptions {
     const uint8_t* pt_hash = nullptr;
     const uint8_t* ct_hash = nullptr;
     int max_cached_tiles = -1;         // cap on LDE tiles kept between the commitment and constraint passes (-1 = memory bound)
+    // block AIR (chacha/bitwise/{gen,constraints,air}.rs): the 32,256-column prefix of the stream AIR (no plaintext / ciphertext),
+    // statement = log_size only; the trace comes from key / nonce / counter + row alone (plaintext = ciphertext = nullptr)
+    bool block_air = false;
 };
 
 struct FriProverState {
@@ -65,7 +68,8 @@ std::vector<uint8_t> aes_expand_key(const uint8_t* key, int key_len);  // aes/mo
 const uint8_t* aes_sbox();                                             // aes/mod.rs:10-30
 
 // ChaCha20 stream AIR on QM31 mask values; alpha_powers_rev[k] = alpha^(K-1-k)
-m31::QM31 chacha_constraints_at_mask(const std::vector<m31::QM31>& mask, const std::vector<m31::QM31>& alpha_powers_rev);
+m31::QM31 chacha_constraints_at_mask(const std::vector<m31::QM31>& mask, const std::vector<m31::QM31>& alpha_powers_rev,
+                                     bool block_air = false);
 
 // ---- host verifier (verify.cu): air_stream.rs:343-421, air_ctr.rs:619-714 followed by upstream stwo::core::verifier::verify.
 // Both return "" when the proof verifies and otherwise the reference's `{:?}` rendering of its VerificationError.
@@ -75,6 +79,8 @@ struct VerifyFormatError : std::runtime_error {
 };
 std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                             size_t pt_len, const uint8_t* ciphertext, size_t ct_len);
+// verify_bitwise (chacha/bitwise/air.rs:139-171): proof = u32 log_size || bincode(StarkProof)
+std::string verify_chacha20_block(const uint8_t* proof, size_t len);
 // *key_size_out: 0 = AES-128, 1 = AES-256 (read from the proof's statement before any check)
 std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out);

@@ -603,6 +603,34 @@ std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonc
     });
 }
 
+// verify_bitwise (chacha/bitwise/air.rs:139-171): statement = log_size, 32,256 trace columns, the block AIR's 53,248 constraints
+std::string verify_chacha20_block(const uint8_t* proof, size_t len) {
+    constexpr int N_COLS = 32256, N_CONSTRAINTS = 53248;
+    Reader r{proof, len};
+    const uint32_t log_size = r.u32();
+    const StarkProofData sp = read_stark(r);
+    std::string e = validate_pcs_config(sp.cfg);
+    if (!e.empty()) return e;
+    if (sp.commitments.size() < 2) return "OodsNotMatching";
+    if (log_size < 1 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
+    Channel ch;
+    ch.mix_root(sp.commitments[0]);
+    ch.mix_u64(log_size);
+    ch.mix_root(sp.commitments[1]);
+    AirSpec air;
+    air.log_size = (int)log_size;
+    air.trees.resize(2);
+    air.trees[1].assign(N_COLS, ColumnSpec{(int)log_size, 1});
+    return verify_stark(air, ch, sp, [&](const PtQ& z, const std::vector<std::vector<std::vector<QM31>>>& sampled, const QM31& rc) {
+        std::vector<QM31> apr(N_CONSTRAINTS);
+        QM31 cur = qone();
+        for (int k = 0; k < N_CONSTRAINTS; k++) { apr[N_CONSTRAINTS - 1 - k] = cur; cur = qmul(cur, rc); }
+        std::vector<QM31> mask(N_COLS);
+        for (int j = 0; j < N_COLS; j++) mask[j] = sampled[1][j][0];
+        return qmul(chacha_constraints_at_mask(mask, apr, true), qinv(vanishing_at((int)log_size, z)));
+    });
+}
+
 // ================================================================================================ AES-CTR
 std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out) {
