@@ -140,6 +140,7 @@ struct DevMerkle {
 cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int lifting_log, uint32_t* h_state, uint64_t bytes_before,
                                  int is_first, int is_final, uint32_t* out);
 cudaError_t launch_merkle_nodes(cudaStream_t st, const uint32_t* prev, uint32_t n_parents, uint32_t* out);
+cudaError_t launch_merkle_tree_small(cudaStream_t st, uint32_t* nodes, int log_leaves);
 cudaError_t launch_chacha_witness(cudaStream_t st, const uint32_t key[8], const uint32_t nonce[3], uint32_t counter,
                                   uint32_t num_blocks, uint32_t n_active_rows, const uint32_t* pt, const uint32_t* ct, int log_size,
                                   uint32_t* W, size_t stride, int* invalid);

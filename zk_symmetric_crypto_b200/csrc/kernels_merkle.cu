@@ -261,7 +261,35 @@ __global__ void __launch_bounds__(256) nodes_kernel(const uint4* __restrict__ pr
     out[2 * (size_t)i + 1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// all upper layers of a small tree in one launch: nodes = all layers concatenated, layer 0 (2^L hashes) already filled
+__global__ void __launch_bounds__(256) nodes_all_kernel(uint32_t* nodes, int L) {
+    size_t off = 0;
+    for (int l = 0; l < L; l++) {
+        const uint32_t n_parents = 1u << (L - l - 1);
+        const uint4* __restrict__ prev = (const uint4*)(nodes + off * 8);
+        uint4* __restrict__ out = (uint4*)(nodes + (off + ((size_t)1 << (L - l))) * 8);
+        for (uint32_t i = threadIdx.x; i < n_parents; i += blockDim.x) {
+            uint4 a = prev[4 * (size_t)i], b = prev[4 * (size_t)i + 1], c = prev[4 * (size_t)i + 2], d = prev[4 * (size_t)i + 3];
+            uint32_t m[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+            uint32_t h[8];
+            blake2s::init(h);
+            blake2s::compress(h, m, 64, true);
+            out[2 * (size_t)i] = make_uint4(h[0], h[1], h[2], h[3]);
+            out[2 * (size_t)i + 1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+        __syncthreads();
+        off += (size_t)1 << (L - l);
+    }
+}
+
 }  // namespace merk
+
+// upper layers of a tree with 2^log_leaves <= 2^11 leaves in one launch (product-size proofs)
+cudaError_t launch_merkle_tree_small(cudaStream_t st, uint32_t* nodes, int log_leaves) {
+    if (log_leaves <= 0) return cudaSuccess;
+    merk::nodes_all_kernel<<<1, 256, 0, st>>>(nodes, log_leaves);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int lifting_log, uint32_t* h_state,
                                  uint64_t bytes_before, int is_first, int is_final, uint32_t* out) {

@@ -28,6 +28,23 @@ __global__ void basis_step_kernel(uint32_t* b, size_t n_stride, uint32_t half, Q
     for (int c = 0; c < 4; c++) b[c * n_stride + half + k] = r.v[c];
 }
 
+// the same table for n <= 2^10 entries in one launch (product-size proofs: launch count matters more than parallelism)
+struct BasisMaps { QM31 f[10]; };
+__global__ void __launch_bounds__(512) basis_all_kernel(uint32_t* b, size_t n_stride, int log_n, BasisMaps maps) {
+    if (threadIdx.x == 0) { b[0] = 1; b[n_stride] = 0; b[2 * n_stride] = 0; b[3 * n_stride] = 0; }
+    __syncthreads();
+    for (int j = 0; j < log_n; j++) {
+        const uint32_t half = 1u << j;
+        for (uint32_t k = threadIdx.x; k < half; k += blockDim.x) {
+            QM31 v{{b[k], b[n_stride + k], b[2 * n_stride + k], b[3 * n_stride + k]}};
+            QM31 r = qmul(v, maps.f[j]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) b[c * n_stride + half + k] = r.v[c];
+        }
+        __syncthreads();
+    }
+}
+
 // out[col] = sum_k coeffs[col][k] * basis[k]   (M31 x QM31 dot product).  One block per (column, slice): with only a handful
 // of columns (the 4 + 4 composition coefficient columns) one block per column left 144 SMs idle (2.2 ms per launch at n = 20).
 __global__ void __launch_bounds__(256) oods_dot_kernel(const uint32_t* __restrict__ coeffs, size_t stride, uint32_t n,
@@ -209,6 +226,12 @@ __global__ void secure_powers_rev_kernel(QM31 alpha, QM31 alpha_chunk /* alpha^2
 using m31::QM31;
 
 cudaError_t launch_basis(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const QM31* maps /*host, log_n entries*/) {
+    if (log_n <= 10) {
+        pcs::BasisMaps bm{};
+        for (int j = 0; j < log_n; j++) bm.f[j] = maps[j];
+        pcs::basis_all_kernel<<<1, 512, 0, st>>>(basis, stride, log_n, bm);
+        return cudaGetLastError();
+    }
     // basis[0] = 1
     uint32_t one[4] = {1, 0, 0, 0};
     for (int c = 0; c < 4; c++) cudaMemcpyAsync(basis + c * stride, &one[c], 4, cudaMemcpyHostToDevice, st);

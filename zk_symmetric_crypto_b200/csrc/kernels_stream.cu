@@ -883,8 +883,33 @@ cudaError_t launch_rowcomb_m31(cudaStream_t st, const uint32_t* vals, size_t str
 }
 
 // basis[c][k] = init[c] * prod over set bits j of k of maps[j][c]   (4 independent base-field coordinates)
+namespace strm {
+struct Basis4Maps { uint4 f[10]; };
+__global__ void __launch_bounds__(512) basis4_all_kernel(uint32_t* b, size_t stride, int log_n, uint4 init, Basis4Maps maps) {
+    if (threadIdx.x == 0) { b[0] = init.x; b[stride] = init.y; b[2 * stride] = init.z; b[3 * stride] = init.w; }
+    __syncthreads();
+    for (int j = 0; j < log_n; j++) {
+        const uint32_t half = 1u << j;
+        const uint4 f = maps.f[j];
+        for (uint32_t k = threadIdx.x; k < half; k += blockDim.x) {
+            b[half + k] = mulm(b[k], f.x);
+            b[stride + half + k] = mulm(b[stride + k], f.y);
+            b[2 * stride + half + k] = mulm(b[2 * stride + k], f.z);
+            b[3 * stride + half + k] = mulm(b[3 * stride + k], f.w);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace strm
+
 cudaError_t launch_basis4(cudaStream_t st, uint32_t* basis, size_t stride, int log_n, const uint32_t init[4],
                           const uint32_t (*maps)[4]) {
+    if (log_n <= 10) {  // product-size proofs: one launch
+        strm::Basis4Maps bm{};
+        for (int j = 0; j < log_n; j++) bm.f[j] = make_uint4(maps[j][0], maps[j][1], maps[j][2], maps[j][3]);
+        strm::basis4_all_kernel<<<1, 512, 0, st>>>(basis, stride, log_n, make_uint4(init[0], init[1], init[2], init[3]), bm);
+        return cudaGetLastError();
+    }
     for (int c = 0; c < 4; c++) cudaMemcpyAsync(basis + c * stride, &init[c], 4, cudaMemcpyHostToDevice, st);
     for (int j = 0; j < log_n; j++) {
         uint32_t half = 1u << j;

@@ -449,7 +449,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         DBuf<uint32_t> basis(ctx, 4 * nn), d_out(ctx, (size_t)ncols * 4);
         CB_CUDA(launch_basis(st, basis.p, nn, lg, maps.data()));
         CB_CUDA(launch_oods_dot(st, coeffs, stride, ncols, lg, basis.p, nn, d_out.p));
-        ctx->launches += lg + 1;
+        ctx->launches += (lg <= 10 ? 1 : lg) + 1;
         CB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)ncols * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
     };
@@ -467,7 +467,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         ColSrc bs{SRC_M31, basis.p, nn, 0};
         CB_CUDA(launch_fft(st, bs, 4, lg, 0, 4, nullptr, 0, wt.p, nn, tw_t, nullptr, 0));
         CB_CUDA(launch_oods_dot(st, vals, stride, ncols, lg, wt.p, nn, d_out.p));
-        ctx->launches += lg + 3;
+        ctx->launches += (lg <= 10 ? 1 : lg) + 3;
         CB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)ncols * 16, cudaMemcpyDeviceToHost, st));
         ctx->sync();
         const uint32_t inv_n = 1u << (31 - lg);

@@ -850,6 +850,10 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
         ctx->stage_begin("merkle_nodes");
         // local subtrees: one over Mr leaves, or (virtual shards) two over Mv leaves each, whose roots are the two nodes of layer lv
         const int local_top = p2p ? lv : lr;
+        if (G == 1 && lr <= 11) {
+            CB_CUDA(launch_merkle_tree_small(st, ln, lr));
+            ctx->launches++;
+        } else
         for (int l = 0; l < local_top; l++) {
             CB_CUDA(launch_merkle_nodes(st, ln + local.layer_offset(l) * 8, 1u << (lr - l - 1), ln + local.layer_offset(l + 1) * 8));
             ctx->launches++;
@@ -1084,7 +1088,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 CB_CUDA(cudaMemcpyAsync(comp_coef.p + (size_t)c * M + N, &cc, 4, cudaMemcpyHostToDevice, st));
             }
             ctx->sync();
-            ctx->launches += n + 4;
+            ctx->launches += (n <= 10 ? 1 : n) + 4;
         } else {
             CB_CUDA(launch_fft(st, src, 4, m, 0, 1 | 2, comp_coef.p, M, nullptr, 0, ctx->tw, scratch4.p, M));
         }
@@ -1146,7 +1150,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 CB_CUDA(launch_oods_dot(st, comp_coef.p + half * N, M, 4, n, basis.p, N, d_sampled.p + ((size_t)D.cols + 4 * half) * 4));
         if (G > 1) comm_allreduce_sum_u32(cm, d_sampled.p, ((size_t)D.cols + 8) * 4, st);
         CB_CUDA(launch_oods_fill_sums(st, d_sampled.p, cdev.combs, cdev.n_combs));  // the adder-sum words' samples, from their operands'
-        ctx->launches += n + 7;
+        ctx->launches += (n <= 10 ? 1 : n) + 7;
         uint32_t* const pin = ctx->pinned_words(sampled.size() * 4);  // read-backs go through the context's pinned buffer
         CB_CUDA(cudaMemcpyAsync(pin, d_sampled.p, sampled.size() * 16, cudaMemcpyDeviceToHost, st));
         // prove()'s closing check (numerator): the AIR on the sampled mask, read back at the end
@@ -1297,7 +1301,7 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                 ColSrc bs{SRC_M31, basis.p, N, 0};
                 CB_CUDA(launch_fft(st, bs, 4, n, 0, 4, nullptr, 0, wt.p, N, tw_t, nullptr, 0));
                 CB_CUDA(launch_bitcol_dot(st, W.p, N, (int)need.size(), wt.p, inv_n, d_q1.p, d_need.p));
-                ctx->launches += n + 3;
+                ctx->launches += (n <= 10 ? 1 : n) + 3;
             }
             if (need.size() < (size_t)D.indep) {
                 uint32_t rows4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // 0xffffffff: row held by another rank

@@ -181,6 +181,10 @@ DevMerkle build_merkle(cb_ctx* ctx, const LeafGroups& groups, int lifting_log, c
     CB_CUDA(launch_merkle_leaves(ctx->stream, groups, lifting_log, nullptr, 0, 1, 1, t.nodes.p));
     ctx->launches++;
     if (leaf_stage) ctx->stage_end();
+    if (lifting_log <= 11) {
+        CB_CUDA(launch_merkle_tree_small(ctx->stream, t.nodes.p, lifting_log));
+        ctx->launches++;
+    } else
     for (int l = 0; l < lifting_log; l++) {
         const uint32_t* prev = t.nodes.p + t.layer_offset(l) * 8;
         uint32_t* out = t.nodes.p + t.layer_offset(l + 1) * 8;
