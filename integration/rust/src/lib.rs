@@ -83,6 +83,14 @@ impl Ctx {
         Ok(self.take(p, n))
     }
 
+    /// `prove_bitwise::<Blake2sMerkleChannel>(log_size, PcsConfig::default())` (chacha/bitwise/air.rs:53): returns
+    /// `u32 log_size || bincode(stark_proof)`; compare `stark_proof` with `bincode::serialize(&proof.stark_proof)` of the reference.
+    pub fn prove_bitwise(&self, log_size: u32) -> Result<Vec<u8>> {
+        let (mut p, mut n) = (ptr::null_mut(), 0usize);
+        self.check(unsafe { ffi::s2c_prove_chacha20_block(self.raw, log_size as i32, &mut p, &mut n) })?;
+        Ok(self.take(p, n))
+    }
+
     pub fn raw(&self) -> *mut ffi::cb_ctx {
         self.raw
     }
