@@ -4,7 +4,8 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
 CSRC      := zk_symmetric_crypto_b200/csrc
 SRCS      := $(wildcard $(CSRC)/*.cu)
-OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+CXXSRCS   := $(wildcard $(CSRC)/*.cpp)
+OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS)) $(patsubst $(CSRC)/%.cpp,build/%.o,$(CXXSRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/s2c_b200.h
 LIB       := zk_symmetric_crypto_b200/libs2c_b200.so
 
@@ -13,6 +14,11 @@ all: $(LIB)
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+# host-only translation units (vector intrinsics with per-function targets and run-time dispatch; no -march flag)
+build/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl

@@ -99,6 +99,9 @@ __device__ __forceinline__ void compress_fma(uint32_t h[8], const uint32_t m[16]
 }
 #endif
 
+// SIMD compression of full non-final blocks (host_blake2s_simd.cpp; returns 0 when the CPU has no usable vector path)
+extern "C" int s2c_host_blake2s_blocks(uint32_t h[8], const uint8_t* data, size_t nblocks, uint64_t t);
+
 // host: incremental form for data that arrives in chunks.  Every update() but the last must carry a multiple of 64 bytes.
 struct Incremental {
     uint32_t h[8];
@@ -109,6 +112,13 @@ struct Incremental {
     void update(const uint8_t* data, size_t len, bool more, uint8_t* out = nullptr) {
         uint32_t m[16];
         size_t off = 0;
+        {
+            const size_t nb = more ? len / 64 : (len ? (len - 1) / 64 : 0);  // full blocks that are not the final one
+            if (nb >= 4 && s2c_host_blake2s_blocks(h, data, nb, total)) {
+                off = nb * 64;
+                total += off;
+            }
+        }
         while (len - off > (more ? 63 : 64)) {
             memcpy(m, data + off, 64);
             off += 64;
@@ -131,6 +141,10 @@ inline void hash(const uint8_t* data, size_t len, uint8_t out[32]) {
     init(h);
     uint32_t m[16];
     size_t off = 0;
+    {
+        const size_t nb = len ? (len - 1) / 64 : 0;  // full blocks that are not the final one
+        if (nb >= 4 && s2c_host_blake2s_blocks(h, data, nb, 0)) off = nb * 64;
+    }
     while (len - off > 64) {
         memcpy(m, data + off, 64);  // little-endian host (see above)
         off += 64;

@@ -141,19 +141,20 @@ inline Hash32 blake2s_bytes(const uint8_t* d, size_t n) {
 inline uint32_t load_le32(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
+// little-endian host (the same assumption as blake2s.cuh): integers are appended as their memory image
 inline void put_u32(std::vector<uint8_t>& v, uint32_t x) {
-    for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i)));
+    const uint8_t* b = (const uint8_t*)&x;
+    v.insert(v.end(), b, b + 4);
 }
 inline void put_u64(std::vector<uint8_t>& v, uint64_t x) {
-    for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i)));
+    const uint8_t* b = (const uint8_t*)&x;
+    v.insert(v.end(), b, b + 8);
 }
 inline void put_bytes(std::vector<uint8_t>& v, const void* p, size_t n) {
     const uint8_t* b = (const uint8_t*)p;
     v.insert(v.end(), b, b + n);
 }
-inline void put_qm31(std::vector<uint8_t>& v, const QM31& q) {
-    for (int c = 0; c < 4; c++) put_u32(v, q.v[c]);
-}
+inline void put_qm31(std::vector<uint8_t>& v, const QM31& q) { put_bytes(v, q.v, 16); }
 
 // Blake2sChannel as the reference binary behaves (oracle/trace_blake.py):
 //   mix: digest = H(digest || payload);  draw: H(digest || n_sent as 4 LE bytes || 0x00), n_sent++
@@ -166,11 +167,22 @@ struct Channel {
         n_sent = 0;
     }
     void mix_bytes(const uint8_t* p, size_t n) {
-        std::vector<uint8_t> buf;
-        buf.reserve(32 + n);
-        put_bytes(buf, digest.b, 32);
-        put_bytes(buf, p, n);
-        update(blake2s_bytes(buf.data(), buf.size()));
+        if (n <= 32) {
+            uint8_t buf[64];
+            memcpy(buf, digest.b, 32);
+            memcpy(buf + 32, p, n);
+            update(blake2s_bytes(buf, 32 + n));
+            return;
+        }
+        // H(digest || payload) without copying the payload: the first block is digest || payload[0..32), the rest streams
+        uint8_t first[64];
+        memcpy(first, digest.b, 32);
+        memcpy(first + 32, p, 32);
+        blake2s::Incremental inc;
+        inc.update(first, 64, true);
+        Hash32 out;
+        inc.update(p + 32, n - 32, false, out.b);
+        update(out);
     }
     void mix_root(const Hash32& r) { mix_bytes(r.b, 32); }
     void mix_u64(uint64_t v) {
@@ -179,10 +191,9 @@ struct Channel {
         mix_bytes(b, 8);
     }
     void mix_felts(const QM31* f, size_t n) {
-        std::vector<uint8_t> buf;
-        buf.reserve(16 * n);
-        for (size_t i = 0; i < n; i++) put_qm31(buf, f[i]);
-        mix_bytes(buf.data(), buf.size());
+        // canonical QM31 values are 4 little-endian u32 words each: the array is its own serialisation
+        static_assert(sizeof(QM31) == 16, "QM31 layout");
+        mix_bytes((const uint8_t*)f, 16 * n);
     }
     void draw_u32s(uint32_t out[8]) {
         uint8_t buf[37];

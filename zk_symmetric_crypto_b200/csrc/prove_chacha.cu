@@ -1377,8 +1377,17 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     for (auto& r : roots) host::put_bytes(proof, r.b, 32);
     host::put_u64(proof, 3);
     host::put_u64(proof, 0);
+    auto bulk = [&](size_t bytes) {  // appends `bytes` and returns where to write them
+        const size_t o = proof.size();
+        proof.resize(o + bytes);
+        return proof.data() + o;
+    };
     host::put_u64(proof, D.cols);
-    for (int j = 0; j < D.cols; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[j]); }
+    {
+        uint8_t* w = bulk((size_t)D.cols * 24);
+        const uint64_t one = 1;
+        for (int j = 0; j < D.cols; j++, w += 24) { memcpy(w, &one, 8); memcpy(w + 8, sampled[j].v, 16); }
+    }
     host::put_u64(proof, 8);
     for (int j = 0; j < 8; j++) { host::put_u64(proof, 1); host::put_qm31(proof, sampled[D.cols + j]); }
     host::put_u64(proof, 3);
@@ -1390,7 +1399,12 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
     host::put_u64(proof, 3);
     host::put_u64(proof, 0);
     host::put_u64(proof, D.cols);
-    for (int j = 0; j < D.cols; j++) { host::put_u64(proof, nq); host::put_bytes(proof, &qv1[(size_t)j * nq], 4 * nq); }
+    {
+        const size_t each = 8 + 4 * (size_t)nq;
+        uint8_t* w = bulk((size_t)D.cols * each);
+        const uint64_t cnt = (uint64_t)nq;
+        for (int j = 0; j < D.cols; j++, w += each) { memcpy(w, &cnt, 8); memcpy(w + 8, &qv1[(size_t)j * nq], 4 * (size_t)nq); }
+    }
     host::put_u64(proof, 8);
     for (int j = 0; j < 8; j++) { host::put_u64(proof, nq); host::put_bytes(proof, &qv2[(size_t)j * nq], 4 * nq); }
     host::put_u64(proof, pow_nonce);
