@@ -79,6 +79,38 @@ B2_HD void compress(uint32_t h[8], const uint32_t m[16], uint64_t t, bool last) 
     B2S_GD(v0, v5, v10, v15, m[s8], m[s9]) B2S_GD(v1, v6, v11, v12, m[s10], m[s11])       \
     B2S_GD(v2, v7, v8, v13, m[s12], m[s13]) B2S_GD(v3, v4, v9, v14, m[s14], m[s15])
 
+// Lone-warp variant (product-size proofs: one warp hashes all leaves, bound by that warp's issue rate on the 16-lane ALU pipe):
+// the 3-input additions stay one IADD3 each (two chained IMADs would lengthen the dependent chain), only c += d moves to the
+// FMA pipe: 10 instead of 12 ALU-pipe instructions per G at an unchanged chain length.
+#define B2S_GM(a, b, c, d, x, y) \
+    a = a + b + x; d = rotr(d ^ a, 16); c = c * one + d; b = rotr(b ^ c, 12); \
+    a = a + b + y; d = rotr(d ^ a, 8);  c = c * one + d; b = rotr(b ^ c, 7);
+
+#define B2S_ROUNDM(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    B2S_GM(v0, v4, v8, v12, m[s0], m[s1]) B2S_GM(v1, v5, v9, v13, m[s2], m[s3])           \
+    B2S_GM(v2, v6, v10, v14, m[s4], m[s5]) B2S_GM(v3, v7, v11, v15, m[s6], m[s7])         \
+    B2S_GM(v0, v5, v10, v15, m[s8], m[s9]) B2S_GM(v1, v6, v11, v12, m[s10], m[s11])       \
+    B2S_GM(v2, v7, v8, v13, m[s12], m[s13]) B2S_GM(v3, v4, v9, v14, m[s14], m[s15])
+
+__device__ __forceinline__ void compress_mix(uint32_t h[8], const uint32_t m[16], uint64_t t, bool last, uint32_t one) {
+    uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    uint32_t v8 = B2S_IV0, v9 = B2S_IV1, v10 = B2S_IV2, v11 = B2S_IV3;
+    uint32_t v12 = B2S_IV4 ^ (uint32_t)t, v13 = B2S_IV5 ^ (uint32_t)(t >> 32);
+    uint32_t v14 = last ? ~B2S_IV6 : B2S_IV6, v15 = B2S_IV7;
+    B2S_ROUNDM(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2S_ROUNDM(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+    B2S_ROUNDM(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+    B2S_ROUNDM(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+    B2S_ROUNDM(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+    B2S_ROUNDM(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+    B2S_ROUNDM(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+    B2S_ROUNDM(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+    B2S_ROUNDM(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+    B2S_ROUNDM(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+    h[0] ^= v0 ^ v8; h[1] ^= v1 ^ v9; h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+    h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+
 __device__ __forceinline__ void compress_fma(uint32_t h[8], const uint32_t m[16], uint64_t t, bool last, uint32_t one) {
     uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
     uint32_t v8 = B2S_IV0, v9 = B2S_IV1, v10 = B2S_IV2, v11 = B2S_IV3;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) leaves_tiles_kernel(LeafGroups groups, in
 // loads are issued before the current compression.  The additions stay IADD3 here: the FMA-pipe form (two IMAD per 3-input add)
 // lengthens the chain and measured slower for a lone warp (2.6 vs 2.2 ms for the 2,080 compressions of a ChaCha leaf).
 __global__ void __launch_bounds__(64) leaves_seq_kernel(const uint32_t* __restrict__ arena, size_t tile_words, uint32_t n_leaves, int n_words,
-                                                        uint32_t* __restrict__ out) {
+                                                        uint32_t* __restrict__ out, uint32_t one, int variant) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n_leaves) return;
     uint32_t h[8];
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(64) leaves_seq_kernel(const uint32_t* __restri
             for (int w = 0; w < 16; w++) nxt[w] = __ldg(q + (size_t)w * n_leaves);
         }
         t += 64;
-        blake2s::compress(h, m, t, b + 1 == n_blocks);
+        if (variant) blake2s::compress_mix(h, m, t, b + 1 == n_blocks, one);
+        else blake2s::compress(h, m, t, b + 1 == n_blocks);
     }
 #pragma unroll
     for (int w = 0; w < 8; w++) out[(size_t)leaf * 8 + w] = h[w];
@@ -318,7 +319,8 @@ cudaError_t launch_merkle_leaves(cudaStream_t st, const LeafGroups& groups, int 
 cudaError_t launch_merkle_leaves_seq(cudaStream_t st, const uint32_t* arena, size_t tile_words, int n_words, int lifting_log, uint32_t* out) {
     const uint32_t n = 1u << lifting_log;
     const int threads = n >= 64 * 148 ? 64 : 32;
-    merk::leaves_seq_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(arena, tile_words, n, n_words, out);
+    static const int variant = getenv("S2C_LEAVES_SEQ_MIX") ? atoi(getenv("S2C_LEAVES_SEQ_MIX")) : 0;  // A/B switch (1: c += d on the FMA pipe)
+    merk::leaves_seq_kernel<<<(n + threads - 1) / threads, threads, 0, st>>>(arena, tile_words, n, n_words, out, 1u, variant);
     return cudaGetLastError();
 }
 
