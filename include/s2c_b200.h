@@ -273,6 +273,9 @@ int s2c_prove_aes128_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len
 int s2c_prove_aes256_ctr_encrypt(cb_ctx* ctx, const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len,
                                  uint32_t counter, const uint8_t* plaintext, size_t plaintext_len, const uint8_t* ciphertext,
                                  size_t ciphertext_len, char** json_out, size_t* json_len);
+/* Blake2s-256 of a host buffer with the library's host implementation (the one the Fiat-Shamir channel, the public-input hashes
+   and the verifier use: scalar, or SIMD with run-time dispatch, host_blake2s_simd.cpp).  Host only, no GPU needed. */
+int s2c_debug_blake2s(const uint8_t* data, size_t len, uint8_t out[32]);
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len);
 /* Block-AIR variant of the ChaCha20 circuit (reference: stwo/src/chacha/bitwise/air.rs:53-171 prove_bitwise / verify_bitwise,

@@ -65,3 +65,18 @@ def test_raw_entry_points_validate_lengths_before_reaching_c():
         with pytest.raises(z.BackendError, match=msg.replace("+", r"\+")):
             ck(*args)
     ck(bytes(32), (32,), bytes(12), 0xFFFFFFFF, 64, 64, 64)   # a single block at the last counter value is fine
+
+
+def test_host_blake2s_matches_hashlib():
+    """The library's host Blake2s (scalar tail + SIMD blocks with run-time dispatch) against hashlib on every length class:
+    empty, sub-block, block boundaries, the SIMD threshold (4 full non-final blocks) and a long message."""
+    import ctypes
+    import hashlib
+    import random
+    L = z.lib()
+    rng = random.Random(7)
+    for n in [0, 1, 31, 63, 64, 65, 127, 128, 255, 256, 257, 319, 320, 321, 1000, 4096, 65536 + 7, 532608 + 32]:
+        data = bytes(rng.getrandbits(8) for _ in range(n))
+        out = (ctypes.c_uint8 * 32)()
+        assert L.s2c_debug_blake2s(data, ctypes.c_size_t(n), out) == 0
+        assert bytes(out) == hashlib.blake2s(data, digest_size=32).digest(), n

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "s2c_prove_chacha20_raw", "s2c_prove_chacha20_dev", "cb_set_profile", "cb_stage_times", "cb_host_times", "cb_counters",
     "s2c_verify_chacha20_proof", "s2c_verify_aes_ctr_proof", "s2c_verify_chacha20_raw", "s2c_verify_aes_ctr_raw",
     "s2c_prove_chacha20_encrypt", "s2c_prove_aes128_ctr_encrypt", "s2c_prove_aes256_ctr_encrypt",
-    "s2c_debug_chacha20_keystream", "s2c_get_circuits_info", "s2c_free",
+    "s2c_debug_chacha20_keystream", "s2c_debug_blake2s", "s2c_get_circuits_info", "s2c_free",
     "s2c_prove_chacha20_stream_testdata", "s2c_prove_chacha20_block", "s2c_verify_chacha20_block",
     "cb_bit_reverse", "cb_col_at", "cb_col_set", "cb_batch_inverse_m31", "cb_batch_inverse_qm31", "cb_extend",
     "cb_barycentric_weights", "cb_barycentric_eval_at_point", "cb_precompute_twiddles_coset", "cb_commit_on_layer",

@@ -698,6 +698,13 @@ static void chacha_block_words(const uint32_t key[8], const uint32_t nonce[3], u
     for (int i = 0; i < 16; i++) out[i] = v[i] + s[i];
 }
 
+int s2c_debug_blake2s(const uint8_t* data, size_t len, uint8_t out[32]) {
+    if (!out || (!data && len)) return 1;
+    const host::Hash32 h = host::blake2s_bytes(data, len);
+    memcpy(out, h.b, 32);
+    return 0;
+}
+
 int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8_t* nonce, size_t nonce_len, uint32_t counter,
                                  char** json_out, size_t* json_len) {
     // wasm_api.rs:953-990: native block function, hex of the 64 keystream bytes
