@@ -256,6 +256,26 @@ struct ConsArgs {
     size_t out_stride;
 };
 
+// One round of MixColumns as a program of 96 byte operations {type (0: xor_byte, 1: xtime), a, b, dst} over 64 slots of column
+// indices: 0..15 state, 16..31 state after ShiftRows, 32..36 temporaries, 48..63 the round-key (or plaintext) columns of the
+// current AddRoundKey.  The kernel interprets it in a loop, so its code is the two operation bodies once (a few KB) instead of
+// 112 inlined copies per round (636 KB: every warp then ran at instruction-fetch speed - 4 ms for a 512-row product-size proof).
+// The operations consume trace columns in the reference's evaluation order (ctr.rs:244-281).
+__constant__ uchar4 c_mix_prog[96];
+static void build_mix_prog(uchar4 (&prog)[96]) {
+    int n = 0;
+    auto XT = [&](int a, int dst) { prog[n++] = make_uchar4(1, (unsigned char)a, 0, (unsigned char)dst); };
+    auto XR = [&](int a, int b, int dst) { prog[n++] = make_uchar4(0, (unsigned char)a, (unsigned char)b, (unsigned char)dst); };
+    const int A = 32, B = 33, C = 34, D = 35, E = 36;
+    for (int c = 0; c < 4; c++) {
+        const int s0 = 16 + 4 * c, s1 = s0 + 1, s2 = s0 + 2, s3 = s0 + 3, o = 4 * c;
+        XT(s0, A); XT(s1, E); XR(E, s1, B); XR(A, B, C); XR(C, s2, D); XR(D, s3, o);          // 2 s0 + 3 s1 + s2 + s3
+        XT(s1, A); XT(s2, E); XR(E, s2, B); XR(s0, A, C); XR(C, B, D); XR(D, s3, o + 1);      // s0 + 2 s1 + 3 s2 + s3
+        XT(s2, A); XT(s3, E); XR(E, s3, B); XR(s0, s1, C); XR(C, A, D); XR(D, B, o + 2);      // s0 + s1 + 2 s2 + 3 s3
+        XT(s0, E); XR(E, s0, A); XT(s3, B); XR(A, s1, C); XR(C, s2, D); XR(D, B, o + 3);      // 3 s0 + s1 + s2 + 2 s3
+    }
+}
+
 __global__ void __launch_bounds__(64) constraints_kernel(ConsArgs A) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (1u << A.eval_log)) return;
@@ -268,29 +288,33 @@ __global__ void __launch_bounds__(64) constraints_kernel(ConsArgs A) {
     e.col = 0;
     e.k = 0;
     const int nr = A.n_rounds;
-    int s[16], t[16];
+    int s[64];
     // nonce || counter occupy columns 0..15, round keys 16.., plaintext, ciphertext
     const int rk0 = 16, pt0 = 16 + 16 * (nr + 1), ct0 = pt0 + 16;
     e.col = ct0 + 16;
-    for (int i = 0; i < 16; i++) s[i] = e.xor_byte(i, rk0 + i);
+    auto add_round_key = [&](int key_col0) {  // s[i] = xor_byte(s[i], key_col0 + i)
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) s[i] = e.xor_byte(s[i], key_col0 + i);
+    };
+    for (int i = 0; i < 16; i++) s[i] = i;
+    add_round_key(rk0);
+#pragma unroll 1
     for (int rnd = 1; rnd <= nr; rnd++) {
-        for (int i = 0; i < 16; i++) s[i] = e.col++;  // S-box outputs (their relation entries are consumed below)
-        for (int i = 0; i < 16; i++) t[i] = s[c_shift_rows[i]];
+        // S-box outputs are the next 16 columns (their relation entries are consumed below); ShiftRows renames them
+        for (int i = 0; i < 16; i++) s[16 + i] = e.col + c_shift_rows[i];
+        e.col += 16;
         if (rnd < nr) {
-            for (int c = 0; c < 4; c++) {
-                const int s0 = t[4 * c], s1 = t[4 * c + 1], s2 = t[4 * c + 2], s3 = t[4 * c + 3];
-                int t0, t1, t2, t3;
-                t0 = e.xtime(s0); t1 = e.mul3(s1); t2 = e.xor_byte(t0, t1); t3 = e.xor_byte(t2, s2); s[4 * c] = e.xor_byte(t3, s3);
-                t0 = e.xtime(s1); t1 = e.mul3(s2); t2 = e.xor_byte(s0, t0); t3 = e.xor_byte(t2, t1); s[4 * c + 1] = e.xor_byte(t3, s3);
-                t0 = e.xtime(s2); t1 = e.mul3(s3); t2 = e.xor_byte(s0, s1); t3 = e.xor_byte(t2, t0); s[4 * c + 2] = e.xor_byte(t3, t1);
-                t0 = e.mul3(s0); t1 = e.xtime(s3); t2 = e.xor_byte(t0, s1); t3 = e.xor_byte(t2, s2); s[4 * c + 3] = e.xor_byte(t3, t1);
+#pragma unroll 1
+            for (int j = 0; j < 96; j++) {
+                const uchar4 op = c_mix_prog[j];
+                s[op.w] = op.x ? e.xtime(s[op.y]) : e.xor_byte(s[op.y], s[op.z]);
             }
         } else {
-            for (int i = 0; i < 16; i++) s[i] = t[i];
+            for (int i = 0; i < 16; i++) s[i] = s[16 + i];
         }
-        for (int i = 0; i < 16; i++) s[i] = e.xor_byte(s[i], rk0 + 16 * rnd + i);
+        add_round_key(rk0 + 16 * rnd);
     }
-    for (int i = 0; i < 16; i++) s[i] = e.xor_byte(s[i], pt0 + i);
+    add_round_key(pt0);
     for (int i = 0; i < 16; i++) e.emit(m31d::subm(e.ld(s[i]), e.ld(ct0 + i)));
     // finalize_logup_in_pairs: L/2 extension-field constraints (cur - prev_col [- prev_row + shift]) * den - num
     QM31 ext = qzero(), prev_col = qzero();
@@ -386,6 +410,12 @@ cudaError_t launch_aes_interaction(cudaStream_t st, const uint32_t* T, size_t st
 }
 
 cudaError_t launch_aes_constraints(cudaStream_t st, const AesConsArgs& a) {
+    static const cudaError_t prog_ok = [] {  // once per process and device context
+        uchar4 prog[96];
+        aesk::build_mix_prog(prog);
+        return cudaMemcpyToSymbol(aesk::c_mix_prog, prog, sizeof prog);
+    }();
+    if (prog_ok != cudaSuccess) return prog_ok;
     aesk::ConsArgs A;
     static_assert(sizeof(aesk::ConsArgs) == sizeof(AesConsArgs), "layout");
     memcpy(&A, &a, sizeof A);
