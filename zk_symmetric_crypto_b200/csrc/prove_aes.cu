@@ -456,7 +456,8 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     // columns kept as trace-domain VALUES: f(p) = 2^-lg <values, w(p)>, w(p) = forward butterflies with inverse twiddles applied
     // to basis(p) (the transpose of the inverse transform; kernels_stream.cu fact 2)
     const FftTables tw_t{ctx->tw.IX, ctx->tw.IY, ctx->tw.X, ctx->tw.Y, ctx->tw.max_log};
-    auto eval_vals = [&](const uint32_t* vals, size_t stride, int ncols, int lg, const PtQ& pt, QM31* out) {
+    DBuf<uint32_t> d_v1;  // the main trace's samples stay on the device (unscaled) for the FRI line coefficients below
+    auto eval_vals = [&](const uint32_t* vals, size_t stride, int ncols, int lg, const PtQ& pt, QM31* out, DBuf<uint32_t>* keep = nullptr) {
         const size_t nn = (size_t)1 << lg;
         std::vector<QM31> maps(lg);
         maps[0] = pt.y;
@@ -472,6 +473,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         ctx->sync();
         const uint32_t inv_n = 1u << (31 - lg);
         for (int j = 0; j < ncols; j++) out[j] = qmul_m(out[j], inv_n);
+        if (keep) *keep = std::move(d_out);
     };
     // samples[tree][col] = list of (point, value) in mask order
     struct Sample { PtQ pt; QM31 val; };
@@ -479,7 +481,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     {
         std::vector<QM31> v0(2), v1(C), vm(1), vi(NI), vip(4), vt(4), vtp(4), vc(8);
         eval_cols(pre.p, 256, 2, 8, Z8, v0.data());
-        eval_vals(T.p, N, C, n, Z, v1.data());
+        eval_vals(T.p, N, C, n, Z, v1.data(), &d_v1);
         eval_cols(mult.p, 256, 1, 8, Z8, vm.data());
         eval_vals(I.p, N, NI, n, Z, vi.data());
         eval_vals(I.p + (size_t)(NI - 4) * N, N, 4, n, Zp, vip.data());
@@ -525,10 +527,19 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         add_cols(comp_lde.p, M, 8, m);
         struct Entry { int ci; QM31 val, apow; };
         std::map<std::array<uint32_t, 8>, std::pair<PtQ, std::vector<Entry>>> batches;
+        // The C main-trace columns (one sample each, at z, consecutive powers rc^2 .. rc^(C+1)) are handled by a kernel over
+        // their device-resident samples (kernels_tail.cu quot_coefs_kernel: coefficients straight into the row-combination
+        // table, partial line sums added below); the host walks the remaining ~350 (column, sample) pairs.
+        const int big0 = 2, big1 = 2 + C, big2 = 2 + C + 1, big3 = big2 + NI;   // [big0,big1) = main trace, [big2,big3) = CTR interaction
         QM31 ap = qone();
         int ci = 0;
         for (auto& t : samples)
             for (auto& c : t) {
+                if (ci >= big0 && ci < big1) {
+                    if (ci == big0) ap = qmul(ap, qpow(rc, (uint64_t)C));
+                    ci++;
+                    continue;
+                }
                 std::vector<Sample> entries = c;
                 if (c.size() > 1) {
                     Sample per = c.back();
@@ -546,11 +557,22 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         // Columns of the two big groups (main trace, CTR interaction trace) enter the batch of point z only through
         // G(p) = sum_j coef_j f_j(p), which is the extension of the row-wise combination of their trace-domain values
         // (extension is linear): one pass over the values + 4 column transforms instead of reading their LDE.
-        const int big0 = 2, big1 = 2 + C, big2 = 2 + C + 1, big3 = big2 + NI;   // [big0,big1) = main trace, [big2,big3) = CTR interaction
         auto is_big = [&](int c) { return (c >= big0 && c < big1) || (c >= big2 && c < big3); };
         const auto zkey = pt_key(Z);
         std::vector<uint32_t> gcoef((size_t)(C + NI) * 4, 0);
         DBuf<uint32_t> g(ctx, 4 * N), g_lde(ctx, 4 * M), d_gcoef(ctx, gcoef.size());
+        QM31 lin_main_a = qzero(), lin_main_b = qzero();
+        {
+            DBuf<uint32_t> d_pw(ctx, (size_t)(C + 2) * 4), d_lin(ctx, 8);
+            CB_CUDA(launch_secure_powers_rev(st, rc, C + 2, d_pw.p));   // d_pw[i] = rc^(C+1-i): column j reads index C-1-j = rc^(j+2)
+            CB_CUDA(launch_quot_coefs(st, d_v1.p, C, d_pw.p, Z.y, d_gcoef.p, d_lin.p));
+            uint32_t lin[8];
+            CB_CUDA(cudaMemcpyAsync(lin, d_lin.p, sizeof lin, cudaMemcpyDeviceToHost, st));
+            ctx->sync();
+            ctx->launches += 2;
+            const uint32_t inv_n = 1u << (31 - n);  // the device samples are unscaled; a_j and b_j are linear in the sample
+            for (int k = 0; k < 4; k++) { lin_main_a.v[k] = mul(lin[k], inv_n); lin_main_b.v[k] = mul(lin[4 + k], inv_n); }
+        }
         std::vector<QuotBatch> qbs;
         std::vector<DBuf<uint32_t>> keep32;
         std::vector<DBuf<const uint32_t*>> keep_ptr;
@@ -562,7 +584,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
             std::vector<uint32_t> coefs;
             std::vector<const uint32_t*> ptrs;
             std::vector<uint8_t> logs;
-            QM31 lin_a = qzero(), lin_b = qzero();
+            QM31 lin_a = is_z ? lin_main_a : qzero(), lin_b = is_z ? lin_main_b : qzero();
             const QM31 c = qsub(qconj(pt.y), pt.y);
             if (is_z)
                 for (int k = 0; k < 4; k++) {  // the 4 coordinate columns of G with unit coefficients
@@ -600,7 +622,8 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
             qb.col_ptr = keep_ptr.back().p; qb.col_log = keep8.back().p;
             qbs.push_back(qb);
         }
-        CB_CUDA(cudaMemcpyAsync(d_gcoef.p, gcoef.data(), gcoef.size() * 4, cudaMemcpyHostToDevice, st));
+        // (rows [0, C) of the table were written by the kernel above; the host part covers the interaction columns)
+        CB_CUDA(cudaMemcpyAsync(d_gcoef.p + (size_t)C * 4, gcoef.data() + (size_t)C * 4, (gcoef.size() - (size_t)C * 4) * 4, cudaMemcpyHostToDevice, st));
         CB_CUDA(launch_rowcomb_m31(st, T.p, N, C, N, d_gcoef.p, g.p, 0));
         CB_CUDA(launch_rowcomb_m31(st, I.p, N, NI, N, d_gcoef.p + (size_t)C * 4, g.p, 1));
         {
