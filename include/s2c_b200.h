@@ -284,6 +284,11 @@ int s2c_debug_chacha20_keystream(const uint8_t* key, size_t key_len, const uint8
    bincode(StarkProof); free with s2c_free.  s2c_verify_chacha20_block returns 0 when the proof verifies, else 1 with the
    reference's VerificationError rendering in *err_out (free with s2c_free). */
 int s2c_prove_chacha20_block(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len);
+/* The same for the AES-128 block AIR (reference: stwo/src/aes/lookup/air.rs:139-305 prove_aes_lookup / verify_aes_lookup,
+   constraints.rs aes128_block, gen.rs): key 00..0f, input byte b of row r = (r + b) & 0xFF, log_size in [8, 19].  Proof bytes =
+   u32 log_size || two QM31 claimed sums || two usize interaction column counts || bincode(StarkProof). */
+int s2c_prove_aes128_block(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len);
+int s2c_verify_aes128_block(const uint8_t* proof, size_t proof_len, char** err_out, size_t* err_len);
 int s2c_verify_chacha20_block(const uint8_t* proof, size_t proof_len, char** err_out, size_t* err_len);
 int s2c_get_circuits_info(char** json_out, size_t* json_len);
 void s2c_free(void* p);

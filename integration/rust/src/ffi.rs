@@ -122,6 +122,9 @@ extern "C" {
     // block AIR of the reference's tests (chacha/bitwise/air.rs prove_bitwise / verify_bitwise): u32 log_size || bincode(StarkProof)
     pub fn s2c_prove_chacha20_block(ctx: *mut cb_ctx, log_size: c_int, proof_out: *mut *mut u8, proof_len: *mut size_t) -> c_int;
     pub fn s2c_verify_chacha20_block(proof: *const u8, proof_len: size_t, err_out: *mut *mut c_char, err_len: *mut size_t) -> c_int;
+    // AES-128 block AIR (aes/lookup/air.rs prove_aes_lookup / verify_aes_lookup): u32 log_size || stmt1 || bincode(StarkProof)
+    pub fn s2c_prove_aes128_block(ctx: *mut cb_ctx, log_size: c_int, proof_out: *mut *mut u8, proof_len: *mut size_t) -> c_int;
+    pub fn s2c_verify_aes128_block(proof: *const u8, proof_len: size_t, err_out: *mut *mut c_char, err_len: *mut size_t) -> c_int;
     pub fn s2c_verify_chacha20_raw(proof: *const u8, proof_len: size_t, nonce: *const u8, counter: u32, pt: *const u8, pt_len: size_t,
                                    ct: *const u8, ct_len: size_t, error_out: *mut *mut c_char) -> c_int;
     pub fn s2c_verify_aes_ctr_raw(proof: *const u8, proof_len: size_t, nonce: *const u8, counter: u32, pt: *const u8, pt_len: size_t,

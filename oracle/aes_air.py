@@ -101,22 +101,23 @@ def ctr_encrypt(key, nonce, counter, data):
     return bytes(out)
 
 
-def n_cols(key_len):
+def n_cols(key_len, block=False):
+    """block: the block AIR (aes/lookup/{gen,constraints,air}.rs) - no plaintext / ciphertext columns, no final xor."""
     r = 10 if key_len == 16 else 14
-    return (12 + 4 + 16 * (r + 1) + 32) + 400 + (r - 1) * (16 + 2144 + 400) + 16 + 400 + 400
+    return (12 + 4 + 16 * (r + 1) + (0 if block else 32)) + 400 + (r - 1) * (16 + 2144 + 400) + 16 + 400 + (0 if block else 400)
 
 
 def n_lookups(key_len):
     return 16 * (10 if key_len == 16 else 14)
 
 
-def n_constraints(key_len):
+def n_constraints(key_len, block=False):
     r = 10 if key_len == 16 else 14
-    return 560 + (r - 1) * (3072 + 560) + 560 + 560 + 16 + n_lookups(key_len) // 2
+    return 560 + (r - 1) * (3072 + 560) + 560 + (0 if block else 560 + 16) + n_lookups(key_len) // 2
 
 
 # ---------------------------------------------------------------- witness (gen_ctr.rs)
-def generate_ctr_trace(log_size, key, nonce_rows, counters, plaintext, ciphertext):
+def generate_ctr_trace(log_size, key, nonce_rows, counters, plaintext, ciphertext, block=False):
     """Per-row inputs: nonce_rows[N,12], counters[N], plaintext[N,16], ciphertext[N,16] (uint8/uint32 arrays; callers build
     the padding rows).  Returns (trace [C, N] uint64, lookups [L, 2, N] uint64, mults[256], valid)."""
     n = 1 << log_size
@@ -169,21 +170,29 @@ def generate_ctr_trace(log_size, key, nonce_rows, counters, plaintext, ciphertex
             t0 = mul3(s0); t1 = xtime(s3); t2 = xor_byte(t0, s1); t3 = xor_byte(t2, s2); out[i + 3] = xor_byte(t3, t1)
         return out
 
-    for i in range(12):
-        byte(nonce_rows[:, i])
-    cbytes = [((counters >> np.uint64(8 * (3 - i))) & np.uint64(0xFF)).astype(np.uint8) for i in range(4)]
-    for c in cbytes:
-        byte(c)
     rkv = [[np.full(n, b, dtype=np.uint8) for b in r] for r in rk]
-    for r in rkv:
-        for b in r:
+    if block:   # gen.rs generate_trace: the input block (here `plaintext`), the round keys, then the cipher
+        blk = [pt[:, i] for i in range(16)]
+        for b in blk:
             byte(b)
-    for i in range(16):
-        byte(pt[:, i])
-    for i in range(16):
-        byte(ct[:, i])
-    block = [nonce_rows[:, i] for i in range(12)] + cbytes
-    state = [xor_byte(block[i], rkv[0][i]) for i in range(16)]
+        for r in rkv:
+            for b in r:
+                byte(b)
+    else:
+        for i in range(12):
+            byte(nonce_rows[:, i])
+        cbytes = [((counters >> np.uint64(8 * (3 - i))) & np.uint64(0xFF)).astype(np.uint8) for i in range(4)]
+        for c in cbytes:
+            byte(c)
+        for r in rkv:
+            for b in r:
+                byte(b)
+        for i in range(16):
+            byte(pt[:, i])
+        for i in range(16):
+            byte(ct[:, i])
+        blk = [nonce_rows[:, i] for i in range(12)] + cbytes
+    state = [xor_byte(blk[i], rkv[0][i]) for i in range(16)]
     for rnd in range(1, nr):
         state = [sbox(state[i]) for i in range(16)]
         state = [state[i] for i in SHIFT_ROWS]
@@ -192,10 +201,12 @@ def generate_ctr_trace(log_size, key, nonce_rows, counters, plaintext, ciphertex
     state = [sbox(state[i]) for i in range(16)]
     state = [state[i] for i in SHIFT_ROWS]
     ks = [xor_byte(state[i], rkv[nr][i]) for i in range(16)]
-    comp = [xor_byte(ks[i], pt[:, i]) for i in range(16)]
-    valid = all(np.array_equal(comp[i], ct[:, i]) for i in range(16))
+    valid = True
+    if not block:
+        comp = [xor_byte(ks[i], pt[:, i]) for i in range(16)]
+        valid = all(np.array_equal(comp[i], ct[:, i]) for i in range(16))
     trace = np.stack(cols, axis=0)
-    assert trace.shape[0] == n_cols(len(key)), trace.shape
+    assert trace.shape[0] == n_cols(len(key), block), trace.shape
     lk = np.stack([np.stack(l, axis=0) for l in lookups], axis=0)
     return trace, lk, mults, valid
 
@@ -344,7 +355,7 @@ def _from_partial(cols4):
     return out
 
 
-def evaluate_ctr_constraints(main, inter, inter_prev_last, elems, claimed_sum, log_size, alpha_pows_rev, key_len):
+def evaluate_ctr_constraints(main, inter, inter_prev_last, elems, claimed_sum, log_size, alpha_pows_rev, key_len, block_air=False):
     """AESCtrEvalAtRow::ctr_block (ctr.rs:320-364) + finalize_logup_in_pairs.
     main [C,R] (M31) or [C,R,4] (QM31 mask values); inter [4*L/2, R(,4)] interaction coordinate columns at offset 0;
     inter_prev_last [4, R(,4)] = last interaction QM31 column at offset -1.  alpha_pows_rev[k] multiplies constraint k of
@@ -429,8 +440,9 @@ def evaluate_ctr_constraints(main, inter, inter_prev_last, elems, claimed_sum, l
 
     block = list(nxt(16))
     rks = [list(nxt(16)) for _ in range(nr + 1)]
-    pt = list(nxt(16))
-    ct = list(nxt(16))
+    if not block_air:
+        pt = list(nxt(16))
+        ct = list(nxt(16))
     state = [xor_byte(block[i], rks[0][i]) for i in range(16)]
     for rnd in range(1, nr):
         state = [sbox(state[i]) for i in range(16)]
@@ -440,10 +452,11 @@ def evaluate_ctr_constraints(main, inter, inter_prev_last, elems, claimed_sum, l
     state = [sbox(state[i]) for i in range(16)]
     state = [state[i] for i in SHIFT_ROWS]
     ks = [xor_byte(state[i], rks[nr][i]) for i in range(16)]
-    comp = [xor_byte(ks[i], pt[i]) for i in range(16)]
-    for i in range(16):
-        emit1(sub(comp[i], ct[i]))
-    assert col[0] == n_cols(key_len), (col[0], n_cols(key_len))
+    if not block_air:
+        comp = [xor_byte(ks[i], pt[i]) for i in range(16)]
+        for i in range(16):
+            emit1(sub(comp[i], ct[i]))
+    assert col[0] == n_cols(key_len, block_air), (col[0], n_cols(key_len, block_air))
     # finalize_logup_in_pairs
     nb = len(rel) // 2
     prev_col = np.zeros((R, 4), dtype=U64)
@@ -461,7 +474,7 @@ def evaluate_ctr_constraints(main, inter, inter_prev_last, elems, claimed_sum, l
             diff = q_add(q_sub(q_sub(cur, prv), prev_col), shift)
         prev_col = cur
         A.emit_ext(q_sub(q_mul(diff, den), num)[None])
-    assert A.k == n_constraints(key_len), (A.k, n_constraints(key_len))
+    assert A.k == n_constraints(key_len, block_air), (A.k, n_constraints(key_len, block_air))
     return A.acc
 
 

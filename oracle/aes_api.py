@@ -51,14 +51,16 @@ def _pt_add_q(p, q):
     return p[0] * q[0] - p[1] * q[1], p[0] * q[1] + p[1] * q[0]
 
 
-def prove_aes_ctr_internal(log_size, key, nonce_rows, counters, PT, CT, pub, config=None, debug=None):
+def prove_aes_ctr_internal(log_size, key, nonce_rows, counters, PT, CT, pub, config=None, debug=None, block=False):
+    """block=True: aes/lookup/air.rs:139-260 prove_aes_lookup (the block AIR: same flow, statement 0 = log_size alone, PT = the
+    input block of every row)."""
     config = config or PcsConfig()
     if log_size < 8:
         raise ProofError("log_size (%d) must be >= 8 for S-box table" % log_size)
     if log_size > 24:
         raise ProofError("log_size (%d) must be <= MAX_LOG_SIZE (24)" % log_size)
     key_len = len(key)
-    trace, lookups, mults, valid = aa.generate_ctr_trace(log_size, key, nonce_rows, counters, PT, CT)
+    trace, lookups, mults, valid = aa.generate_ctr_trace(log_size, key, nonce_rows, counters, PT, CT, block)
     if not valid:
         raise ProofError("Ciphertext does not match encryption - invalid witness")
     channel = Blake2sChannel()
@@ -66,12 +68,13 @@ def prove_aes_ctr_internal(log_size, key, nonce_rows, counters, PT, CT, pub, con
     tab = aa.sbox_table_columns()
     scheme.commit_evals([tab[0], tab[1]], channel)                                   # tree 0
     channel.mix_u64(log_size)
-    channel.mix_u64(0 if key_len == 16 else 1)
-    for i in range(3):
-        channel.mix_u64(struct.unpack_from("<I", pub, 4 * i)[0])
-    channel.mix_u64(struct.unpack_from("<I", pub, 12)[0])
-    for i in range(16):
-        channel.mix_u64(struct.unpack_from("<I", pub, 16 + 4 * i)[0])
+    if not block:
+        channel.mix_u64(0 if key_len == 16 else 1)
+        for i in range(3):
+            channel.mix_u64(struct.unpack_from("<I", pub, 4 * i)[0])
+        channel.mix_u64(struct.unpack_from("<I", pub, 12)[0])
+        for i in range(16):
+            channel.mix_u64(struct.unpack_from("<I", pub, 16 + 4 * i)[0])
     C = trace.shape[0]
     scheme.commit_evals([trace[j] for j in range(C)] + [mults.astype(U64)], channel)  # tree 1
     elems = aa.SboxElements.draw(channel)
@@ -83,14 +86,14 @@ def prove_aes_ctr_internal(log_size, key, nonce_rows, counters, PT, CT, pub, con
         raise ProofError("LogUp sums don't balance")
     # ---- stwo::prover::prove
     random_coeff = channel.draw_secure_felt()
-    K = aa.n_constraints(key_len)
+    K = aa.n_constraints(key_len, block)
     apr = secure_powers(random_coeff, K + 1)[::-1].copy()       # apr[k] = alpha^(K_total-1-k), ctr component first
     n_i = len(icols)
     ev1, ev2, ev0 = scheme.trees[1].evals, scheme.trees[2].evals, scheme.trees[0].evals
     main = np.stack(ev1[:C], axis=0)
     inter = np.stack(ev2[:n_i], axis=0)
     prev = aa.prev_row_index(log_size, log_size + 1)
-    acc = aa.evaluate_ctr_constraints(main, inter, inter[n_i - 4:][:, prev], elems, csum, log_size, apr[:K], key_len)
+    acc = aa.evaluate_ctr_constraints(main, inter, inter[n_i - 4:][:, prev], elems, csum, log_size, apr[:K], key_len, block)
     acc = q_mul_m31(acc, m_inv(coset_vanishing_on_domain(log_size, log_size + 1)))
     prev8 = aa.prev_row_index(8, 9)
     tinter = np.stack(ev2[n_i:], axis=0)
@@ -120,9 +123,20 @@ def prove_aes_ctr_internal(log_size, key, nonce_rows, counters, PT, CT, pub, con
     proof, info = prove_values(scheme, sp, channel, log_size + 1)
     if debug is not None:
         debug.update(info, scheme=scheme, oods=oods, acc=acc, random_coeff=random_coeff)
-    stmt0 = struct.pack("<II", log_size, 0 if key_len == 16 else 1) + pub
+    stmt0 = struct.pack("<I", log_size) if block else struct.pack("<II", log_size, 0 if key_len == 16 else 1) + pub
     stmt1 = struct.pack("<4I", *csum.v) + struct.pack("<4I", *tsum.v) + struct.pack("<QQ", n_i, len(tcols))
     return stmt0 + stmt1 + proof
+
+
+def prove_aes_lookup(log_size, config=None):
+    """aes/lookup/air.rs:139-260 with its fixed generator: key 00..0f, input byte b of row r = (r + b) & 0xFF.
+    Returns u32 log_size || stmt1 || bincode(StarkProof) (AESLookupProof's field order; the reference does not serialise it)."""
+    n = 1 << log_size
+    rows = np.arange(n, dtype=np.uint64)[:, None]
+    blocks = ((rows + np.arange(16, dtype=np.uint64)[None, :]) & np.uint64(0xFF)).astype(np.uint8)
+    zeros12 = np.zeros((n, 12), dtype=np.uint8)
+    return prove_aes_ctr_internal(log_size, bytes(range(16)), zeros12, np.zeros(n, dtype=np.uint64), blocks,
+                                  np.zeros((n, 16), dtype=np.uint8), b"", config, block=True)
 
 
 def _generate(key_len, name, key, nonce, counter, plaintext, ciphertext, debug=None):

@@ -512,3 +512,24 @@ def test_block_air_streaming_path(backend, log_size, cap):
     assert z.verify_chacha20_block(bytes(bad)) != ""
     if cap >= 0:
         assert proof == backend.prove_chacha20_block(log_size)
+
+
+AES_BLOCK_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "aes128_block_golden.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", AES_BLOCK_GOLDEN, ids=lambda c: "log%d" % c["log_size"])
+def test_aes_block_air_proof_bytes_match_fixture(backend, case):
+    """AES-128 block AIR (reference: aes/lookup/air.rs prove_aes_lookup): GPU proof bytes == the restatement's fixture."""
+    import zk_symmetric_crypto_b200 as z
+    proof = backend.prove_aes128_block(case["log_size"])
+    assert len(proof) == case["proof_bytes"] and hashlib.sha256(proof).hexdigest() == case["sha256"]
+    assert z.verify_aes128_block(proof) == ""
+
+
+def test_aes_block_air_larger_trace_verifies(backend):
+    import zk_symmetric_crypto_b200 as z
+    proof = backend.prove_aes128_block(14)
+    assert z.verify_aes128_block(proof) == ""
+    bad = bytearray(proof)
+    bad[len(bad) // 3] ^= 2
+    assert z.verify_aes128_block(bytes(bad)) != ""

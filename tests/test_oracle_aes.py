@@ -84,3 +84,22 @@ def test_reference_verifier_accepts_oracle_proof():
     key, nonce, counter, pt, ct = aes_case_inputs(32, 2, 12)
     mine = aes_api.generate_aes256_ctr_proof(key, nonce, counter, pt, ct)
     assert ref_wasm.verify_aes_ctr_proof(mine["proof"], nonce, counter, pt, ct) == {"algorithm": "aes256-ctr", "valid": True}
+
+
+def test_aes_block_air_oracle_proof_and_host_verifier():
+    """AES-128 block AIR (aes/lookup/air.rs prove_aes_lookup / verify_aes_lookup): the restatement's proof matches its fixture, the C++
+    host verifier accepts it and rejects mutations."""
+    import hashlib
+    import json
+    import os
+    import zk_symmetric_crypto_b200 as z
+    import aes_api
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "aes128_block_golden.json")))["cases"][0]
+    proof = aes_api.prove_aes_lookup(gold["log_size"])
+    assert len(proof) == gold["proof_bytes"] and hashlib.sha256(proof).hexdigest() == gold["sha256"]
+    assert z.verify_aes128_block(proof) == ""
+    for pos in (0, 10, 60, len(proof) // 2, len(proof) - 40):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert z.verify_aes128_block(bytes(bad)) != ""
+    assert z.verify_aes128_block(proof[:-1]).startswith("Invalid proof format")

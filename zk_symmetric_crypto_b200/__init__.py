@@ -8,12 +8,12 @@ raises `BackendError` if libs2c_b200.so or a CUDA device is missing (verificatio
 """
 from .backend import (BackendError, Backend, lib, lib_path, generate_chacha20_proof, prove_chacha20_raw,
                       generate_aes128_ctr_proof, generate_aes256_ctr_proof,
-                      verify_chacha20_proof, verify_aes_ctr_proof, verify_chacha20_raw, verify_aes_ctr_raw, verify_chacha20_block,
+                      verify_chacha20_proof, verify_aes_ctr_proof, verify_chacha20_raw, verify_aes_ctr_raw, verify_chacha20_block, verify_aes128_block,
                       prove_chacha20_encrypt, prove_aes128_ctr_encrypt, prove_aes256_ctr_encrypt,
                       debug_chacha20_keystream, get_circuits_info, EXPORTED_SYMBOLS)
 from .operator import make_stwo_zk_operator
 
 __all__ = ["BackendError", "Backend", "lib", "lib_path", "generate_chacha20_proof", "prove_chacha20_raw", "generate_aes128_ctr_proof", "generate_aes256_ctr_proof",
-           "verify_chacha20_proof", "verify_aes_ctr_proof", "verify_chacha20_raw", "verify_aes_ctr_raw", "verify_chacha20_block",
+           "verify_chacha20_proof", "verify_aes_ctr_proof", "verify_chacha20_raw", "verify_aes_ctr_raw", "verify_chacha20_block", "verify_aes128_block",
            "prove_chacha20_encrypt", "prove_aes128_ctr_encrypt", "prove_aes256_ctr_encrypt",
            "debug_chacha20_keystream", "get_circuits_info", "make_stwo_zk_operator", "EXPORTED_SYMBOLS"]

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "s2c_prove_chacha20_encrypt", "s2c_prove_aes128_ctr_encrypt", "s2c_prove_aes256_ctr_encrypt",
     "s2c_debug_chacha20_keystream", "s2c_debug_blake2s", "s2c_get_circuits_info", "s2c_free",
     "s2c_prove_chacha20_stream_testdata", "s2c_prove_chacha20_block", "s2c_verify_chacha20_block",
+    "s2c_prove_aes128_block", "s2c_verify_aes128_block",
     "cb_bit_reverse", "cb_col_at", "cb_col_set", "cb_batch_inverse_m31", "cb_batch_inverse_qm31", "cb_extend",
     "cb_barycentric_weights", "cb_barycentric_eval_at_point", "cb_precompute_twiddles_coset", "cb_commit_on_layer",
     "cb_accumulate", "cb_lift_and_accumulate", "cb_accumulate_quotients_batches", "cb_aes_ctr_layout", "cb_gen_trace_aes_ctr",
@@ -208,6 +209,15 @@ class Backend:
         self.L.s2c_free(out)
         return proof
 
+    def prove_aes128_block(self, log_size):
+        """The reference's AES-128 block-AIR prover `prove_aes_lookup` (aes/lookup/air.rs:139-260) at `log_size`; proof bytes."""
+        out = ctypes.POINTER(ctypes.c_uint8)()
+        n = ctypes.c_size_t()
+        self._ck(self.L.s2c_prove_aes128_block(self.ctx, int(log_size), ctypes.byref(out), ctypes.byref(n)))
+        proof = ctypes.string_at(out, n.value)
+        self.L.s2c_free(out)
+        return proof
+
     def set_max_cached_tiles(self, n_tiles):
         """Cap on LDE tiles the streaming prover keeps between its two passes (-1: as many as memory allows)."""
         self._ck(self.L.cb_set_max_cached_tiles(self.ctx, int(n_tiles)))
@@ -351,6 +361,19 @@ def verify_chacha20_block(proof):
     n = ctypes.c_size_t()
     pb = bytes(proof)
     L.s2c_verify_chacha20_block(pb, ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n))
+    msg = ctypes.string_at(out, n.value).decode() if out else ""
+    if out:
+        L.s2c_free(out)
+    return msg
+
+
+def verify_aes128_block(proof):
+    """verify_aes_lookup (aes/lookup/air.rs:262-305) on proof bytes: "" when the proof verifies, else the error rendering."""
+    L = lib()
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    pb = bytes(proof)
+    L.s2c_verify_aes128_block(pb, ctypes.c_size_t(len(pb)), ctypes.byref(out), ctypes.byref(n))
     msg = ctypes.string_at(out, n.value).decode() if out else ""
     if out:
         L.s2c_free(out)

@@ -797,6 +797,41 @@ int s2c_verify_chacha20_block(const uint8_t* proof, size_t proof_len, char** err
     return e.empty() ? 0 : 1;
 }
 
+// AES-128 block AIR of the reference's tests (aes/lookup/air.rs:139-305 prove_aes_lookup / verify_aes_lookup; constraints.rs,
+// gen.rs): the CTR AIR without the counter block, the plaintext / ciphertext columns and the final xor.  The trace is the
+// reference generator's: key 00..0f, input byte b of row r = (r + b) & 0xFF.  Proof bytes = u32 log_size || stmt1 (two QM31
+// claimed sums, two usize column counts) || bincode(StarkProof) - the field order of AESLookupProof.
+int s2c_prove_aes128_block(cb_ctx* ctx, int log_size, uint8_t** proof_out, size_t* proof_len) {
+    CtxUse use(ctx);
+    ctx = use.ctx;
+    if (!ctx) return 2;
+    CB_TRY(ctx)
+    CB_CUDA(cudaSetDevice(ctx->device));
+    if (log_size < 8 || log_size > 19) throw CbError("log_size must be in [8, 19]");
+    const size_t n = (size_t)1 << log_size;
+    uint8_t key[16];
+    for (int i = 0; i < 16; i++) key[i] = (uint8_t)i;
+    std::vector<uint8_t> blocks(n * 16);
+    for (size_t r = 0; r < n; r++)
+        for (int b = 0; b < 16; b++) blocks[r * 16 + b] = (uint8_t)((r + b) & 0xFF);
+    const uint8_t nonce[12] = {0};
+    std::vector<uint8_t> proof;
+    std::string e = prove_aes_ctr(ctx, 16, key, nonce, 0, blocks.data(), nullptr, blocks.size(), proof, true);
+    if (!e.empty()) throw CbError(e);
+    give_proof(proof, proof_out, proof_len);
+    CB_CATCH(ctx)
+}
+int s2c_verify_aes128_block(const uint8_t* proof, size_t proof_len, char** err_out, size_t* err_len) {
+    std::string e;
+    try {
+        e = verify_aes128_block(proof, proof_len);
+    } catch (const std::exception& ex) {
+        e = std::string("Invalid proof format: ") + ex.what();
+    }
+    if (err_out) ret_json(e, err_out, err_len);
+    return e.empty() ? 0 : 1;
+}
+
 int s2c_get_circuits_info(char** json_out, size_t* json_len) {
     // wasm_api.rs:993-1008 (values confirmed against the reference binary's own get_circuits_info())
     return ret_json("{\"aes128_ctr\":{\"block_bytes\":16,\"cols\":24480,\"constraints\":34464,\"key_bytes\":16},"

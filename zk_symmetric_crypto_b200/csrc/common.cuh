@@ -125,6 +125,7 @@ struct AesConsArgs {
     int eval_log, trace_log, n_rounds, n_lookups;
     uint32_t* out;
     size_t out_stride;
+    int block;  // block AIR variant (aes/lookup/constraints.rs aes128_block)
 };
 struct AesTableArgs {
     const uint32_t *pre_in, *pre_out, *mult;
@@ -138,7 +139,7 @@ struct AesTableArgs {
 cudaError_t aes_upload_sbox(const uint8_t sbox[256]);
 cudaError_t launch_aes_witness(cudaStream_t st, const uint8_t* rk, int n_rounds, const uint8_t nonce[12], uint32_t counter,
                                uint32_t num_blocks, uint32_t n_active_rows, const uint8_t* pt, const uint8_t* ct, int log_size,
-                               uint32_t* T, size_t stride, unsigned int* mults, int* invalid);
+                               uint32_t* T, size_t stride, unsigned int* mults, int* invalid, int block_air = 0);
 cudaError_t launch_aes_interaction(cudaStream_t st, const uint32_t* T, size_t stride, int log_size, const int* lk_in, const int* lk_out,
                                    int n_lookups, m31::QM31 z, m31::QM31 alpha, uint32_t* I, size_t i_stride);
 cudaError_t launch_aes_constraints(cudaStream_t st, const AesConsArgs& a);

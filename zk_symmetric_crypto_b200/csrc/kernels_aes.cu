@@ -57,6 +57,7 @@ struct WitnessArgs {
     uint32_t num_blocks;     // rows with caller-supplied plaintext/ciphertext
     uint32_t n_active_rows;  // rows covered by provided vec-rows (multiple of 16); rows beyond use the default input
     int n_rounds;            // 10 or 14
+    int block;               // block AIR (aes/lookup/{gen,constraints,air}.rs): input block = pt[row], no counter block, no pt/ct columns
 };
 
 __global__ void __launch_bounds__(128) witness_kernel(WitnessArgs a, const uint8_t* __restrict__ pt, const uint8_t* __restrict__ ct,
@@ -71,16 +72,24 @@ __global__ void __launch_bounds__(128) witness_kernel(WitnessArgs a, const uint8
         const uint32_t ctr = active ? a.counter + row : (row & 15u);
         Emit e{T + row, stride, 0};
         uint32_t blk[16], p[16];
+        if (a.block) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) { blk[i] = active ? a.nonce[i] : 0u; e.byte(blk[i]); }
+            for (int i = 0; i < 16; i++) { blk[i] = pt[(size_t)row * 16 + i]; e.byte(blk[i]); }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { blk[12 + i] = (ctr >> (8 * (3 - i))) & 0xffu; e.byte(blk[12 + i]); }
+            for (int i = 0; i < 12; i++) { blk[i] = active ? a.nonce[i] : 0u; e.byte(blk[i]); }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { blk[12 + i] = (ctr >> (8 * (3 - i))) & 0xffu; e.byte(blk[12 + i]); }
+        }
         for (int r = 0; r <= a.n_rounds; r++)
             for (int i = 0; i < 16; i++) e.byte(a.rk[16 * r + i]);
+        int ct_col = 0;
+        if (!a.block) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) { p[i] = real ? pt[(size_t)row * 16 + i] : 0u; e.byte(p[i]); }
-        const int ct_col = e.col;  // ciphertext columns are written once the keystream is known (padding: ct = keystream)
-        e.col += 16;
+            for (int i = 0; i < 16; i++) { p[i] = real ? pt[(size_t)row * 16 + i] : 0u; e.byte(p[i]); }
+            ct_col = e.col;  // ciphertext columns are written once the keystream is known (padding: ct = keystream)
+            e.col += 16;
+        }
         uint32_t s[16], t[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = e.xor_byte(blk[i], a.rk[i]);
@@ -111,6 +120,7 @@ __global__ void __launch_bounds__(128) witness_kernel(WitnessArgs a, const uint8
             for (int i = 0; i < 16; i++) s[i] = e.xor_byte(s[i], a.rk[16 * rnd + i]);
         }
         bool ok = true;
+        if (!a.block)
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const uint32_t comp = e.xor_byte(s[i], p[i]);
@@ -254,6 +264,7 @@ struct ConsArgs {
     int eval_log, trace_log, n_rounds, n_lookups;
     uint32_t* out;           // 4 coordinate columns
     size_t out_stride;
+    int block;               // block AIR: no plaintext / ciphertext columns, the walk ends with the last AddRoundKey
 };
 
 // One round of MixColumns as a program of 96 byte operations {type (0: xor_byte, 1: xtime), a, b, dst} over 64 slots of column
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(64) constraints_kernel(ConsArgs A) {
     int s[64];
     // nonce || counter occupy columns 0..15, round keys 16.., plaintext, ciphertext
     const int rk0 = 16, pt0 = 16 + 16 * (nr + 1), ct0 = pt0 + 16;
-    e.col = ct0 + 16;
+    e.col = A.block ? pt0 : ct0 + 16;
     auto add_round_key = [&](int key_col0) {  // s[i] = xor_byte(s[i], key_col0 + i)
 #pragma unroll 1
         for (int i = 0; i < 16; i++) s[i] = e.xor_byte(s[i], key_col0 + i);
@@ -314,8 +325,10 @@ __global__ void __launch_bounds__(64) constraints_kernel(ConsArgs A) {
         }
         add_round_key(rk0 + 16 * rnd);
     }
-    add_round_key(pt0);
-    for (int i = 0; i < 16; i++) e.emit(m31d::subm(e.ld(s[i]), e.ld(ct0 + i)));
+    if (!A.block) {
+        add_round_key(pt0);
+        for (int i = 0; i < 16; i++) e.emit(m31d::subm(e.ld(s[i]), e.ld(ct0 + i)));
+    }
     // finalize_logup_in_pairs: L/2 extension-field constraints (cur - prev_col [- prev_row + shift]) * den - num
     QM31 ext = qzero(), prev_col = qzero();
     const int nb = A.n_lookups / 2;
@@ -389,8 +402,9 @@ cudaError_t aes_upload_sbox(const uint8_t sbox[256]) { return cudaMemcpyToSymbol
 
 cudaError_t launch_aes_witness(cudaStream_t st, const uint8_t* rk, int n_rounds, const uint8_t nonce[12], uint32_t counter,
                                uint32_t num_blocks, uint32_t n_active_rows, const uint8_t* pt, const uint8_t* ct, int log_size,
-                               uint32_t* T, size_t stride, unsigned int* mults, int* invalid) {
+                               uint32_t* T, size_t stride, unsigned int* mults, int* invalid, int block_air) {
     aesk::WitnessArgs a;
+    a.block = block_air;
     memcpy(a.rk, rk, 16 * (n_rounds + 1));
     memcpy(a.nonce, nonce, 12);
     a.counter = counter;

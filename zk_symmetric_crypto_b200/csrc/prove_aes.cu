@@ -68,10 +68,10 @@ std::vector<uint8_t> expand_key(const uint8_t* key, int key_len) {
 
 // Column bookkeeping of the AIR (same traversal as the witness / constraint kernels): S-box (input, output) columns.
 }  // namespace
-AesLayout aes_make_layout(int nr) {
+AesLayout aes_make_layout(int nr, bool block) {
     static const int SR[16] = {0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 1, 6, 11};
     AesLayout L;
-    int col = 16 + 16 * (nr + 1) + 32, k = 0;
+    int col = 16 + 16 * (nr + 1) + (block ? 0 : 32), k = 0;
     auto xor_byte = [&]() { col += 25; k += 35; return col - 1; };
     auto xtime = [&]() { col += 17; k += 26; return col - 1; };
     int s[16], t[16];
@@ -96,8 +96,10 @@ AesLayout aes_make_layout(int nr) {
         }
         for (int i = 0; i < 16; i++) s[i] = xor_byte();
     }
-    for (int i = 0; i < 16; i++) s[i] = xor_byte();
-    k += 16;
+    if (!block) {
+        for (int i = 0; i < 16; i++) s[i] = xor_byte();
+        k += 16;
+    }
     L.n_cols = col;
     L.n_constraints = k + (int)L.lk_in.size() / 2;
     return L;
@@ -108,7 +110,7 @@ const uint8_t* aes_sbox() { return tables().sbox; }
 
 namespace {
 using Layout = AesLayout;
-Layout make_layout(int nr) { return aes_make_layout(nr); }
+Layout make_layout(int nr, bool block = false) { return aes_make_layout(nr, block); }
 
 struct PtQ {
     QM31 x, y;
@@ -167,7 +169,7 @@ struct Tree {
 }  // namespace
 
 std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter,
-                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof) {
+                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof, bool block_air) {
     const PcsConfig cfg;
     const uint32_t num_blocks = (uint32_t)(len / 16);
     int log_size = 8;
@@ -175,8 +177,9 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     if (log_size > 24) return "log_size (" + std::to_string(log_size) + ") must be <= MAX_LOG_SIZE (24)";
     const int n = log_size, m = n + 1, nr = key_len == 16 ? 10 : 14;
     const size_t N = (size_t)1 << n, M = (size_t)1 << m;
-    static const Layout L128 = make_layout(10), L256 = make_layout(14);
-    const Layout& lay = nr == 10 ? L128 : L256;
+    static const Layout L128 = make_layout(10), L256 = make_layout(14), L128b = make_layout(10, true);
+    if (block_air && (key_len != 16 || len != ((size_t)16 << log_size))) return "block AIR: AES-128, one input block per row";
+    const Layout& lay = block_air ? L128b : (nr == 10 ? L128 : L256);
     const int C = lay.n_cols, K = lay.n_constraints, NL = (int)lay.lk_in.size(), NI = 4 * (NL / 2);
     cudaStream_t st = ctx->stream;
     {
@@ -206,17 +209,17 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
 
     // ---- witness
     ctx->stage_begin("witness");
-    DBuf<uint8_t> d_pt(ctx, len), d_ct(ctx, len);
+    DBuf<uint8_t> d_pt(ctx, len), d_ct(ctx, block_air ? 16 : len);
     DBuf<uint32_t> T(ctx, (size_t)C * N);
     DBuf<unsigned int> d_mults(ctx, 256);
     DBuf<int> d_invalid(ctx, 1);
     CB_CUDA(cudaMemcpyAsync(d_pt.p, plaintext, len, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(d_ct.p, ciphertext, len, cudaMemcpyHostToDevice, st));
+    if (!block_air) CB_CUDA(cudaMemcpyAsync(d_ct.p, ciphertext, len, cudaMemcpyHostToDevice, st));
     CB_CUDA(cudaMemsetAsync(d_mults.p, 0, 256 * 4, st));
     CB_CUDA(cudaMemsetAsync(d_invalid.p, 0, 4, st));
     const uint32_t rows_needed = (num_blocks + 15) / 16;
     CB_CUDA(launch_aes_witness(st, rk.data(), nr, nonce, counter, num_blocks, rows_needed * 16, d_pt.p, d_ct.p, n, T.p, N, d_mults.p,
-                               d_invalid.p));
+                               d_invalid.p, block_air ? 1 : 0));
     ctx->launches++;
     ctx->stage_end();
     int invalid = 0;
@@ -224,7 +227,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     CB_CUDA(cudaMemcpyAsync(&invalid, d_invalid.p, 4, cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaMemcpyAsync(mults.data(), d_mults.p, 256 * 4, cudaMemcpyDeviceToHost, st));
     ctx->sync();
-    if (invalid) return "Ciphertext does not match encryption - invalid witness";
+    if (invalid && !block_air) return "Ciphertext does not match encryption - invalid witness";
     d_pt.release();
     d_ct.release();
 
@@ -293,19 +296,21 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
     // ---- statement 0 (air_ctr.rs:156-160, 66-99); the public-input hashes cover the caller's plaintext / ciphertext
     std::vector<uint8_t> stmt;
     host::put_u32(stmt, (uint32_t)log_size);
-    host::put_u32(stmt, key_len == 16 ? 0u : 1u);
-    host::put_bytes(stmt, nonce, 12);
-    host::put_u32(stmt, counter);
-    {
-        Hash32 pth = host::blake2s_bytes(plaintext, len), cth = host::blake2s_bytes(ciphertext, len);
-        host::put_bytes(stmt, pth.b, 32);
-        host::put_bytes(stmt, cth.b, 32);
+    ch.mix_u64((uint64_t)log_size);  // AESLookupStatement0::mix_into (aes/lookup/air.rs:65-67) stops here
+    if (!block_air) {
+        host::put_u32(stmt, key_len == 16 ? 0u : 1u);
+        host::put_bytes(stmt, nonce, 12);
+        host::put_u32(stmt, counter);
+        {
+            Hash32 pth = host::blake2s_bytes(plaintext, len), cth = host::blake2s_bytes(ciphertext, len);
+            host::put_bytes(stmt, pth.b, 32);
+            host::put_bytes(stmt, cth.b, 32);
+        }
+        ch.mix_u64(key_len == 16 ? 0 : 1);
+        for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[8 + 4 * i]));
+        ch.mix_u64(counter);
+        for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[24 + 4 * i]));
     }
-    ch.mix_u64((uint64_t)log_size);
-    ch.mix_u64(key_len == 16 ? 0 : 1);
-    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(&stmt[8 + 4 * i]));
-    ch.mix_u64(counter);
-    for (int i = 0; i < 16; i++) ch.mix_u64(host::load_le32(&stmt[24 + 4 * i]));
 
     // ---- tree 1: main trace + S-box multiplicities
     DBuf<uint32_t> lde1(ctx, (size_t)C * M), mult(ctx, 256), mult_lde(ctx, 512);
@@ -393,6 +398,7 @@ std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const ui
         AesConsArgs a{};
         a.lde = lde1.p; a.stride = M; a.inter = inter_lde.p; a.i_stride = M;
         a.apr_lo = apr_lo.p; a.apr_hi = apr_hi.p; a.apr = apr.p; a.den_inv = d_den.p;
+        a.block = block_air ? 1 : 0;
         a.lk_in = d_lk_in.p; a.lk_out = d_lk_out.p;
         a.z = z; a.alpha = alpha; a.shift = div_n(csum, n);
         a.eval_log = m; a.trace_log = n; a.n_rounds = nr; a.n_lookups = NL;

@@ -55,15 +55,18 @@ std::string prove_chacha20(cb_ctx* ctx, const uint8_t key[32], const uint8_t non
                            const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof, ProveOptions opt = ProveOptions());
 
 // AES-128/256-CTR (prove_aes.cu): key_len 16 or 32; len = multiple of 16 bytes.  Returns "" or the reference's error string.
+// block_air: the AES-128 block AIR (aes/lookup/air.rs prove_aes_lookup): `plaintext` = one 16-byte input block per row
+// (len = 16 << log_size), nonce / counter / ciphertext unused; proof = u32 log_size || stmt1 || bincode(StarkProof)
 std::string prove_aes_ctr(cb_ctx* ctx, int key_len, const uint8_t* key, const uint8_t nonce[12], uint32_t counter,
-                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof);
+                          const uint8_t* plaintext, const uint8_t* ciphertext, size_t len, std::vector<uint8_t>& proof,
+                          bool block_air = false);
 
 // AES-CTR AIR column bookkeeping shared by the prover and the host verifier
 struct AesLayout {
     int n_cols = 0, n_constraints = 0;
     std::vector<int> lk_in, lk_out;  // S-box lookup (input, output) columns in relation order
 };
-AesLayout aes_make_layout(int n_rounds);
+AesLayout aes_make_layout(int n_rounds, bool block_air = false);
 std::vector<uint8_t> aes_expand_key(const uint8_t* key, int key_len);  // aes/mod.rs:213-270
 const uint8_t* aes_sbox();                                             // aes/mod.rs:10-30
 
@@ -81,6 +84,8 @@ std::string verify_chacha20(const uint8_t* proof, size_t len, const uint8_t nonc
                             size_t pt_len, const uint8_t* ciphertext, size_t ct_len);
 // verify_bitwise (chacha/bitwise/air.rs:139-171): proof = u32 log_size || bincode(StarkProof)
 std::string verify_chacha20_block(const uint8_t* proof, size_t len);
+// verify_aes_lookup (aes/lookup/air.rs:262-305)
+std::string verify_aes128_block(const uint8_t* proof, size_t len);
 // *key_size_out: 0 = AES-128, 1 = AES-256 (read from the proof's statement before any check)
 std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
                            size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out);

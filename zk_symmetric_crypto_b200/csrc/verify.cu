@@ -632,41 +632,49 @@ std::string verify_chacha20_block(const uint8_t* proof, size_t len) {
 }
 
 // ================================================================================================ AES-CTR
-std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
-                           size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out) {
+// block = true: the AES-128 block AIR (aes/lookup/air.rs verify_aes_lookup): statement 0 is log_size alone, no public inputs
+static std::string verify_aes_impl(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                                   size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out, bool block) {
     Reader r{proof, len};
     const uint32_t log_size = r.u32();
-    const uint32_t key_size = r.u32();
+    const uint32_t key_size = block ? 0u : r.u32();
     if (key_size > 1) throw VerifyFormatError("invalid value: integer `" + std::to_string(key_size) + "`, expected variant index 0 <= i < 2");
     if (key_size_out) *key_size_out = (int)key_size;
-    uint8_t p_nonce[12];
-    for (int i = 0; i < 12; i++) p_nonce[i] = r.u8();
-    const uint32_t p_counter = r.u32();
-    const Hash32 pth = r.hash(), cth = r.hash();
+    uint8_t p_nonce[12] = {0};
+    uint32_t p_counter = 0;
+    Hash32 pth, cth;
+    if (!block) {
+        for (int i = 0; i < 12; i++) p_nonce[i] = r.u8();
+        p_counter = r.u32();
+        pth = r.hash();
+        cth = r.hash();
+    }
     const QM31 csum = r.qm31(), tsum = r.qm31();
     const uint64_t n_ctr_inter = r.usize(), n_sbox_inter = r.usize();
     const StarkProofData sp = read_stark(r);
 
     std::string e = validate_pcs_config(sp.cfg);
     if (!e.empty()) return e;
-    if (!public_inputs_match(p_nonce, p_counter, pth, cth, nonce, counter, plaintext, pt_len, ciphertext, ct_len)) return "OodsNotMatching";
+    if (!block && !public_inputs_match(p_nonce, p_counter, pth, cth, nonce, counter, plaintext, pt_len, ciphertext, ct_len)) return "OodsNotMatching";
     if (n_ctr_inter > (1u << 16) || n_sbox_inter > (1u << 16)) return "OodsNotMatching";
     if (sp.commitments.size() < 3) return "OodsNotMatching";
     if (log_size < 8 || log_size > 26) return "InvalidStructure(\"log_size out of range\")";
 
     const int n = (int)log_size, nr = key_size == 0 ? 10 : 14;
-    static const AesLayout L128 = aes_make_layout(10), L256 = aes_make_layout(14);
-    const AesLayout& lay = nr == 10 ? L128 : L256;
+    static const AesLayout L128 = aes_make_layout(10), L256 = aes_make_layout(14), L128b = aes_make_layout(10, true);
+    const AesLayout& lay = block ? L128b : (nr == 10 ? L128 : L256);
     const int C = lay.n_cols, NL = (int)lay.lk_in.size(), NI = 4 * (NL / 2);
 
     Channel ch;
     ch.mix_root(sp.commitments[0]);
     ch.mix_u64(log_size);
-    ch.mix_u64(key_size);
-    for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(p_nonce + 4 * i));
-    ch.mix_u64(p_counter);
-    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(pth.b + 4 * i));
-    for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(cth.b + 4 * i));
+    if (!block) {
+        ch.mix_u64(key_size);
+        for (int i = 0; i < 3; i++) ch.mix_u64(host::load_le32(p_nonce + 4 * i));
+        ch.mix_u64(p_counter);
+        for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(pth.b + 4 * i));
+        for (int i = 0; i < 8; i++) ch.mix_u64(host::load_le32(cth.b + 4 * i));
+    }
     ch.mix_root(sp.commitments[1]);
     uint32_t zf[8];
     ch.draw_base_felts(zf);
@@ -697,7 +705,7 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
         int s[16], t[16];
         static const int SR[16] = {0, 5, 10, 15, 4, 9, 14, 3, 8, 13, 2, 7, 12, 1, 6, 11};
         const int rk0 = 16, pt0 = 16 + 16 * (nr + 1), ct0 = pt0 + 16;
-        ev.col = ct0 + 16;
+        ev.col = block ? pt0 : ct0 + 16;
         for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(i, rk0 + i);
         for (int rnd = 1; rnd <= nr; rnd++) {
             for (int i = 0; i < 16; i++) s[i] = ev.col++;
@@ -716,8 +724,10 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
             }
             for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(s[i], rk0 + 16 * rnd + i);
         }
-        for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(s[i], pt0 + i);
-        for (int i = 0; i < 16; i++) ev.emit(qsub(ev.ld(s[i]), ev.ld(ct0 + i)));
+        if (!block) {
+            for (int i = 0; i < 16; i++) s[i] = ev.xor_byte(s[i], pt0 + i);
+            for (int i = 0; i < 16; i++) ev.emit(qsub(ev.ld(s[i]), ev.ld(ct0 + i)));
+        }
         // finalize_logup_in_pairs
         const auto& inter = sampled[2];
         QM31 prev_col = qzero();
@@ -747,4 +757,12 @@ std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce
         }
         return ev.acc;
     });
+}
+
+std::string verify_aes_ctr(const uint8_t* proof, size_t len, const uint8_t nonce[12], uint32_t counter, const uint8_t* plaintext,
+                           size_t pt_len, const uint8_t* ciphertext, size_t ct_len, int* key_size_out) {
+    return verify_aes_impl(proof, len, nonce, counter, plaintext, pt_len, ciphertext, ct_len, key_size_out, false);
+}
+std::string verify_aes128_block(const uint8_t* proof, size_t len) {
+    return verify_aes_impl(proof, len, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, true);
 }
